@@ -1,0 +1,182 @@
+/*
+ * lvg_ops.h -- C ABI of liblvg_ops.so, the sm_100a operator library behind the
+ * torch_utils.ops drop-in (bias_act, upfirdn2d, filtered_lrelu, conv2d, fma).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in _host;
+ *   - the caller owns all buffers (outputs are allocated by the host side,
+ *     e.g. torch.empty) -- the library never allocates device memory that
+ *     outlives a call, and keeps no mutable global device state, so calls are
+ *     safe from any thread on any stream;
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream);
+ *     calls only enqueue work and never synchronise;
+ *   - strides are in ELEMENTS, shapes are [N, C, H, W] order;
+ *   - return 0 = launched, LVG_UNSUPPORTED (-1) = no kernel for this
+ *     configuration (the caller may compose other entry points, mirroring the
+ *     reference plugin's return code, filtered_lrelu.cpp:53-57), >0 = argument
+ *     or CUDA error; lvg_last_error() then describes it (thread local).
+ *
+ * Each entry point names the reference plugin function it replaces
+ * (paths relative to the NVlabs/long-video-gan tree).
+ */
+#ifndef LVG_OPS_H_
+#define LVG_OPS_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LVG_ABI_VERSION 1
+
+#define LVG_OK            0
+#define LVG_UNSUPPORTED (-1)
+#define LVG_ERR_ARG       1
+#define LVG_ERR_CUDA      2
+
+/* element types */
+#define LVG_F32 0
+#define LVG_F16 1
+#define LVG_F64 2
+
+/* activation codes: same numbering as `cuda_idx` in torch_utils/ops/bias_act.py:21-31 */
+#define LVG_ACT_LINEAR   1
+#define LVG_ACT_RELU     2
+#define LVG_ACT_LRELU    3
+#define LVG_ACT_TANH     4
+#define LVG_ACT_SIGMOID  5
+#define LVG_ACT_ELU      6
+#define LVG_ACT_SELU     7
+#define LVG_ACT_SOFTPLUS 8
+#define LVG_ACT_SWISH    9
+
+int         lvg_abi_version(void);
+const char* lvg_last_error(void);
+/* compile-time facts about the build: "sm_100a;..." */
+const char* lvg_build_info(void);
+
+/*
+ * bias_act -- replaces bias_act_plugin.bias_act (torch_utils/ops/bias_act.cpp:32-90,
+ * kernel bias_act.cu:23-147).
+ *   grad = 0: y = clamp(act(x + b) * gain)
+ *   grad = 1: y = x * gain * act'(.)   , zero where yref is outside (-clamp, clamp)
+ *   grad = 2: y = x * dy * gain * act''(.), same masking
+ * x, xref, yref, dy, y are dense buffers of n elements in one common layout;
+ * the bias of element i is b[(i / step_b) % size_b]. NULL = operand absent.
+ * clamp < 0 disables clamping.
+ */
+int lvg_bias_act(const void* x, const void* b, const void* xref, const void* yref,
+                 const void* dy, void* y, int dtype, int64_t n, int64_t size_b,
+                 int64_t step_b, int grad, int act, float alpha, float gain,
+                 float clamp, void* stream);
+
+/*
+ * bias_act backward with the bias-gradient reduction fused in: as grad = 1
+ * above, and additionally db[c] += sum of y over all elements whose bias index
+ * is c (fp32 accumulators, db_f32 has size_b floats and must be zeroed by the
+ * caller). Saves the extra read of dx that `dx.sum(...)` costs
+ * (torch_utils/ops/bias_act.py:169-170).
+ */
+int lvg_bias_act_grad_db(const void* dy_in, const void* b, const void* xref,
+                         const void* yref, void* dx, float* db_f32, int dtype,
+                         int64_t n, int64_t size_b, int64_t step_b, int act,
+                         float alpha, float gain, float clamp, void* stream);
+
+/*
+ * upfirdn2d -- replaces upfirdn2d_plugin.upfirdn2d (torch_utils/ops/upfirdn2d.cpp:16-98,
+ * kernels upfirdn2d.cu:29-200). Full 2-D filter f[fh][fw] (float32, element
+ * strides f_stride_y / f_stride_x). Output size per axis:
+ *   out = (in * up + pad0 + pad1 - ftaps + down) / down      (upfirdn2d.cpp:35-36)
+ * so y_shape carries the caller's choice of pad1. Any x / y strides.
+ */
+int lvg_upfirdn2d(const void* x, const float* f, void* y, int dtype,
+                  const int64_t x_shape[4], const int64_t x_stride[4],
+                  const int64_t y_shape[4], const int64_t y_stride[4],
+                  int fw, int fh, int64_t f_stride_x, int64_t f_stride_y,
+                  int upx, int upy, int downx, int downy, int padx0, int pady0,
+                  int flip, float gain, void* stream);
+
+/*
+ * Separable upfirdn2d in ONE launch: horizontal pass with fx[fw], vertical
+ * pass with fy[fh], the intermediate stays in shared memory. Replaces the two
+ * chained plugin calls of torch_utils/ops/upfirdn2d.py:244-245 (and their HBM
+ * round trip). fx == NULL or fy == NULL means "no filter along that axis"
+ * (1 tap of weight 1). `gain` is applied once.
+ * Returns LVG_UNSUPPORTED for shapes the tiled kernel does not cover
+ * (caller then issues two lvg_upfirdn2d calls).
+ */
+int lvg_upfirdn2d_sep(const void* x, const float* fx, const float* fy, void* y,
+                      int dtype, const int64_t x_shape[4], const int64_t x_stride[4],
+                      const int64_t y_shape[4], const int64_t y_stride[4],
+                      int fw, int fh, int upx, int upy, int downx, int downy,
+                      int padx0, int pady0, int flip, float gain, void* stream);
+
+/*
+ * filtered_lrelu -- replaces filtered_lrelu_plugin.filtered_lrelu
+ * (torch_utils/ops/filtered_lrelu.cpp:16-209, kernel filtered_lrelu.cu:139-1099):
+ *   y = downfir( clamp( lrelu( upfir(x + b) * up^2 * gain ) ) )
+ * fu / fd: float32, separable when f?_h == 0 (f?_w taps used on both axes),
+ * else full [f?_h][f?_w] row-major. Sign tensor: uint8 [N][C][s_h][s_wbytes],
+ * 2 bits per up-sampled sample, 4 samples per byte along x (bit0 = negative,
+ * bit1 = clamped; filtered_lrelu.cu:494-519). Exactly one of the modes:
+ *   write_signs != 0 : so written (forward with gradients)
+ *   si != NULL       : signs read at offset (sx, sy) instead of evaluating lrelu/clamp (backward)
+ *   neither          : plain forward
+ * Returns LVG_UNSUPPORTED when no fused kernel covers (up, down, filter sizes).
+ */
+int lvg_filtered_lrelu(const void* x, const float* fu, const float* fd, const void* b,
+                       const uint8_t* si, void* y, uint8_t* so, int dtype,
+                       const int64_t x_shape[4], const int64_t x_stride[4],
+                       const int64_t y_shape[4], const int64_t y_stride[4],
+                       int fu_w, int fu_h, int fd_w, int fd_h, int up, int down,
+                       int px0, int py0, int s_h, int s_wbytes, int sx, int sy,
+                       float gain, float slope, float clamp, int flip,
+                       int write_signs, void* stream);
+
+/* 0 if lvg_filtered_lrelu has a fused kernel for this configuration, else LVG_UNSUPPORTED */
+int lvg_filtered_lrelu_supported(int dtype, int fu_w, int fu_h, int fd_w, int fd_h,
+                                 int up, int down);
+
+/*
+ * In-place gain * lrelu * clamp with sign write / read -- replaces
+ * filtered_lrelu_plugin.filtered_lrelu_act_ (filtered_lrelu.cpp:213-290,
+ * kernel filtered_lrelu.cu:1105-1211). x is modified in place.
+ */
+int lvg_filtered_lrelu_act(void* x, const uint8_t* si, uint8_t* so, int dtype,
+                           const int64_t x_shape[4], const int64_t x_stride[4],
+                           int s_h, int s_wbytes, int sx, int sy, float gain,
+                           float slope, float clamp, int write_signs, void* stream);
+
+/*
+ * fma -- out = a * b + c with numpy-style broadcasting (torch_utils/ops/fma.py:15-25).
+ * All operands are described on the common broadcast shape (rank <= 6):
+ * a stride of 0 marks a broadcast dimension. out is dense in `shape` order.
+ */
+int lvg_fma(const void* a, const void* b, const void* c, void* out, int dtype,
+            int rank, const int64_t shape[6], const int64_t a_stride[6],
+            const int64_t b_stride[6], const int64_t c_stride[6], void* stream);
+
+/*
+ * Grouped 2-D convolution (cross-correlation, like torch.nn.functional.conv2d)
+ * on tcgen05 tensor cores -- the kernel behind conv2d_gradfix.conv2d
+ * (torch_utils/ops/conv2d_gradfix.py:37-40) for the per-sample-weight
+ * "modulated" convolutions (model/generator_sres.py:63-65) and the
+ * discriminator convolutions (conv2d_resample.py:29-41).
+ *   x [N][G*Cin][H][W]  w [G*Cout][Cin][kh][kw]  y [N][G*Cout][Ho][Wo]
+ * NCHW-contiguous operands, fp16 storage with fp32 accumulation, or fp32
+ * storage computed as split-tf32 (3 MMAs per product, fp32-level accuracy).
+ * Returns LVG_UNSUPPORTED outside the covered envelope.
+ */
+int lvg_conv2d_fprop(const void* x, const void* w, void* y, int dtype,
+                     int n, int groups, int cin, int cout, int h, int wd,
+                     int kh, int kw, int stride, int pad_h, int pad_w,
+                     void* workspace, int64_t workspace_bytes, void* stream);
+int64_t lvg_conv2d_fprop_workspace(int dtype, int n, int groups, int cin, int cout,
+                                   int h, int wd, int kh, int kw, int stride,
+                                   int pad_h, int pad_w);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LVG_OPS_H_ */

@@ -1,0 +1,432 @@
+"""Plugin loader for the sm_100a operator library (replaces the JIT loader).
+
+The reference builds three pybind11 modules at first use
+(``torch_utils/custom_ops.py:59-157`` -> ``torch.utils.cpp_extension.load``).
+Here there is ONE ahead-of-time built C-ABI shared library, ``liblvg_ops.so``
+(``include/lvg_ops.h``), opened with ``ctypes``; ``get_plugin(name)`` returns an
+object exposing the same functions, argument order and return values as the
+reference's pybind module of that name:
+
+    bias_act_plugin.bias_act            bias_act.cpp:32,96
+    upfirdn2d_plugin.upfirdn2d          upfirdn2d.cpp:16,104
+    filtered_lrelu_plugin.filtered_lrelu / filtered_lrelu_act_   filtered_lrelu.cpp:16,213,296
+
+Tensors are allocated here with torch; the library only sees raw device
+pointers, shapes, strides and the current CUDA stream. There is no CPU
+implementation behind these objects: a missing library or a non-CUDA tensor
+raises.
+"""
+import ctypes
+import os
+
+import torch
+
+verbosity = 'brief'  # kept for API compatibility ('none' | 'brief' | 'full')
+
+_LIB_NAME = 'liblvg_ops.so'
+_lib = None
+_plugins = {}
+
+_c_void_p = ctypes.c_void_p
+_c_int = ctypes.c_int
+_c_i64 = ctypes.c_int64
+_c_float = ctypes.c_float
+_I64x4 = ctypes.c_int64 * 4
+_I64x6 = ctypes.c_int64 * 6
+
+_DTYPE_CODE = {torch.float32: 0, torch.float16: 1, torch.float64: 2}
+
+# every exported symbol of include/lvg_ops.h with its C signature
+_SIGNATURES = {
+    'lvg_abi_version': (_c_int, []),
+    'lvg_last_error': (ctypes.c_char_p, []),
+    'lvg_build_info': (ctypes.c_char_p, []),
+    'lvg_bias_act': (_c_int, [_c_void_p] * 6 + [_c_int, _c_i64, _c_i64, _c_i64, _c_int, _c_int, _c_float, _c_float, _c_float, _c_void_p]),
+    'lvg_bias_act_grad_db': (_c_int, [_c_void_p] * 6 + [_c_int, _c_i64, _c_i64, _c_i64, _c_int, _c_float, _c_float, _c_float, _c_void_p]),
+    'lvg_upfirdn2d': (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _I64x4, _I64x4, _I64x4, _I64x4, _c_int, _c_int, _c_i64, _c_i64]
+                      + [_c_int] * 7 + [_c_float, _c_void_p]),
+    'lvg_upfirdn2d_sep': (_c_int, [_c_void_p] * 4 + [_c_int, _I64x4, _I64x4, _I64x4, _I64x4] + [_c_int] * 9 + [_c_float, _c_void_p]),
+    'lvg_filtered_lrelu': (_c_int, [_c_void_p] * 7 + [_c_int, _I64x4, _I64x4, _I64x4, _I64x4] + [_c_int] * 12
+                           + [_c_float, _c_float, _c_float, _c_int, _c_int, _c_void_p]),
+    'lvg_filtered_lrelu_supported': (_c_int, [_c_int] * 7),
+    'lvg_filtered_lrelu_act': (_c_int, [_c_void_p] * 3 + [_c_int, _I64x4, _I64x4] + [_c_int] * 4 + [_c_float] * 3 + [_c_int, _c_void_p]),
+    'lvg_fma': (_c_int, [_c_void_p] * 4 + [_c_int, _c_int, _I64x6, _I64x6, _I64x6, _I64x6, _c_void_p]),
+    'lvg_conv2d_fprop': (_c_int, [_c_void_p] * 3 + [_c_int] * 12 + [_c_void_p, _c_i64, _c_void_p]),
+    'lvg_conv2d_fprop_workspace': (_c_i64, [_c_int] * 12),
+}
+
+LVG_UNSUPPORTED = -1
+
+
+def library_path():
+    """Absolute path where liblvg_ops.so is expected (next to this package)."""
+    return os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), _LIB_NAME)
+
+
+def load_library():
+    """Open liblvg_ops.so once and declare every entry point. Raises if it is missing."""
+    global _lib
+    if _lib is None:
+        path = os.environ.get('LVG_OPS_LIBRARY', library_path())
+        if not os.path.isfile(path):
+            raise RuntimeError(
+                f'{_LIB_NAME} not found at {path}: build it with `python -c "import __graft_entry__ as g; g.build()"` '
+                f'or `make -C long-video-gan_b200/csrc`. There is no fallback for CUDA tensors.')
+        lib = ctypes.CDLL(path)
+        for name, (restype, argtypes) in _SIGNATURES.items():
+            fn = getattr(lib, name)  # AttributeError here = header / library mismatch
+            fn.restype = restype
+            fn.argtypes = argtypes
+        if lib.lvg_abi_version() != 1:
+            raise RuntimeError(f'{path}: unexpected ABI version {lib.lvg_abi_version()}')
+        _lib = lib
+    return _lib
+
+
+def exported_symbols():
+    return sorted(_SIGNATURES)
+
+
+def _check(rc, what):
+    if rc > 0:
+        raise RuntimeError(f'{what}: {_lib.lvg_last_error().decode()}')
+    return rc
+
+
+def _ptr(t):
+    """Device pointer of a tensor, or NULL for None / empty ("absent" in the reference API)."""
+    if t is None or t.numel() == 0:
+        return None
+    return t.data_ptr()
+
+
+def _stream(t):
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _i4(seq):
+    return _I64x4(*[int(v) for v in seq])
+
+
+def _dtype_code(t, what):
+    try:
+        return _DTYPE_CODE[t.dtype]
+    except KeyError:
+        raise RuntimeError(f'{what}: unsupported dtype {t.dtype}') from None
+
+
+def _absent(t):
+    return t is None or t.numel() == 0
+
+
+def _same_layout(a, b):
+    return a.shape == b.shape and a.stride() == b.stride()
+
+
+def _is_dense(x):
+    dims = sorted((d for d in range(x.ndim) if x.shape[d] != 1), key=lambda d: x.stride(d))
+    expect = 1
+    for d in dims:
+        if x.stride(d) != expect:
+            return False
+        expect *= x.shape[d]
+    return True
+
+
+class _DeviceGuard:
+    """Makes t's device current for the duration of a launch (like OptionalCUDAGuard)."""
+
+    def __init__(self, t):
+        self.idx = t.device.index
+        self.prev = None
+
+    def __enter__(self):
+        cur = torch.cuda.current_device()
+        if self.idx is not None and self.idx != cur:
+            self.prev = cur
+            torch.cuda.set_device(self.idx)
+
+    def __exit__(self, *exc):
+        if self.prev is not None:
+            torch.cuda.set_device(self.prev)
+
+
+# ----------------------------------------------------------------------------
+
+class BiasActPlugin:
+    """``bias_act_plugin`` (bias_act.cpp:32-96)."""
+
+    def __init__(self, lib):
+        self._lib = lib
+
+    def bias_act(self, x, b, xref, yref, dy, grad, dim, act, alpha, gain, clamp):
+        if not x.is_cuda:
+            raise RuntimeError('x must reside on CUDA device')
+        code = _dtype_code(x, 'bias_act')
+        for name, t in (('xref', xref), ('yref', yref), ('dy', dy)):
+            if not _absent(t) and not (t.dtype == x.dtype and t.device == x.device and _same_layout(t, x)):
+                raise RuntimeError(f'{name} must have the same shape, dtype, device and layout as x')
+        if grad < 0:
+            raise RuntimeError('grad must be non-negative')
+        size_b, step_b = 1, 1
+        if not _absent(b):
+            if b.dtype != x.dtype or b.device != x.device:
+                raise RuntimeError('b must have the same dtype and device as x')
+            if b.ndim != 1:
+                raise RuntimeError('b must have rank 1')
+            if not (0 <= dim < x.ndim):
+                raise RuntimeError('dim is out of bounds')
+            if b.numel() != x.shape[dim]:
+                raise RuntimeError('b has wrong number of elements')
+            if not b.is_contiguous():
+                raise RuntimeError('b must be contiguous')
+            size_b, step_b = b.numel(), x.stride(dim)
+        if not _is_dense(x):
+            raise RuntimeError('x must be non-overlapping and dense')
+        y = torch.empty_like(x)
+        if not _same_layout(y, x):
+            raise RuntimeError('y must have the same layout as x')
+        with _DeviceGuard(x):
+            _check(self._lib.lvg_bias_act(_ptr(x), _ptr(b), _ptr(xref), _ptr(yref), _ptr(dy), _ptr(y), code,
+                                          x.numel(), size_b, max(step_b, 1), int(grad), int(act),
+                                          float(alpha), float(gain), float(clamp), _stream(x)), 'bias_act')
+        return y
+
+    def bias_act_grad_db(self, dy, b, xref, yref, dim, act, alpha, gain, clamp):
+        """Backward pass with the bias-gradient reduction fused in. Returns (dx, db) with db in dy.dtype."""
+        if not dy.is_cuda:
+            raise RuntimeError('dy must reside on CUDA device')
+        code = _dtype_code(dy, 'bias_act_grad_db')
+        if not _is_dense(dy):
+            raise RuntimeError('dy must be non-overlapping and dense')
+        for name, t in (('xref', xref), ('yref', yref)):
+            if not _absent(t) and not (t.dtype == dy.dtype and _same_layout(t, dy)):
+                raise RuntimeError(f'{name} must have the same shape, dtype and layout as dy')
+        size_b, step_b = dy.shape[dim], max(dy.stride(dim), 1)
+        dx = torch.empty_like(dy)
+        db = torch.zeros([size_b], dtype=torch.float32, device=dy.device)
+        with _DeviceGuard(dy):
+            _check(self._lib.lvg_bias_act_grad_db(_ptr(dy), _ptr(b), _ptr(xref), _ptr(yref), _ptr(dx), _ptr(db), code,
+                                                  dy.numel(), size_b, step_b, int(act), float(alpha), float(gain),
+                                                  float(clamp), _stream(dy)), 'bias_act_grad_db')
+        return dx, db.to(dy.dtype)
+
+
+class Upfirdn2dPlugin:
+    """``upfirdn2d_plugin`` (upfirdn2d.cpp:16-104), plus the single-launch separable entry point."""
+
+    def __init__(self, lib):
+        self._lib = lib
+
+    @staticmethod
+    def _out_size(x, fw, fh, upx, upy, downx, downy, padx0, padx1, pady0, pady1):
+        ow = (x.shape[3] * upx + padx0 + padx1 - fw + downx) // downx
+        oh = (x.shape[2] * upy + pady0 + pady1 - fh + downy) // downy
+        if ow < 1 or oh < 1:
+            raise RuntimeError('output must be at least 1x1')
+        return oh, ow
+
+    @staticmethod
+    def _alloc_like(x, oh, ow):
+        fmt = torch.channels_last if (x.shape[1] > 1 and x.stride(1) == 1) else torch.contiguous_format
+        return torch.empty([x.shape[0], x.shape[1], oh, ow], dtype=x.dtype, device=x.device, memory_format=fmt)
+
+    @staticmethod
+    def _validate(x, f):
+        if not x.is_cuda:
+            raise RuntimeError('x must reside on CUDA device')
+        if f.device != x.device:
+            raise RuntimeError('f must reside on the same device as x')
+        if f.dtype != torch.float32:
+            raise RuntimeError('f must be float32')
+        if x.numel() == 0:
+            raise RuntimeError('x has zero size')
+        if f.numel() == 0:
+            raise RuntimeError('f has zero size')
+        if x.ndim != 4:
+            raise RuntimeError('x must be rank 4')
+
+    def upfirdn2d(self, x, f, upx, upy, downx, downy, padx0, padx1, pady0, pady1, flip, gain):
+        self._validate(x, f)
+        if f.ndim != 2:
+            raise RuntimeError('f must be rank 2')
+        if upx < 1 or upy < 1:
+            raise RuntimeError('upsampling factor must be at least 1')
+        if downx < 1 or downy < 1:
+            raise RuntimeError('downsampling factor must be at least 1')
+        code = _dtype_code(x, 'upfirdn2d')
+        fh, fw = f.shape
+        oh, ow = self._out_size(x, fw, fh, upx, upy, downx, downy, padx0, padx1, pady0, pady1)
+        y = self._alloc_like(x, oh, ow)
+        with _DeviceGuard(x):
+            _check(self._lib.lvg_upfirdn2d(_ptr(x), _ptr(f), _ptr(y), code, _i4(x.shape), _i4(x.stride()), _i4(y.shape),
+                                           _i4(y.stride()), fw, fh, f.stride(1), f.stride(0), upx, upy, downx, downy,
+                                           padx0, pady0, int(bool(flip)), float(gain), _stream(x)), 'upfirdn2d')
+        return y
+
+    def upfirdn2d_sep(self, x, fx, fy, upx, upy, downx, downy, padx0, padx1, pady0, pady1, flip, gain):
+        """Both passes of a separable filter in one launch (fx along W, fy along H; None = no filter
+        on that axis). Returns None when the tiled kernel does not cover the configuration."""
+        f_any = fx if fx is not None else fy
+        self._validate(x, f_any)
+        for f in (fx, fy):
+            if f is not None and (f.ndim != 1 or not f.is_contiguous() or f.dtype != torch.float32):
+                raise RuntimeError('separable filters must be contiguous float32 vectors')
+        code = _dtype_code(x, 'upfirdn2d_sep')
+        fw = fx.numel() if fx is not None else 1
+        fh = fy.numel() if fy is not None else 1
+        oh, ow = self._out_size(x, fw, fh, upx, upy, downx, downy, padx0, padx1, pady0, pady1)
+        y = self._alloc_like(x, oh, ow)
+        with _DeviceGuard(x):
+            rc = _check(self._lib.lvg_upfirdn2d_sep(_ptr(x), _ptr(fx), _ptr(fy), _ptr(y), code, _i4(x.shape), _i4(x.stride()),
+                                                    _i4(y.shape), _i4(y.stride()), fw, fh, upx, upy, downx, downy,
+                                                    padx0, pady0, int(bool(flip)), float(gain), _stream(x)), 'upfirdn2d_sep')
+        return None if rc == LVG_UNSUPPORTED else y
+
+
+class FilteredLReluPlugin:
+    """``filtered_lrelu_plugin`` (filtered_lrelu.cpp:16-297)."""
+
+    def __init__(self, lib):
+        self._lib = lib
+
+    def filtered_lrelu(self, x, fu, fd, b, si, up, down, px0, px1, py0, py1, sx, sy, gain, slope, clamp, flip_filters, writeSigns):
+        if not x.is_cuda:
+            raise RuntimeError('x must reside on CUDA device')
+        if not (fu.device == x.device and fd.device == x.device and b.device == x.device):
+            raise RuntimeError('all input tensors must reside on the same device')
+        if fu.dtype != torch.float32 or fd.dtype != torch.float32:
+            raise RuntimeError('fu and fd must be float32')
+        if b.dtype != x.dtype:
+            raise RuntimeError('x and b must have the same dtype')
+        if x.dtype not in (torch.float16, torch.float32):
+            raise RuntimeError('x and b must be float16 or float32')
+        if x.ndim != 4:
+            raise RuntimeError('x must be rank 4')
+        if x.numel() == 0:
+            raise RuntimeError('x is empty')
+        if fu.ndim not in (1, 2) or fd.ndim not in (1, 2):
+            raise RuntimeError('fu and fd must be rank 1 or 2')
+        if fu.numel() == 0 or fd.numel() == 0:
+            raise RuntimeError('fu and fd must not be empty')
+        if b.ndim != 1 or b.shape[0] != x.shape[1]:
+            raise RuntimeError('b must be a vector with the same number of channels as x')
+        if up < 1 or down < 1:
+            raise RuntimeError('up and down must be at least 1')
+        code = _dtype_code(x, 'filtered_lrelu')
+
+        fu_w, fu_h = fu.shape[-1], (fu.shape[0] if fu.ndim == 2 else 0)   # height 0 marks a separable filter
+        fd_w, fd_h = fd.shape[-1], (fd.shape[0] if fd.ndim == 2 else 0)
+        if self._lib.lvg_filtered_lrelu_supported(code, fu_w, fu_h, fd_w, fd_h, up, down) != 0:
+            return None, None, -1   # same contract as the reference: caller runs the generic path
+
+        fut_w, fut_h = fu.shape[-1] - 1, fu.shape[0] - 1
+        fdt_w, fdt_h = fd.shape[-1] - 1, fd.shape[0] - 1
+        cw = x.shape[3] * up + (px0 + px1) - fut_w      # logical size of the up-sampled buffer
+        ch = x.shape[2] * up + (py0 + py1) - fut_h
+        if not (cw > fdt_w and ch > fdt_h):
+            raise RuntimeError('upsampled buffer must be at least the size of downsampling filter')
+        yw = (cw - fdt_w + (down - 1)) // down
+        yh = (ch - fdt_h + (down - 1)) // down
+        if yw < 1 or yh < 1:
+            raise RuntimeError('output must be at least 1x1')
+        fmt = torch.channels_last if (x.shape[1] > 1 and x.stride(1) == 1) else torch.contiguous_format
+        y = torch.empty([x.shape[0], x.shape[1], yh, yw], dtype=x.dtype, device=x.device, memory_format=fmt)
+
+        so = None
+        s = si if not _absent(si) else None
+        read_signs = s is not None
+        if writeSigns:
+            if read_signs:
+                raise RuntimeError('cannot read and write signs in the same call')
+            sw_active = yw * down - (down - 1) + fdt_w
+            sh = yh * down - (down - 1) + fdt_h
+            sw = (sw_active + 15) & ~15
+            s = so = torch.empty([x.shape[0], x.shape[1], sh, sw >> 2], dtype=torch.uint8, device=x.device)
+        if s is not None:
+            if not (s.is_contiguous() and s.dtype == torch.uint8 and s.device == x.device and s.ndim == 4
+                    and s.shape[0] == x.shape[0] and s.shape[1] == x.shape[1]):
+                raise RuntimeError('signs must be a contiguous uint8 [N, C, H, W/4] tensor on the same device as x')
+        s_h, s_wb = (s.shape[2], s.shape[3]) if s is not None else (0, 0)
+        fu_c, fd_c, b_c = fu.contiguous(), fd.contiguous(), b.contiguous()
+        with _DeviceGuard(x):
+            rc = _check(self._lib.lvg_filtered_lrelu(
+                _ptr(x), _ptr(fu_c), _ptr(fd_c), _ptr(b_c), _ptr(s) if read_signs else None, _ptr(y),
+                _ptr(so) if writeSigns else None, code, _i4(x.shape), _i4(x.stride()), _i4(y.shape), _i4(y.stride()),
+                fu_w, fu_h, fd_w, fd_h, up, down, px0, py0, s_h, s_wb, sx, sy, float(gain), float(slope),
+                float(clamp), int(bool(flip_filters)), int(bool(writeSigns)), _stream(x)), 'filtered_lrelu')
+        if rc == LVG_UNSUPPORTED:
+            return None, None, -1
+        return y, so, 0
+
+    def filtered_lrelu_act_(self, x, si, sx, sy, gain, slope, clamp, writeSigns):
+        if not x.is_cuda:
+            raise RuntimeError('x must reside on CUDA device')
+        if x.ndim != 4:
+            raise RuntimeError('x must be rank 4')
+        if x.numel() == 0:
+            raise RuntimeError('x is empty')
+        code = _dtype_code(x, 'filtered_lrelu_act_')
+        so = None
+        s = si if not _absent(si) else None
+        read_signs = s is not None
+        if writeSigns:
+            sw = (x.shape[3] + 15) & ~15
+            s = so = torch.empty([x.shape[0], x.shape[1], x.shape[2], sw >> 2], dtype=torch.uint8, device=x.device)
+        if s is not None:
+            if not (s.is_contiguous() and s.dtype == torch.uint8 and s.device == x.device and s.ndim == 4
+                    and s.shape[0] == x.shape[0] and s.shape[1] == x.shape[1]):
+                raise RuntimeError('signs must be a contiguous uint8 [N, C, H, W/4] tensor on the same device as x')
+        s_h, s_wb = (s.shape[2], s.shape[3]) if s is not None else (0, 0)
+        with _DeviceGuard(x):
+            _check(self._lib.lvg_filtered_lrelu_act(_ptr(x), _ptr(s) if (read_signs and not writeSigns) else None,
+                                                    _ptr(so) if writeSigns else None, code, _i4(x.shape), _i4(x.stride()),
+                                                    s_h, s_wb, sx, sy, float(gain), float(slope), float(clamp),
+                                                    int(bool(writeSigns)), _stream(x)), 'filtered_lrelu_act_')
+        return so
+
+
+class FmaPlugin:
+    """Elementwise a * b + c with broadcasting (no reference plugin: fma.py uses torch.addcmul)."""
+
+    def __init__(self, lib):
+        self._lib = lib
+
+    def fma(self, a, b, c):
+        if not (a.is_cuda and b.device == a.device and c.device == a.device):
+            raise RuntimeError('fma operands must reside on one CUDA device')
+        dtype = torch.result_type(torch.result_type(a, b), c)
+        a, b, c = a.to(dtype), b.to(dtype), c.to(dtype)
+        code = _dtype_code(a, 'fma')
+        shape = torch.broadcast_shapes(a.shape, b.shape, c.shape)
+        if len(shape) > 6:
+            raise RuntimeError('fma supports at most 6 dimensions')
+        out = torch.empty(shape, dtype=dtype, device=a.device)
+        if out.numel() == 0:
+            return out
+        ae, be, ce = a.expand(shape), b.expand(shape), c.expand(shape)
+        pad = [0] * (6 - len(shape))
+        with _DeviceGuard(out):
+            _check(self._lib.lvg_fma(_ptr(ae), _ptr(be), _ptr(ce), _ptr(out), code, len(shape),
+                                     _I64x6(*(list(shape) + [1] * len(pad))), _I64x6(*(list(ae.stride()) + pad)),
+                                     _I64x6(*(list(be.stride()) + pad)), _I64x6(*(list(ce.stride()) + pad)),
+                                     _stream(out)), 'fma')
+        return out
+
+
+_PLUGIN_CLASSES = {
+    'bias_act_plugin': BiasActPlugin,
+    'upfirdn2d_plugin': Upfirdn2dPlugin,
+    'filtered_lrelu_plugin': FilteredLReluPlugin,
+    'fma_plugin': FmaPlugin,
+}
+
+
+def get_plugin(module_name, sources=None, headers=None, source_dir=None, **build_kwargs):
+    """Same call shape as the reference loader (custom_ops.py:59); sources/headers/build flags
+    are accepted and ignored because the library is prebuilt for sm_100a."""
+    if module_name not in _plugins:
+        if module_name not in _PLUGIN_CLASSES:
+            raise RuntimeError(f'unknown plugin "{module_name}"')
+        _plugins[module_name] = _PLUGIN_CLASSES[module_name](load_library())
+    return _plugins[module_name]
