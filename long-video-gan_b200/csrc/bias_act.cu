@@ -163,10 +163,21 @@ __global__ void __launch_bounds__(kThreads, (G == 2 ? 2 : 4)) bias_act_vec_kerne
     const T* __restrict__ pdy = kUseDy ? (const T*)p.dy : nullptr;
     T* __restrict__ py = (T*)p.y;
 
+    // fused bias gradient: per tile, rows (= runs of step_b elements sharing one bias index) are
+    // binned in shared memory relative to the tile's first row, then flushed with one global
+    // atomic per touched bin -- a tile of 1024 packs rarely spans more than a couple of rows
+    constexpr int kBins = 32;
+    __shared__ float s_bins[FUSE_DB ? kBins : 1];
+
     const int64_t tile = (int64_t)kThreads * kUnroll;
     for (int64_t base = (int64_t)blockIdx.x * tile; base < n_pack; base += (int64_t)gridDim.x * tile) {
         Pack<T> vx[kUnroll], vref[kUnroll], vdy[kUnroll];
         const T* __restrict__ pref = kUseX ? pxr : pyr;
+        const int64_t row0 = (FUSE_DB && bmode == BIAS_PER_PACK) ? (base * N) / p.step_b : 0;
+        if (FUSE_DB && bmode == BIAS_PER_PACK) {
+            if (threadIdx.x < kBins) s_bins[threadIdx.x] = 0.f;
+            __syncthreads();
+        }
 #pragma unroll
         for (int u = 0; u < kUnroll; u++) {
             const int64_t pk = base + (int64_t)u * kThreads + threadIdx.x;
@@ -207,21 +218,30 @@ __global__ void __launch_bounds__(kThreads, (G == 2 ? 2 : 4)) bias_act_vec_kerne
                 store_pack(py + e0, out);
 
                 if (FUSE_DB && bmode == BIAS_PER_PACK) {
-                    // warp-level combine when the whole warp sits in one channel (the usual case)
-                    const unsigned full = 0xffffffffu;
+                    const int64_t rel = e0 / p.step_b - row0;
+                    // combine lanes that share a row before touching shared memory
                     const unsigned active = __activemask();
-                    int64_t b0 = __shfl_sync(active, bidx, __ffs(active) - 1);
-                    bool uniform = __all_sync(active, b0 == bidx) && active == full;
-                    if (uniform) {
-                        float s = (float)dbsum;
+                    const unsigned peers = __match_any_sync(active, rel);
+                    float ssum = (float)dbsum;
+                    if (peers == 0xffffffffu) {
 #pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(full, s, o);
-                        if ((threadIdx.x & 31) == 0) atomicAdd(p.db + bidx, s);
+                        for (int o = 16; o > 0; o >>= 1) ssum += __shfl_xor_sync(0xffffffffu, ssum, o);
+                        if ((threadIdx.x & 31) == 0) {
+                            if (rel < kBins) atomicAdd(&s_bins[rel], ssum); else atomicAdd(p.db + bidx, ssum);
+                        }
                     } else {
-                        atomicAdd(p.db + bidx, (float)dbsum);
+                        if (rel < kBins) atomicAdd(&s_bins[rel], ssum); else atomicAdd(p.db + bidx, ssum);
                     }
                 }
             }
+        }
+        if (FUSE_DB && bmode == BIAS_PER_PACK) {
+            __syncthreads();
+            if (threadIdx.x < kBins) {
+                const float v = s_bins[threadIdx.x];
+                if (v != 0.f) atomicAdd(p.db + (row0 + threadIdx.x) % p.size_b, v);
+            }
+            __syncthreads();
         }
     }
 }

@@ -1,0 +1,363 @@
+// Fused filtered leaky ReLU: bias -> up-FIR -> gain*lrelu*clamp (+ 2-bit signs) -> down-FIR
+// in ONE kernel; the up-sampled intermediate (4x / 16x the input) never leaves shared memory.
+//
+// Semantics follow the reference kernel (torch_utils/ops/filtered_lrelu.cu:139-1099) and
+// _filtered_lrelu_ref (filtered_lrelu.py:121-153):
+//   t[U]   = up^2 * sum_s gu[s] * z[U + s - pad0],  z = zero-stuffed (x + b), zero outside the image
+//   v      = t * gain;  write/plain: v < 0 -> v *= slope (code 1); |v| > clamp -> +-clamp (code 2)
+//            read: code = signs[U + sx, V + sy]; bit0 -> v *= slope; bit1 -> v = 0; outside the tensor: unchanged
+//   y[o]   = sum_t gd[t] * v[o*down + t]
+// for separable filters (the only kind the networks use), per axis.
+//
+// One CTA = one TOW x TOH output tile of one (n, c) plane, five stages through two shared-memory
+// buffers (A: input tile, then the activated up-sampled tile; B: x-up-sampled rows, then
+// x-down-sampled rows). All passes are the register-blocked polyphase routines of fir_passes.cuh.
+// Filters arrive as device pointers and are staged per CTA in shared memory -- no global
+// __constant__ state (the reference's c_fbuf, filtered_lrelu.cu:78), so the op is stream-safe.
+// Sign bytes are packed from a per-sample code tile in shared memory; every CTA owns a
+// byte-aligned slab of the sign tensor, so no two CTAs touch the same byte.
+
+#include "common.cuh"
+#include "fir_passes.cuh"
+
+namespace lvg {
+namespace {
+
+enum { SIGN_NONE = 0, SIGN_WRITE = 1, SIGN_READ = 2 };
+
+struct FlParams {
+    const void* x;
+    const float* fu;
+    const float* fd;
+    const void* b;
+    const uint8_t* si;
+    void* y;
+    uint8_t* so;
+    int64_t xs[4], ys[4];
+    int n, c, ih, iw, oh, ow;
+    int px0, py0;
+    int s_h, s_wb, sx, sy;
+    int sw_active;          // write mode: samples at U >= sw_active get code 0
+    int tiles_x, tiles_y;
+    float gain, slope, clamp;
+    int flip;
+};
+
+constexpr int kThreads = 256;
+constexpr int kR = 4;       // outputs (down passes) / input groups (up passes) per thread
+
+template <int UP, int FU, int DOWN, int FD, int TOW, int TOH>
+struct Geom {
+    static constexpr int KU = FU / UP;
+    static constexpr int TUW = (TOW - 1) * DOWN + FD;                 // up-sampled samples the tile consumes
+    static constexpr int TUH = (TOH - 1) * DOWN + FD;
+    static constexpr int NQX = (TUW + UP - 1 + UP - 1) / UP;          // phase-aligned groups incl. alignment slack
+    static constexpr int NQY = (TUH + UP - 1 + UP - 1) / UP;
+    static constexpr int NQXR = fir::round_up(NQX, kR);
+    static constexpr int NQYR = fir::round_up(NQY, kR);
+    static constexpr int TUWA = NQXR * UP;                            // computed (aligned) up-sampled extent
+    static constexpr int TUHA = NQYR * UP;
+    static constexpr int TIW = NQXR + KU;                             // input tile incl. filter support
+    static constexpr int TIH = NQYR + KU;
+    static constexpr int P_IN = fir::odd_pitch(TIW);
+    static constexpr int P_UX = fir::odd_pitch(TUWA);
+    static constexpr int P_UXY = fir::odd_pitch(fir::round_up(TUWA + DOWN * kR, 2));   // slack for the down-x overrun
+    static constexpr int TOWR = fir::round_up(TOW, kR);
+    static constexpr int TOHR = fir::round_up(TOH, kR);
+    static constexpr int P_DX = fir::odd_pitch(TOWR);
+    static constexpr int UXY_ROWS = TUHA + DOWN * kR;                 // slack rows for the down-y overrun
+    static constexpr int A_SIZE = (TIH * P_IN > UXY_ROWS * P_UXY) ? TIH * P_IN : UXY_ROWS * P_UXY;
+    static constexpr int B_SIZE = (TIH * P_UX > UXY_ROWS * P_DX) ? TIH * P_UX : UXY_ROWS * P_DX;
+    static constexpr int CODE_BYTES = fir::round_up(TUHA * TUWA, 16);
+    static constexpr size_t smem_bytes(bool codes) {
+        return (size_t)(A_SIZE + B_SIZE + FU + FD) * sizeof(float) + (codes ? CODE_BYTES : 0);
+    }
+};
+
+template <class T, int UP, int FU, int DOWN, int FD, int TOW, int TOH, int MODE>
+__global__ void __launch_bounds__(kThreads, 2) filtered_lrelu_kernel(FlParams p)
+{
+    typedef Geom<UP, FU, DOWN, FD, TOW, TOH> G;
+    extern __shared__ __align__(16) float smem[];
+    float* bufA = smem;
+    float* bufB = bufA + G::A_SIZE;
+    float* s_fu = bufB + G::B_SIZE;
+    float* s_fd = s_fu + FU;
+    uint8_t* s_code = reinterpret_cast<uint8_t*>(s_fd + FD);
+
+    const int tiles = p.tiles_x * p.tiles_y;
+    const int64_t plane = blockIdx.x / tiles;
+    const int tile = (int)(blockIdx.x - plane * tiles);
+    const int ty = tile / p.tiles_x, tx = tile - ty * p.tiles_x;
+    const int ox0 = tx * TOW, oy0 = ty * TOH;
+    const int cc = (int)(plane % p.c);
+    const int nn = (int)(plane / p.c);
+
+    fir::load_taps(s_fu, p.fu, FU, p.flip != 0);
+    fir::load_taps(s_fd, p.fd, FD, p.flip != 0);
+
+    // geometry of this tile: U0 = first consumed up-sampled sample; the phase-aligned origin is
+    // Ua = U0 - dxo with (Ua - pad0) a multiple of UP; m0 = first input sample of group 0
+    const int U0 = ox0 * DOWN, V0 = oy0 * DOWN;
+    const int m0x = floordiv(U0 - p.px0, UP), m0y = floordiv(V0 - p.py0, UP);
+    const int dxo = (U0 - p.px0) - m0x * UP, dyo = (V0 - p.py0) - m0y * UP;
+    const int tow_e = min(TOW, p.ow - ox0), toh_e = min(TOH, p.oh - oy0);
+    const int tuw_e = (tow_e - 1) * DOWN + FD, tuh_e = (toh_e - 1) * DOWN + FD;
+    const int nqx_e = (tuw_e + dxo + UP - 1) / UP, nqy_e = (tuh_e + dyo + UP - 1) / UP;
+    const int tiw_e = fir::round_up(nqx_e, kR) + G::KU, tih_e = fir::round_up(nqy_e, kR) + G::KU;
+
+    // ---- stage 1: input tile (+ bias inside the image, zero outside) -> A
+    {
+        const T* xp = (const T*)p.x + (int64_t)nn * p.xs[0] + (int64_t)cc * p.xs[1];
+        const float bias = to_acc(((const T*)p.b)[cc]);
+        const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+        for (int iy = warp; iy < tih_e; iy += kThreads / 32) {
+            const int gy = m0y + iy;
+            const bool rowok = gy >= 0 && gy < p.ih;
+            const T* xrow = xp + (int64_t)gy * p.xs[2];
+            for (int ix = lane; ix < tiw_e; ix += 32) {
+                const int gx = m0x + ix;
+                float v = 0.f;
+                if (rowok && gx >= 0 && gx < p.iw) v = to_acc(xrow[(int64_t)gx * p.xs[3]]) + bias;
+                bufA[iy * G::P_IN + ix] = v;
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- stage 2: up-sample along x: A [tih][tiw] -> B [tih][TUWA]
+    fir::up_x<UP, FU, kR, kThreads>(bufA, G::P_IN, bufB, G::P_UX, tih_e, nqx_e, s_fu);
+    __syncthreads();
+
+    // ---- stage 3: up-sample along y, scale, activation, signs: B -> A [TUHA][TUWA]
+    {
+        const float scale = (float)(UP * UP) * p.gain;
+        const float slope = p.slope, clamp = p.clamp;
+        const int Uax = U0 - dxo, Vay = V0 - dyo;          // global up-sampled coords of aligned sample (0, 0)
+        const uint8_t* sgn = (MODE == SIGN_READ) ? p.si + plane * (int64_t)p.s_h * p.s_wb : nullptr;
+        const int s_w = p.s_wb * 4;
+        const int cols = nqx_e * UP;
+        fir::up_y<UP, FU, kR, kThreads>(bufB, G::P_UX, cols, nqy_e, s_fu,
+            [&](int row, int col, float acc) {
+                float v = acc * scale;
+                if (MODE == SIGN_READ) {
+                    const int qx = Uax + col + p.sx, qy = Vay + row + p.sy;
+                    if ((unsigned)qx < (unsigned)s_w && (unsigned)qy < (unsigned)p.s_h) {
+                        const unsigned s = sgn[(int64_t)qy * p.s_wb + (qx >> 2)] >> ((qx & 3) << 1);
+                        if (s & 1u) v *= slope;
+                        if (s & 2u) v = 0.f;
+                    }
+                } else {
+                    unsigned code = 0;
+                    if (v < 0.f) { v *= slope; code = 1; }
+                    if (fabsf(v) > clamp) { v = v < 0.f ? -clamp : clamp; code = 2; }
+                    if (MODE == SIGN_WRITE) s_code[row * G::TUWA + col] = (uint8_t)code;
+                }
+                bufA[row * G::P_UXY + col] = v;
+            });
+    }
+    __syncthreads();
+
+    // ---- stage 3b: pack and store this CTA's slab of the sign tensor
+    if (MODE == SIGN_WRITE) {
+        const bool lastx = (tx == p.tiles_x - 1), lasty = (ty == p.tiles_y - 1);
+        const int b0 = U0 >> 2;                                              // TOW*DOWN is a multiple of 4
+        const int b1 = lastx ? p.s_wb : min(p.s_wb, (U0 + TOW * DOWN) >> 2);
+        const int r0 = V0;
+        const int r1 = lasty ? p.s_h : min(p.s_h, V0 + TOH * DOWN);
+        const int nb = b1 - b0, nr = r1 - r0;
+        uint8_t* dst = p.so + plane * (int64_t)p.s_h * p.s_wb;
+        const int cols = nqx_e * UP, rows = nqy_e * UP;
+        for (int i = threadIdx.x; i < nb * nr; i += kThreads) {
+            const int rr = i / nb, bb = i - rr * nb;
+            const int row = rr + dyo;                                        // local aligned row of global row r0 + rr
+            unsigned byte = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int U = (b0 + bb) * 4 + k;
+                const int col = U - (U0 - dxo);
+                if (U < p.sw_active && col < cols && row < rows)
+                    byte |= (unsigned)s_code[row * G::TUWA + col] << (2 * k);
+            }
+            dst[(int64_t)(r0 + rr) * p.s_wb + b0 + bb] = (uint8_t)byte;
+        }
+    }
+
+    // ---- stage 4: down-sample along x: A [tuh][.] (from column dxo, rows from dyo) -> B [tuh][TOW]
+    fir::down_x<DOWN, FD, kR, kThreads>(bufA + dyo * G::P_UXY, G::P_UXY, dxo, bufB, G::P_DX, tuh_e, tow_e, s_fd);
+    __syncthreads();
+
+    // ---- stage 5: down-sample along y and store
+    {
+        T* yp = (T*)p.y + (int64_t)nn * p.ys[0] + (int64_t)cc * p.ys[1];
+        fir::down_y<DOWN, FD, kR, kThreads>(bufB, G::P_DX, 0, tow_e, toh_e, s_fd,
+            [&](int o, int col, float acc) {
+                yp[(int64_t)(oy0 + o) * p.ys[2] + (int64_t)(ox0 + col) * p.ys[3]] = from_acc<T>(acc);
+            });
+    }
+}
+
+// up = down = 1 with 1x1 filters (the ToRGB layer): an element-wise op; one thread = one sign byte.
+template <class T, int MODE>
+__global__ void __launch_bounds__(256) filtered_lrelu_1x1_kernel(FlParams p, int64_t total, int wq)
+{
+    const float fu = p.fu[0], fd = p.fd[0];
+    const float scale = fu * p.gain;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int q = (int)(idx % wq);
+        int64_t r = idx / wq;
+        const int yy = (int)(r % p.oh);
+        const int64_t plane = r / p.oh;
+        const int cc = (int)(plane % p.c), nn = (int)(plane / p.c);
+        const float bias = to_acc(((const T*)p.b)[cc]);
+        // output pixel (ox, oy) reads input pixel (ox - px0, oy - py0)
+        const T* xp = (const T*)p.x + (int64_t)nn * p.xs[0] + (int64_t)cc * p.xs[1];
+        T* yp = (T*)p.y + (int64_t)nn * p.ys[0] + (int64_t)cc * p.ys[1] + (int64_t)yy * p.ys[2];
+        const int iy = yy - p.py0;
+        unsigned byte = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int ox = q * 4 + k;
+            if (ox >= p.ow) continue;
+            const int ix = ox - p.px0;
+            float v = 0.f;
+            if (ix >= 0 && ix < p.iw && iy >= 0 && iy < p.ih) v = to_acc(xp[(int64_t)iy * p.xs[2] + (int64_t)ix * p.xs[3]]) + bias;
+            v *= scale;
+            if (MODE == SIGN_READ) {
+                const int qx = ox + p.sx, qy = yy + p.sy;
+                if ((unsigned)qx < (unsigned)(p.s_wb * 4) && (unsigned)qy < (unsigned)p.s_h) {
+                    const unsigned s = p.si[(plane * p.s_h + qy) * p.s_wb + (qx >> 2)] >> ((qx & 3) << 1);
+                    if (s & 1u) v *= p.slope;
+                    if (s & 2u) v = 0.f;
+                }
+            } else {
+                unsigned code = 0;
+                if (v < 0.f) { v *= p.slope; code = 1; }
+                if (fabsf(v) > p.clamp) { v = v < 0.f ? -p.clamp : p.clamp; code = 2; }
+                byte |= code << (2 * k);
+            }
+            yp[(int64_t)ox * p.ys[3]] = from_acc<T>(v * fd);
+        }
+        if (MODE == SIGN_WRITE && q < p.s_wb && yy < p.s_h)
+            p.so[(plane * p.s_h + yy) * p.s_wb + q] = (uint8_t)byte;
+    }
+}
+
+template <class T, int UP, int FU, int DOWN, int FD, int TOW, int TOH>
+int launch_cfg(FlParams& p, int mode, cudaStream_t s)
+{
+    typedef Geom<UP, FU, DOWN, FD, TOW, TOH> G;
+    static_assert((TOW * DOWN) % 4 == 0, "sign slabs must be byte aligned");
+    p.tiles_x = (p.ow + TOW - 1) / TOW;
+    p.tiles_y = (p.oh + TOH - 1) / TOH;
+    const int64_t blocks = (int64_t)p.n * p.c * p.tiles_x * p.tiles_y;
+    LVG_REQUIRE(blocks <= INT32_MAX, "filtered_lrelu: grid too large");
+    const size_t smem = G::smem_bytes(mode == SIGN_WRITE);
+    void (*k)(FlParams) = nullptr;
+    if (mode == SIGN_WRITE)     k = filtered_lrelu_kernel<T, UP, FU, DOWN, FD, TOW, TOH, SIGN_WRITE>;
+    else if (mode == SIGN_READ) k = filtered_lrelu_kernel<T, UP, FU, DOWN, FD, TOW, TOH, SIGN_READ>;
+    else                        k = filtered_lrelu_kernel<T, UP, FU, DOWN, FD, TOW, TOH, SIGN_NONE>;
+    LVG_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<(unsigned)blocks, kThreads, smem, s>>>(p);
+    LVG_LAUNCH_CHECK();
+    return LVG_OK;
+}
+
+template <class T>
+int launch_1x1(FlParams& p, int mode, cudaStream_t s)
+{
+    const int wq = max((p.ow + 3) / 4, mode == SIGN_WRITE ? p.s_wb : 0);
+    const int64_t total = (int64_t)p.n * p.c * p.oh * wq;
+    int64_t blocks = (total + 255) / 256;
+    const int64_t cap = (int64_t)num_sms() * 8 * 16;
+    if (blocks > cap) blocks = cap;
+    if (mode == SIGN_WRITE)     filtered_lrelu_1x1_kernel<T, SIGN_WRITE><<<(unsigned)blocks, 256, 0, s>>>(p, total, wq);
+    else if (mode == SIGN_READ) filtered_lrelu_1x1_kernel<T, SIGN_READ><<<(unsigned)blocks, 256, 0, s>>>(p, total, wq);
+    else                        filtered_lrelu_1x1_kernel<T, SIGN_NONE><<<(unsigned)blocks, 256, 0, s>>>(p, total, wq);
+    LVG_LAUNCH_CHECK();
+    return LVG_OK;
+}
+
+// configuration table: separable filters only (height 0), the four shapes of SURVEY.md Appendix A
+enum Cfg { CFG_NONE = 0, CFG_1x1, CFG_U2D2, CFG_U4D2, CFG_U2D4 };
+
+Cfg pick(int fu_w, int fu_h, int fd_w, int fd_h, int up, int down)
+{
+    if (up == 1 && down == 1 && fu_w == 1 && fu_h == 1 && fd_w == 1 && fd_h == 1) return CFG_1x1;
+    if (fu_h != 0 || fd_h != 0) return CFG_NONE;
+    if (up == 2 && fu_w == 12 && down == 2 && fd_w == 12) return CFG_U2D2;
+    if (up == 4 && fu_w == 24 && down == 2 && fd_w == 12) return CFG_U4D2;
+    if (up == 2 && fu_w == 12 && down == 4 && fd_w == 24) return CFG_U2D4;
+    return CFG_NONE;
+}
+
+template <class T>
+int dispatch(Cfg cfg, FlParams& p, int mode, cudaStream_t s)
+{
+    switch (cfg) {
+        case CFG_1x1:  return launch_1x1<T>(p, mode, s);
+        case CFG_U2D2: return launch_cfg<T, 2, 12, 2, 12, 64, 32>(p, mode, s);
+        case CFG_U4D2: return launch_cfg<T, 4, 24, 2, 12, 64, 32>(p, mode, s);
+        case CFG_U2D4: return launch_cfg<T, 2, 12, 4, 24, 32, 16>(p, mode, s);
+        default: break;
+    }
+    return LVG_UNSUPPORTED;
+}
+
+}  // namespace
+}  // namespace lvg
+
+using namespace lvg;
+
+extern "C" int lvg_filtered_lrelu_supported(int dtype, int fu_w, int fu_h, int fd_w, int fd_h, int up, int down)
+{
+    if (dtype != LVG_F32 && dtype != LVG_F16) return LVG_UNSUPPORTED;
+    return pick(fu_w, fu_h, fd_w, fd_h, up, down) == CFG_NONE ? LVG_UNSUPPORTED : LVG_OK;
+}
+
+extern "C" int lvg_filtered_lrelu(const void* x, const float* fu, const float* fd, const void* b,
+                                  const uint8_t* si, void* y, uint8_t* so, int dtype,
+                                  const int64_t x_shape[4], const int64_t x_stride[4],
+                                  const int64_t y_shape[4], const int64_t y_stride[4],
+                                  int fu_w, int fu_h, int fd_w, int fd_h, int up, int down,
+                                  int px0, int py0, int s_h, int s_wbytes, int sx, int sy,
+                                  float gain, float slope, float clamp, int flip,
+                                  int write_signs, void* stream)
+{
+    LVG_REQUIRE(x && y && fu && fd && b, "filtered_lrelu: x, y, fu, fd, b must not be NULL");
+    LVG_REQUIRE(dtype == LVG_F32 || dtype == LVG_F16, "filtered_lrelu: x must be float16 or float32");
+    LVG_REQUIRE(up >= 1 && down >= 1, "filtered_lrelu: up and down must be at least 1");
+    for (int i = 0; i < 4; i++) {
+        LVG_REQUIRE(x_shape[i] >= 1 && x_shape[i] <= INT32_MAX, "filtered_lrelu: x dimension %d out of range", i);
+        LVG_REQUIRE(y_shape[i] >= 1 && y_shape[i] <= INT32_MAX, "filtered_lrelu: output must be at least 1x1");
+    }
+    LVG_REQUIRE(x_shape[0] == y_shape[0] && x_shape[1] == y_shape[1], "filtered_lrelu: x and y disagree on batch/channels");
+    LVG_REQUIRE(!(write_signs && si), "filtered_lrelu: cannot read and write signs in one call");
+    LVG_REQUIRE(!write_signs || so, "filtered_lrelu: write_signs needs an output sign buffer");
+    LVG_REQUIRE(!(write_signs || si) || (s_h >= 1 && s_wbytes >= 1), "filtered_lrelu: bad sign tensor shape");
+    const Cfg cfg = pick(fu_w, fu_h, fd_w, fd_h, up, down);
+    if (cfg == CFG_NONE) {
+        set_error("filtered_lrelu: no fused kernel for up=%d fu=%dx%d down=%d fd=%dx%d", up, fu_w, fu_h, down, fd_w, fd_h);
+        return LVG_UNSUPPORTED;
+    }
+
+    FlParams p;
+    p.x = x; p.fu = fu; p.fd = fd; p.b = b; p.si = si; p.y = y; p.so = so;
+    for (int i = 0; i < 4; i++) { p.xs[i] = x_stride[i]; p.ys[i] = y_stride[i]; }
+    p.n = (int)x_shape[0]; p.c = (int)x_shape[1]; p.ih = (int)x_shape[2]; p.iw = (int)x_shape[3];
+    p.oh = (int)y_shape[2]; p.ow = (int)y_shape[3];
+    p.px0 = px0; p.py0 = py0;
+    p.s_h = s_h; p.s_wb = s_wbytes; p.sx = sx; p.sy = sy;
+    p.sw_active = p.ow * down - (down - 1) + (fd_w - 1);
+    p.tiles_x = p.tiles_y = 1;
+    p.gain = gain; p.slope = slope; p.clamp = clamp; p.flip = flip ? 1 : 0;
+    if (write_signs) {
+        // the sign tensor must span the consumed up-sampled extent (filtered_lrelu.cpp:87-94)
+        const int need_h = p.oh * down - (down - 1) + ((fd_h ? fd_h : fd_w) - 1);
+        LVG_REQUIRE(s_h == need_h && s_wbytes * 4 >= p.sw_active, "filtered_lrelu: sign tensor has the wrong shape");
+        LVG_REQUIRE(sx == 0 && sy == 0, "filtered_lrelu: sign offsets only apply when reading signs");
+    }
+    const int mode = write_signs ? SIGN_WRITE : (si ? SIGN_READ : SIGN_NONE);
+    cudaStream_t s = (cudaStream_t)stream;
+    return dtype == LVG_F32 ? dispatch<float>(cfg, p, mode, s) : dispatch<__half>(cfg, p, mode, s);
+}

@@ -81,6 +81,11 @@ __global__ void __launch_bounds__(256) upfirdn2d_any_kernel(UpfirdnParams p, int
 
 }  // namespace
 
+int upfirdn2d_tiled(const void* x, const float* fx, int64_t fsx, const float* fy, int64_t fsy, void* y, int dtype,
+                    const int64_t* xsh, const int64_t* xst, const int64_t* ysh, const int64_t* yst,
+                    int fw, int fh, int upx, int upy, int downx, int downy, int padx0, int pady0,
+                    int flip, float gain, cudaStream_t s);
+
 int upfirdn2d_check(const void* x, const void* y, int dtype, const int64_t* xsh, const int64_t* ysh,
                     int fw, int fh, int upx, int upy, int downx, int downy)
 {
@@ -111,6 +116,14 @@ extern "C" int lvg_upfirdn2d(const void* x, const float* f, void* y, int dtype,
     int rc = upfirdn2d_check(x, y, dtype, x_shape, y_shape, fw, fh, upx, upy, downx, downy);
     if (rc) return rc;
     LVG_REQUIRE(f != nullptr, "upfirdn2d: f must not be NULL");
+
+    // a filter spanning one axis only ([k, 1] temporal filters, [1, k]) is a 1-D pass: tiled kernel
+    if ((fw == 1) != (fh == 1) && ((fw == 1 && upx == 1 && downx == 1) || (fh == 1 && upy == 1 && downy == 1))) {
+        rc = upfirdn2d_tiled(x, fw == 1 ? nullptr : f, f_stride_x, fh == 1 ? nullptr : f, f_stride_y, y, dtype,
+                             x_shape, x_stride, y_shape, y_stride, fw, fh, upx, upy, downx, downy, padx0, pady0,
+                             flip, gain, (cudaStream_t)stream);
+        if (rc != LVG_UNSUPPORTED) return rc;
+    }
 
     UpfirdnParams p;
     p.x = x; p.f = f; p.y = y;

@@ -1,0 +1,291 @@
+// Single-launch separable upfirdn2d: both passes of a separable FIR (or one pass when the filter
+// only spans one axis, e.g. the [k, 1] temporal filters on [N, C, T, H*W] tensors) in ONE kernel.
+// The intermediate of the two-pass scheme (torch_utils/ops/upfirdn2d.py:244-245 writes it to HBM)
+// stays in shared memory, so HBM sees exactly x once and y once.
+//
+// Per axis the operator is one of
+//   ID            no filter: out[o] = x[o - pad0]
+//   UP<S, F>      zero-insertion by S, F taps (F % S == 0), no decimation
+//   DOWN<S, F>    F taps, keep every S-th sample (S == 1: plain filtering)
+// with the definition of upfirdn2d.cu in this directory. Combinations of up- and down-sampling on
+// the same axis, filters that are not a multiple of the up factor, and fp64 go to the general kernel.
+//
+// One CTA = one TOW x TOH output tile of one (n, c) plane: load the input tile (zero outside the
+// image) -> x pass into a second tile -> y pass straight to global memory. Tile sizes are chosen
+// on the host per call (runtime), filter length and factors are template parameters so the taps
+// live in registers and the polyphase loops unroll (fir_passes.cuh).
+
+#include "common.cuh"
+#include "fir_passes.cuh"
+
+namespace lvg {
+
+int upfirdn2d_check(const void* x, const void* y, int dtype, const int64_t* xsh, const int64_t* ysh,
+                    int fw, int fh, int upx, int upy, int downx, int downy);
+
+namespace {
+
+enum { AX_ID = 0, AX_UP = 1, AX_DOWN = 2 };
+
+struct TiledParams {
+    const void* x;
+    const float* fx;
+    const float* fy;
+    void* y;
+    int64_t xs[4], ys[4];
+    int64_t fsx, fsy;     // element strides of the tap vectors
+    int n, c, ih, iw, oh, ow;
+    int padx0, pady0;
+    int flip;
+    float gain;
+    int tow, toh, tiles_x, tiles_y;
+    int p_in, p_mid;      // row pitches (odd)
+    int a_size;           // floats reserved for the input tile
+};
+
+constexpr int kThreads = 256;
+constexpr int kR = 4;
+
+// extent of the input tile an axis needs for `n` outputs (upper bound over alignments)
+template <int KIND, int S, int F>
+__host__ __device__ constexpr int in_extent(int n)
+{
+    return KIND == AX_ID ? n
+         : KIND == AX_DOWN ? (fir::round_up(n, kR) - 1) * S + F
+         : fir::round_up((n + S - 1 + S - 1) / S, kR) + F / S;
+}
+// extent of the x-pass output (row length of the mid tile)
+template <int KIND, int S, int F>
+__host__ __device__ constexpr int mid_extent(int n)
+{
+    return KIND == AX_UP ? fir::round_up((n + S - 1 + S - 1) / S, kR) * S : fir::round_up(n, kR);
+}
+
+template <class T, int KX, int SX, int FX, int KY, int SY, int FY>
+__global__ void __launch_bounds__(kThreads) upfirdn2d_tiled_kernel(TiledParams p)
+{
+    extern __shared__ __align__(16) float smem[];
+    // layout: [input tile a_size][mid tile (absent when the x axis is ID)][FX taps][FY taps]
+    constexpr bool kHasMid = (KX != AX_ID);
+    float* tin = smem;
+    float* tmid = kHasMid ? smem + p.a_size : tin;
+    const int mid_size = kHasMid ? in_extent<KY, SY, FY>(p.toh) * p.p_mid : 0;
+    float* s_fx = smem + p.a_size + mid_size;
+    float* s_fy = s_fx + FX;
+
+    const int tiles = p.tiles_x * p.tiles_y;
+    const int64_t plane = blockIdx.x / tiles;
+    const int tile = (int)(blockIdx.x - plane * tiles);
+    const int ty = tile / p.tiles_x, tx = tile - ty * p.tiles_x;
+    const int ox0 = tx * p.tow, oy0 = ty * p.toh;
+    const int tow_e = min(p.tow, p.ow - ox0), toh_e = min(p.toh, p.oh - oy0);
+    const int cc = (int)(plane % p.c), nn = (int)(plane / p.c);
+
+    if (KX != AX_ID) for (int i = threadIdx.x; i < FX; i += kThreads) s_fx[i] = p.flip ? p.fx[i * p.fsx] : p.fx[(FX - 1 - i) * p.fsx];
+    if (KY != AX_ID) for (int i = threadIdx.x; i < FY; i += kThreads) s_fy[i] = p.flip ? p.fy[i * p.fsy] : p.fy[(FY - 1 - i) * p.fsy];
+
+    // per-axis geometry: first input sample of the tile, how many to load, phase offsets
+    int in_x0, in_w, nqx = 0, dxo = 0;
+    if (KX == AX_UP) {
+        in_x0 = floordiv(ox0 - p.padx0, SX);
+        dxo = (ox0 - p.padx0) - in_x0 * SX;
+        nqx = (tow_e + dxo + SX - 1) / SX;
+        in_w = fir::round_up(nqx, kR) + FX / SX;
+    } else if (KX == AX_DOWN) {
+        in_x0 = ox0 * SX - p.padx0;
+        in_w = (tow_e - 1) * SX + FX;
+    } else {
+        in_x0 = ox0 - p.padx0;
+        in_w = tow_e;
+    }
+    int in_y0, in_h, nqy = 0, dyo = 0;
+    if (KY == AX_UP) {
+        in_y0 = floordiv(oy0 - p.pady0, SY);
+        dyo = (oy0 - p.pady0) - in_y0 * SY;
+        nqy = (toh_e + dyo + SY - 1) / SY;
+        in_h = fir::round_up(nqy, kR) + FY / SY;
+    } else if (KY == AX_DOWN) {
+        in_y0 = oy0 * SY - p.pady0;
+        in_h = (toh_e - 1) * SY + FY;
+    } else {
+        in_y0 = oy0 - p.pady0;
+        in_h = toh_e;
+    }
+
+    // ---- input tile, zero outside the image
+    {
+        const T* xp = (const T*)p.x + (int64_t)nn * p.xs[0] + (int64_t)cc * p.xs[1];
+        const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+        for (int iy = warp; iy < in_h; iy += kThreads / 32) {
+            const int gy = in_y0 + iy;
+            const bool rowok = gy >= 0 && gy < p.ih;
+            const T* xrow = xp + (int64_t)gy * p.xs[2];
+            for (int ix = lane; ix < in_w; ix += 32) {
+                const int gx = in_x0 + ix;
+                float v = 0.f;
+                if (rowok && gx >= 0 && gx < p.iw) v = to_acc(xrow[(int64_t)gx * p.xs[3]]);
+                tin[iy * p.p_in + ix] = v;
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- x pass
+    int pmid = p.p_in;
+    if constexpr (KX == AX_UP) {
+        fir::up_x<SX, FX, kR, kThreads>(tin, p.p_in, tmid, p.p_mid, in_h, nqx, s_fx);
+        pmid = p.p_mid;
+        __syncthreads();
+    } else if constexpr (KX == AX_DOWN) {
+        fir::down_x<SX, FX, kR, kThreads>(tin, p.p_in, 0, tmid, p.p_mid, in_h, tow_e, s_fx);
+        pmid = p.p_mid;
+        __syncthreads();
+    }
+
+    // ---- y pass -> global
+    T* yp = (T*)p.y + (int64_t)nn * p.ys[0] + (int64_t)cc * p.ys[1];
+    const float gain = p.gain;
+    const float* src = tmid + dxo;
+    if constexpr (KY == AX_UP) {
+        fir::up_y<SY, FY, kR, kThreads>(src, pmid, tow_e, nqy, s_fy,
+            [&](int a, int col, float acc) {
+                const int o = a - dyo;
+                if (o >= 0 && o < toh_e)
+                    yp[(int64_t)(oy0 + o) * p.ys[2] + (int64_t)(ox0 + col) * p.ys[3]] = from_acc<T>(acc * gain);
+            });
+    } else if constexpr (KY == AX_DOWN) {
+        fir::down_y<SY, FY, kR, kThreads>(src, pmid, 0, tow_e, toh_e, s_fy,
+            [&](int o, int col, float acc) {
+                yp[(int64_t)(oy0 + o) * p.ys[2] + (int64_t)(ox0 + col) * p.ys[3]] = from_acc<T>(acc * gain);
+            });
+    } else {
+        const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+        for (int o = warp; o < toh_e; o += kThreads / 32)
+            for (int col = lane; col < tow_e; col += 32)
+                yp[(int64_t)(oy0 + o) * p.ys[2] + (int64_t)(ox0 + col) * p.ys[3]] = from_acc<T>(src[o * pmid + col] * gain);
+    }
+}
+
+// widest tile <= 128 that wastes the fewest lanes of the 32-wide column chunks
+int pick_tow(int ow)
+{
+    if (ow <= 128) return ow;
+    int best = 64, best_waste = INT32_MAX;
+    for (int cand = 128; cand >= 64; cand -= 32) {
+        const int tiles = (ow + cand - 1) / cand;
+        const int last = ow - (tiles - 1) * cand;
+        const int waste = tiles * cand - ow + (fir::round_up(last, 32) - last);
+        if (waste < best_waste) { best_waste = waste; best = cand; }
+    }
+    return best;
+}
+
+template <class T, int KX, int SX, int FX, int KY, int SY, int FY>
+int launch_tiled(TiledParams& p, cudaStream_t s)
+{
+    // tile: as wide as reasonable, tall enough for ~4K outputs, input + mid tiles within ~56 KB
+    p.tow = pick_tow(p.ow);
+    int toh = 4096 / (p.tow > 0 ? p.tow : 1);
+    toh = fir::round_up(toh < 4 ? 4 : toh, 4);
+    if (toh > p.oh) toh = p.oh;
+    size_t smem = 0;
+    for (;;) {
+        const int in_w = in_extent<KX, SX, FX>(p.tow), in_h = in_extent<KY, SY, FY>(toh);
+        p.p_in = fir::odd_pitch(in_w);
+        p.p_mid = fir::odd_pitch(mid_extent<KX, SX, FX>(p.tow) + (KX == AX_UP ? SX : 0));
+        p.a_size = in_h * p.p_in;
+        const int mid = (KX == AX_ID) ? 0 : in_h * p.p_mid;
+        smem = (size_t)(p.a_size + mid + FX + FY) * sizeof(float);
+        if (smem <= 56 * 1024 || toh <= 4) break;
+        toh = fir::round_up(toh / 2, 4);
+    }
+    if (smem > 200 * 1024) return LVG_UNSUPPORTED;
+    p.toh = toh;
+    p.tiles_x = (p.ow + p.tow - 1) / p.tow;
+    p.tiles_y = (p.oh + p.toh - 1) / p.toh;
+    const int64_t blocks = (int64_t)p.n * p.c * p.tiles_x * p.tiles_y;
+    if (blocks > INT32_MAX) return LVG_UNSUPPORTED;
+    auto k = upfirdn2d_tiled_kernel<T, KX, SX, FX, KY, SY, FY>;
+    if (smem > 48 * 1024) LVG_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<(unsigned)blocks, kThreads, smem, s>>>(p);
+    LVG_LAUNCH_CHECK();
+    return LVG_OK;
+}
+
+struct Axis { int kind, s, f; };
+
+Axis classify(bool has_filter, int up, int down, int taps)
+{
+    if (!has_filter && up == 1 && down == 1) return {AX_ID, 1, 1};
+    if (!has_filter) return {-1, 0, 0};
+    if (up > 1 && down == 1 && taps % up == 0) return {AX_UP, up, taps};
+    if (up == 1) return {AX_DOWN, down, taps};
+    return {-1, 0, 0};
+}
+
+#define LVG_TILED_CASE(kx, sx, fx_, ky, sy, fy_)                                                        \
+    if (ax.kind == kx && ax.s == sx && ax.f == fx_ && ay.kind == ky && ay.s == sy && ay.f == fy_)       \
+        return launch_tiled<T, kx, sx, fx_, ky, sy, fy_>(p, s);
+
+template <class T>
+int dispatch(const Axis& ax, const Axis& ay, TiledParams& p, cudaStream_t s)
+{
+    // the resampling signatures of the LongVideoGAN networks and their adjoints
+    LVG_TILED_CASE(AX_UP, 2, 4, AX_UP, 2, 4)          // U3  bilinear 2x spatial up-sampling
+    LVG_TILED_CASE(AX_DOWN, 2, 4, AX_DOWN, 2, 4)      // U4  2x spatial down-sampling (and adjoint of U3)
+    LVG_TILED_CASE(AX_ID, 1, 1, AX_UP, 2, 4)          // U2  temporal linear up-sampling
+    LVG_TILED_CASE(AX_ID, 1, 1, AX_DOWN, 2, 4)        // U5  temporal down-sampling
+    LVG_TILED_CASE(AX_ID, 1, 1, AX_DOWN, 2, 12)       // U1  temporal Kaiser down-sampling
+    LVG_TILED_CASE(AX_ID, 1, 1, AX_UP, 2, 12)         //     adjoint of U1
+    LVG_TILED_CASE(AX_DOWN, 4, 24, AX_DOWN, 4, 24)    // U6  Kaiser down 4
+    LVG_TILED_CASE(AX_DOWN, 2, 12, AX_DOWN, 2, 12)    // U6 / U9 down 2, 12 taps
+    LVG_TILED_CASE(AX_UP, 2, 12, AX_UP, 2, 12)        // U6 / U9 up 2, 12 taps
+    LVG_TILED_CASE(AX_UP, 4, 24, AX_UP, 4, 24)        // U6  Kaiser up 4
+    LVG_TILED_CASE(AX_UP, 4, 8, AX_UP, 4, 8)          // U7  4x up-sampling of the low-res frames
+    LVG_TILED_CASE(AX_DOWN, 4, 8, AX_DOWN, 4, 8)      //     adjoint of U7
+    LVG_TILED_CASE(AX_DOWN, 1, 4, AX_DOWN, 1, 4)      // U8  4x4 blur before a strided convolution
+    return LVG_UNSUPPORTED;
+}
+
+}  // namespace
+
+// shared by lvg_upfirdn2d (rank-1-in-one-axis filters) and lvg_upfirdn2d_sep
+int upfirdn2d_tiled(const void* x, const float* fx, int64_t fsx, const float* fy, int64_t fsy, void* y, int dtype,
+                    const int64_t* xsh, const int64_t* xst, const int64_t* ysh, const int64_t* yst,
+                    int fw, int fh, int upx, int upy, int downx, int downy, int padx0, int pady0,
+                    int flip, float gain, cudaStream_t s)
+{
+    if (dtype != LVG_F32 && dtype != LVG_F16) return LVG_UNSUPPORTED;
+    const Axis ax = classify(fx != nullptr, upx, downx, fw), ay = classify(fy != nullptr, upy, downy, fh);
+    if (ax.kind < 0 || ay.kind < 0) return LVG_UNSUPPORTED;
+    // small planes: the tile machinery has nothing to amortise over, the general kernel does better
+    if (ysh[2] * ysh[3] < 256) return LVG_UNSUPPORTED;
+    TiledParams p;
+    p.x = x; p.fx = fx; p.fy = fy; p.y = y;
+    for (int i = 0; i < 4; i++) { p.xs[i] = xst[i]; p.ys[i] = yst[i]; }
+    p.fsx = fsx; p.fsy = fsy;
+    p.n = (int)xsh[0]; p.c = (int)xsh[1]; p.ih = (int)xsh[2]; p.iw = (int)xsh[3];
+    p.oh = (int)ysh[2]; p.ow = (int)ysh[3];
+    p.padx0 = padx0; p.pady0 = pady0; p.flip = flip ? 1 : 0; p.gain = gain;
+    return dtype == LVG_F32 ? dispatch<float>(ax, ay, p, s) : dispatch<__half>(ax, ay, p, s);
+}
+
+}  // namespace lvg
+
+using namespace lvg;
+
+extern "C" int lvg_upfirdn2d_sep(const void* x, const float* fx, const float* fy, void* y,
+                                 int dtype, const int64_t x_shape[4], const int64_t x_stride[4],
+                                 const int64_t y_shape[4], const int64_t y_stride[4],
+                                 int fw, int fh, int upx, int upy, int downx, int downy,
+                                 int padx0, int pady0, int flip, float gain, void* stream)
+{
+    int rc = upfirdn2d_check(x, y, dtype, x_shape, y_shape, fw, fh, upx, upy, downx, downy);
+    if (rc) return rc;
+    LVG_REQUIRE((fx != nullptr) || fw == 1, "upfirdn2d_sep: fx == NULL requires fw == 1");
+    LVG_REQUIRE((fy != nullptr) || fh == 1, "upfirdn2d_sep: fy == NULL requires fh == 1");
+    rc = upfirdn2d_tiled(x, fx, 1, fy, 1, y, dtype, x_shape, x_stride, y_shape, y_stride, fw, fh, upx, upy,
+                         downx, downy, padx0, pady0, flip, gain, (cudaStream_t)stream);
+    if (rc == LVG_UNSUPPORTED) set_error("upfirdn2d_sep: no tiled kernel for this configuration");
+    return rc;
+}
