@@ -1,0 +1,405 @@
+"""Benchmark of the hot path: one G+D training step's worth of torch_utils.ops calls.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload lres|sres] [--impl ours|reference]
+
+A "step" replays, through this repository's public ops (torch_utils.ops.* -> C ABI -> sm_100a
+kernels), every hot-path operator call that one LongVideoGAN training step issues, at the real
+shapes: the call trace was recorded from the unmodified reference networks
+(tools/trace_reference_workload.py -> workloads/*.json) and is replayed as
+    update_G : G forward+backward, D forward+backward          (video_gan_lres.py:100-131)
+    update_D : G forward (no grad), D forward+backward on fake and on real   (:133-176)
+i.e. G ops 2x forward + 1x backward, D ops 3x (forward + backward), on synthetic tensors
+(N(0,1) activations, Kaiser/binomial-shaped filters). Convolutions outside the torch_utils.ops
+API (F.conv3d / F.conv1d) are not part of this path and are not replayed.
+
+Default workload = BASELINE.json configs[1]: train_lres, 128-frame 64x36 video, per-GPU batch 8.
+With --gpus N (torchrun, one rank per GPU) each rank runs the same per-GPU batch (weak scaling)
+and the step ends with the flat-buffer NCCL gradient all-reduce of G and D
+(long-video-gan_b200/lvg_dist/grad_sync.py, replacing utils.sync_grads).
+
+Output: ONE JSON line on rank 0 (see the keys below). `value` = frames/s with inputs resident
+in HBM; `e2e` = the same with the step's real-video batch copied from pinned host memory and
+the result read back inside the timed region; `roofline` = achieved algorithmic HBM GB/s of the
+dominant kernel (bias_act), timed with CUDA events inside the timed steps; `cpu_baseline` = the
+CPU oracle (oracle/, a port of the reference's _ref path) on a bounded sample, reported only.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, 'long-video-gan_b200'))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+WORKLOADS = {
+    # name: (trace file, G pass, D pass, per-GPU batch, frames per sample)
+    'lres': ('lres_step.json', 'lres_G', 'lres_D', 8, 128),
+    'sres': ('sres_step.json', 'sres_G', 'sres_D', 16, 8),
+}
+GRAD_ELEMS = {'lres': (83_200_000, 46_400_000), 'sres': (27_200_000, 24_000_000)}   # G, D parameter counts
+HOT_OPS = ('bias_act', 'upfirdn2d', 'filtered_lrelu', 'conv2d_resample')
+
+
+def load_trace(name):
+    fname, gkey, dkey, batch, frames = WORKLOADS[name]
+    tr = json.load(open(os.path.join(ROOT, 'workloads', fname)))
+    return [c for c in tr[gkey] if c['op'] in HOT_OPS], [c for c in tr[dkey] if c['op'] in HOT_OPS], batch, frames
+
+
+def make_filter(shape, gen):
+    """Low-pass-like synthetic taps of the recorded shape (values do not affect timing)."""
+    if shape is None:
+        return None
+    f = torch.rand(*shape, generator=gen) + 0.1
+    return (f / f.sum()).float()
+
+
+def scaled(shape, batch):
+    return [shape[0] * batch] + list(shape[1:])
+
+
+# ---------------------------------------------------------------------------------------------
+# our arm: replay through torch_utils.ops on the GPU
+
+class Replay:
+    def __init__(self, calls, batch, device, dtype_policy):
+        from torch_utils.ops import bias_act, upfirdn2d, filtered_lrelu, conv2d_resample
+        self.ops = dict(bias_act=bias_act, upfirdn2d=upfirdn2d, filtered_lrelu=filtered_lrelu, conv2d_resample=conv2d_resample)
+        self.device = device
+        self.pool = {}
+        self.items = []
+        gen = torch.Generator().manual_seed(0)
+        for c in calls:
+            dt = torch.float16 if (c.get('fp16') and dtype_policy == 'mixed') else torch.float32
+            x = self._buf('x', scaled(c['x'], batch), dt)
+            item = dict(c=c, x=x, dtype=dt)
+            if c['op'] == 'bias_act':
+                item['b'] = torch.randn(c['x'][c['dim']], device=device, dtype=dt) if c['b'] else None
+            elif c['op'] == 'upfirdn2d':
+                item['f'] = None if c['f'] is None else make_filter(c['f'], gen).to(device)
+            elif c['op'] == 'filtered_lrelu':
+                item['fu'] = None if c['fu'] is None else make_filter(c['fu'], gen).to(device)
+                item['fd'] = None if c['fd'] is None else make_filter(c['fd'], gen).to(device)
+                item['b'] = torch.randn(c['x'][1], device=device, dtype=dt) if c['b'] else None
+            elif c['op'] == 'conv2d_resample':
+                item['w'] = (torch.randn(*c['w'], device=device) / np.sqrt(np.prod(c['w'][1:]))).to(dt)
+                item['f'] = None if c['f'] is None else make_filter(c['f'], gen).to(device)
+            self.items.append(item)
+        # output shapes (and dy buffers) from one dry forward
+        with torch.no_grad():
+            for it in self.items:
+                y = self._fwd(it, it['x'])
+                it['dy'] = self._buf('dy', list(y.shape), y.dtype)
+                it['bytes_fwd'] = (it['x'].numel() + y.numel()) * y.element_size()
+                it['bytes_bwd'] = it['bytes_fwd'] + (y.numel() * y.element_size() if it['c']['op'] == 'bias_act' else 0)
+                del y
+
+    def _buf(self, kind, shape, dt):
+        key = (kind, tuple(shape), dt)
+        if key not in self.pool:
+            self.pool[key] = torch.randn(*shape, device=self.device, dtype=dt)
+        return self.pool[key]
+
+    def _fwd(self, it, x):
+        c = it['c']
+        if c['op'] == 'bias_act':
+            return self.ops['bias_act'].bias_act(x, it['b'], dim=c['dim'], act=c['act'], alpha=c['alpha'], gain=c['gain'], clamp=c['clamp'])
+        if c['op'] == 'upfirdn2d':
+            return self.ops['upfirdn2d'].upfirdn2d(x, it['f'], up=c['up'], down=c['down'], padding=c['padding'],
+                                                   flip_filter=c['flip_filter'], gain=c['gain'])
+        if c['op'] == 'filtered_lrelu':
+            return self.ops['filtered_lrelu'].filtered_lrelu(x, fu=it['fu'], fd=it['fd'], b=it['b'], up=c['up'], down=c['down'],
+                                                             padding=c['padding'], gain=c['gain'], slope=c['slope'],
+                                                             clamp=c['clamp'], flip_filter=c['flip_filter'])
+        return self.ops['conv2d_resample'].conv2d_resample(x, it['w'], f=it['f'], up=c['up'], down=c['down'], padding=c['padding'],
+                                                           groups=c['groups'], flip_weight=c['flip_weight'], flip_filter=c['flip_filter'])
+
+    def forward_only(self):
+        with torch.no_grad():
+            for it in self.items:
+                self._fwd(it, it['x'])
+
+    def forward_backward(self, timer=None):
+        for it in self.items:
+            x = it['x'].detach().requires_grad_(True)
+            leaves = [x]
+            b = it.get('b')
+            if b is not None:
+                b = b.detach().requires_grad_(True)
+                leaves.append(b)
+            saved_b = it.get('b')
+            it['b'] = b
+            if timer is not None and it['c']['op'] == 'bias_act':
+                timer.start()
+                y = self._fwd(it, x)
+                timer.stop(it['bytes_fwd'])
+                if y.requires_grad:
+                    timer.start()
+                    torch.autograd.grad(y, leaves, it['dy'], allow_unused=True)
+                    timer.stop(it['bytes_bwd'])
+            else:
+                y = self._fwd(it, x)
+                if y.requires_grad:
+                    torch.autograd.grad(y, leaves, it['dy'], allow_unused=True)
+            it['b'] = saved_b
+
+
+class KernelTimer:
+    """CUDA-event timing of individual calls inside the timed region (events on the current stream)."""
+
+    def __init__(self):
+        self.pairs = []
+        self._cur = None
+
+    def start(self):
+        self._cur = torch.cuda.Event(enable_timing=True)
+        self._cur.record()
+
+    def stop(self, nbytes):
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        self.pairs.append((self._cur, e, nbytes))
+
+    def summary(self):
+        ms = sum(a.elapsed_time(b) for a, b, _ in self.pairs)
+        nbytes = sum(n for _, _, n in self.pairs)
+        return ms, nbytes, len(self.pairs)
+
+
+class ClockSampler:
+    FIELDS = 'clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+             'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, index):
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--id={index}', f'--query-gpu={self.FIELDS}', '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def finish(self):
+        if self.proc is None:
+            return None
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            return None
+        sm, mx, reasons = [], [], set()
+        for line in out.strip().splitlines():
+            parts = [p.strip() for p in line.split(',')]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, val in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), parts[2:6]):
+                if val.lower().startswith('active'):
+                    reasons.add(name)
+        if not sm:
+            return None
+        return {'sm_mhz': float(np.median(sm)), 'sm_max_mhz': float(max(mx)), 'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+def measured_peak():
+    try:
+        return json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))['hbm_gbs'], 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    except Exception:
+        return 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)'
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU arm: the oracle (port of the reference's _ref path) on a bounded sample of the same trace
+
+def cpu_sample(workload, budget_s=20.0):
+    """Forward of every hot-path op of one G+D pass at batch 1 through the CPU oracle, stopping
+    at the time budget. Returns (frames/s equivalent, description, threads)."""
+    from oracle import oracle as orc
+    g_calls, d_calls, batch, frames = load_trace(workload)
+    gen = torch.Generator().manual_seed(0)
+    t_used, bytes_done, calls_done = 0.0, 0, 0
+    total_bytes = 0
+    per_call = []
+    for c in g_calls + d_calls:
+        n_in = int(np.prod(c['x']))
+        per_call.append((c, n_in))
+        total_bytes += n_in * 4 * 2
+    for c, n_in in per_call:
+        if t_used > budget_s:
+            break
+        if c['op'] == 'conv2d_resample':
+            continue
+        x = np.random.default_rng(0).standard_normal(c['x'], dtype=np.float32)
+        t0 = time.perf_counter()
+        if c['op'] == 'bias_act':
+            b = np.zeros(c['x'][c['dim']], np.float32) if c['b'] else None
+            orc.bias_act(x, b, c['dim'], c['act'], c['alpha'], c['gain'], c['clamp'])
+        elif c['op'] == 'upfirdn2d':
+            f = None if c['f'] is None else make_filter(c['f'], gen).numpy()
+            orc.upfirdn2d(x, f, c['up'], c['down'], c['padding'], c['flip_filter'], c['gain'])
+        elif c['op'] == 'filtered_lrelu':
+            fu = None if c['fu'] is None else make_filter(c['fu'], gen).numpy()
+            fd = None if c['fd'] is None else make_filter(c['fd'], gen).numpy()
+            orc.filtered_lrelu(x, fu, fd, np.zeros(c['x'][1], np.float32), c['up'], c['down'], c['padding'], c['gain'], c['slope'],
+                               c['clamp'], c['flip_filter'])
+        t_used += time.perf_counter() - t0
+        bytes_done += n_in * 4 * 2
+        calls_done += 1
+    # one training step = (2 fwd + 1 bwd) of G ops + 3 (fwd + bwd) of D ops ~ 7.5 forward-equivalents of the
+    # part sampled here; scale the sampled forward time to a whole step at batch 1 by bytes covered
+    frac = bytes_done / max(total_bytes, 1)
+    step_s_batch1 = (t_used / max(frac, 1e-9)) * 4.5
+    fps = frames / step_s_batch1
+    desc = (f'{calls_done} of {len(per_call)} op calls of one G+D forward at batch 1 ({frac:.0%} of the bytes) through the oracle, '
+            f'{t_used:.1f} s; extrapolated x4.5 (2 fwd+1 bwd of G, 3 fwd+bwd of D) to a step')
+    return fps, desc, orc.num_threads()
+
+
+# ---------------------------------------------------------------------------------------------
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--workload', default='lres', choices=sorted(WORKLOADS))
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--cpu-budget', type=float, default=20.0)
+    ap.add_argument('--no-cpu', action='store_true')
+    args = ap.parse_args()
+
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    local_rank = int(os.environ.get('LOCAL_RANK', 0))
+    g_calls, d_calls, batch, frames = load_trace(args.workload)
+    metric = 'frames/sec (G+D train step, hot-path operator trace)'
+    config = {'workload': f'{args.workload}: train_{args.workload} op trace (torch_utils.ops calls of G+D update), per-GPU batch {batch}, '
+                          f'{frames} frames/sample, {"64x36" if args.workload == "lres" else "256x144 from 64x36"}',
+              'global_batch': batch * world, 'parallelism': f'dp{world}',
+              'l2': 'inputs and outputs of the replayed calls exceed L2 (largest tensors 0.75 GB); buffers shared per shape'}
+
+    if args.impl == 'reference':
+        if rank != 0:
+            return
+        steps = max(1, args.steps)
+        vals = []
+        for _ in range(max(0, min(args.warmup, 1))):
+            cpu_sample(args.workload, budget_s=min(args.cpu_budget, 5.0))
+        for _ in range(steps):
+            fps, desc, threads = cpu_sample(args.workload, budget_s=args.cpu_budget)
+            vals.append(fps)
+        v = float(np.mean(vals))
+        print(json.dumps({'impl': 'reference', 'metric': metric, 'value': v, 'unit': 'frames/s', 'n_gpus': args.gpus, 'steps': steps,
+                          'warmup': args.warmup, 'ms_per_step': 1000.0 * frames / v, 'higher_is_better': True, 'scaling': 'weak',
+                          'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': config,
+                          'cpu_baseline': {'value': v, 'unit': 'frames/s', 'cores': threads, 'kind': 'port', 'sample': desc},
+                          'e2e': {'value': v, 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}))
+        return
+
+    assert torch.cuda.is_available(), 'bench.py needs a CUDA device (the ops have no CPU fallback for the product path)'
+    torch.cuda.set_device(local_rank)
+    device = torch.device('cuda', local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=device)
+    from torch_utils import custom_ops
+    from lvg_dist.grad_sync import postprocess_
+    custom_ops.load_library()
+
+    policy = 'mixed' if args.workload == 'sres' else 'fp32'
+    G = Replay(g_calls, batch, device, policy)
+    D = Replay(d_calls, batch, device, policy)
+    flat_g = flat_d = None
+    if world > 1:
+        ng, nd = GRAD_ELEMS[args.workload]
+        flat_g = torch.randn(ng, device=device) * 1e-3
+        flat_d = torch.randn(nd, device=device) * 1e-3
+
+    # e2e buffers: the real-video batch of the step comes from pinned host memory; the result goes back
+    vid_shape = (batch, 3, frames, 36, 64) if args.workload == 'lres' else (batch, 3, frames, 144, 256)
+    host_video = torch.empty(vid_shape, dtype=torch.float32).uniform_(-1, 1).pin_memory()
+    dev_video = torch.empty(vid_shape, dtype=torch.float32, device=device)
+    host_out = torch.empty(1, dtype=torch.float32).pin_memory()
+
+    def step(timer=None, e2e=False):
+        if e2e:
+            dev_video.copy_(host_video, non_blocking=True)
+        # update_G: G fwd+bwd, D fwd+bwd ; update_D: G fwd, D fwd+bwd (fake), D fwd+bwd (real)
+        G.forward_backward(timer)
+        D.forward_backward(timer)
+        if world > 1:
+            dist.all_reduce(flat_g)
+            postprocess_(flat_g, 1.0 / world)
+        G.forward_only()
+        D.forward_backward(timer)
+        D.forward_backward(timer)
+        if world > 1:
+            dist.all_reduce(flat_d)
+            postprocess_(flat_d, 1.0 / world)
+        if e2e:
+            host_out.copy_(dev_video.view(-1)[:1], non_blocking=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(nsteps, e2e, timer=None):
+        barrier()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for _ in range(nsteps):
+            step(timer, e2e)
+        t1.record()
+        barrier()
+        ms = torch.tensor([t0.elapsed_time(t1)], device=device)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    launches0 = custom_ops.launch_count()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    timer = KernelTimer()
+    ms_total = timed(args.steps, e2e=False, timer=timer)
+    launches = custom_ops.launch_count() - launches0
+    ms_e2e = timed(args.steps, e2e=True)
+    clocks = sampler.finish() if sampler is not None else None
+
+    frames_per_step = batch * frames * world
+    value = frames_per_step * args.steps / (ms_total / 1000.0)
+    e2e_value = frames_per_step * args.steps / (ms_e2e / 1000.0)
+    k_ms, k_bytes, k_n = timer.summary()
+    peak, peak_src = measured_peak()
+    achieved = k_bytes / (k_ms / 1000.0) / 1e9 if k_ms > 0 else 0.0
+
+    if rank == 0:
+        out = {'metric': metric, 'value': value, 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps, 'warmup': max(3, args.warmup),
+               'ms_per_step': ms_total / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+               'dtype': 'f32' if policy == 'fp32' else 'f16/f32 mixed (fp16 layers as the reference config)', 'data': 'synthetic',
+               'config': config, 'gpu_launches': int(launches),
+               'e2e': {'value': e2e_value, 'unit': 'frames/s', 'h2d_bytes_per_step': host_video.numel() * 4, 'd2h_bytes_per_step': 4},
+               'roofline': {'bound': 'hbm', 'kernel': 'bias_act (vector kernel, forward + fused dx/db backward)', 'achieved': achieved,
+                            'peak': peak, 'peak_source': peak_src, 'unit': 'GB/s', 'frac': achieved / peak if peak else None,
+                            'launches_timed': k_n, 'share_of_step': k_ms / ms_total if ms_total else None, 'traffic': None},
+               'clocks': clocks}
+        if not args.no_cpu:
+            fps, desc, threads = cpu_sample(args.workload, budget_s=args.cpu_budget)
+            out['cpu_baseline'] = {'value': fps, 'unit': 'frames/s', 'cores': threads, 'kind': 'port', 'sample': desc}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

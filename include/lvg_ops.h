@@ -55,6 +55,8 @@ int         lvg_abi_version(void);
 const char* lvg_last_error(void);
 /* compile-time facts about the build: "sm_100a;..." */
 const char* lvg_build_info(void);
+/* number of kernels this library has launched in the calling process so far */
+int64_t     lvg_launch_count(void);
 
 /*
  * bias_act -- replaces bias_act_plugin.bias_act (torch_utils/ops/bias_act.cpp:32-90,
@@ -175,6 +177,14 @@ int lvg_conv2d_fprop(const void* x, const void* w, void* y, int dtype,
 int64_t lvg_conv2d_fprop_workspace(int dtype, int n, int groups, int cin, int cout,
                                    int h, int wd, int kh, int kw, int stride,
                                    int pad_h, int pad_w);
+
+/*
+ * Post-processing of an all-reduced flat gradient buffer, in place and in one pass:
+ *   g = g * scale;  NaN -> 0, +inf -> +limit, -inf -> -limit  (finite values untouched)
+ * -- the `/ world_size * gain` + `nan_to_num(nan=0, posinf=1e5, neginf=-1e5)` tail of
+ * utils.sync_grads (utils.py:116-124) without its extra passes over the buffer. fp32 only.
+ */
+int lvg_grad_postprocess(float* g, int64_t n, float scale, float limit, void* stream);
 
 #ifdef __cplusplus
 }

@@ -37,8 +37,13 @@ void set_error(const char* fmt, ...);
         }                                                                     \
     } while (0)
 
-// launch check: picks up configuration errors without synchronising
-#define LVG_LAUNCH_CHECK() LVG_CUDA(cudaPeekAtLastError())
+// after every kernel launch: count it (lvg_launch_count) and pick up configuration errors without synchronising
+void count_launch();
+#define LVG_LAUNCH_CHECK()                  \
+    do {                                    \
+        ::lvg::count_launch();              \
+        LVG_CUDA(cudaPeekAtLastError());    \
+    } while (0)
 
 inline int num_sms() {
     static int cached[64] = {0};

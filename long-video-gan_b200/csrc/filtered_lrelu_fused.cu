@@ -107,20 +107,28 @@ __global__ void __launch_bounds__(kThreads, 2) filtered_lrelu_kernel(FlParams p)
     const int tiw_e = fir::round_up(nqx_e, kR) + G::KU, tih_e = fir::round_up(nqy_e, kR) + G::KU;
 
     // ---- stage 1: input tile (+ bias inside the image, zero outside) -> A
+    // All global loads of a thread are issued before the first shared-memory store, so a CTA has
+    // its whole input tile in flight at once instead of one row per warp round trip.
     {
         const T* xp = (const T*)p.x + (int64_t)nn * p.xs[0] + (int64_t)cc * p.xs[1];
         const float bias = to_acc(((const T*)p.b)[cc]);
-        const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-        for (int iy = warp; iy < tih_e; iy += kThreads / 32) {
-            const int gy = m0y + iy;
-            const bool rowok = gy >= 0 && gy < p.ih;
-            const T* xrow = xp + (int64_t)gy * p.xs[2];
-            for (int ix = lane; ix < tiw_e; ix += 32) {
-                const int gx = m0x + ix;
-                float v = 0.f;
-                if (rowok && gx >= 0 && gx < p.iw) v = to_acc(xrow[(int64_t)gx * p.xs[3]]) + bias;
-                bufA[iy * G::P_IN + ix] = v;
-            }
+        constexpr int kTile = G::TIH * G::TIW;
+        constexpr int kLoads = (kTile + kThreads - 1) / kThreads;
+        float v[kLoads];
+#pragma unroll
+        for (int j = 0; j < kLoads; j++) {
+            const int idx = threadIdx.x + j * kThreads;
+            const int iy = idx / G::TIW, ix = idx - iy * G::TIW;
+            const int gy = m0y + iy, gx = m0x + ix;
+            v[j] = 0.f;
+            if (iy < tih_e && ix < tiw_e && gy >= 0 && gy < p.ih && gx >= 0 && gx < p.iw)
+                v[j] = to_acc(xp[(int64_t)gy * p.xs[2] + (int64_t)gx * p.xs[3]]) + bias;
+        }
+#pragma unroll
+        for (int j = 0; j < kLoads; j++) {
+            const int idx = threadIdx.x + j * kThreads;
+            const int iy = idx / G::TIW, ix = idx - iy * G::TIW;
+            if (idx < kTile) bufA[iy * G::P_IN + ix] = v[j];
         }
     }
     __syncthreads();

@@ -112,19 +112,31 @@ __global__ void __launch_bounds__(kThreads) upfirdn2d_tiled_kernel(TiledParams p
         in_h = toh_e;
     }
 
-    // ---- input tile, zero outside the image
+    // ---- input tile, zero outside the image. Loads are issued in batches of 8 per thread before
+    // any shared-memory store so that the whole tile is in flight at once.
     {
         const T* xp = (const T*)p.x + (int64_t)nn * p.xs[0] + (int64_t)cc * p.xs[1];
-        const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-        for (int iy = warp; iy < in_h; iy += kThreads / 32) {
-            const int gy = in_y0 + iy;
-            const bool rowok = gy >= 0 && gy < p.ih;
-            const T* xrow = xp + (int64_t)gy * p.xs[2];
-            for (int ix = lane; ix < in_w; ix += 32) {
-                const int gx = in_x0 + ix;
-                float v = 0.f;
-                if (rowok && gx >= 0 && gx < p.iw) v = to_acc(xrow[(int64_t)gx * p.xs[3]]);
-                tin[iy * p.p_in + ix] = v;
+        const int total = in_h * in_w;
+        const unsigned magic = in_w > 1 ? (unsigned)((0x100000000ull + (unsigned)in_w - 1) / (unsigned)in_w) : 0u;   // idx / in_w for idx < 2^20
+        constexpr int kBatch = 8;
+        for (int base = threadIdx.x; base < total; base += kThreads * kBatch) {
+            float v[kBatch];
+#pragma unroll
+            for (int j = 0; j < kBatch; j++) {
+                const int idx = base + j * kThreads;
+                const int iy = in_w > 1 ? (int)__umulhi((unsigned)idx, magic) : idx;
+                const int ix = idx - iy * in_w;
+                const int gy = in_y0 + iy, gx = in_x0 + ix;
+                v[j] = 0.f;
+                if (idx < total && gy >= 0 && gy < p.ih && gx >= 0 && gx < p.iw)
+                    v[j] = to_acc(xp[(int64_t)gy * p.xs[2] + (int64_t)gx * p.xs[3]]);
+            }
+#pragma unroll
+            for (int j = 0; j < kBatch; j++) {
+                const int idx = base + j * kThreads;
+                const int iy = in_w > 1 ? (int)__umulhi((unsigned)idx, magic) : idx;
+                const int ix = idx - iy * in_w;
+                if (idx < total) tin[iy * p.p_in + ix] = v[j];
             }
         }
     }

@@ -1,0 +1,98 @@
+"""Data-parallel gradient exchange for the train_lres.py / train_sres.py step.
+
+The reference synchronises gradients by hand after every G / D / R1 update
+(utils.py:104-125): ``torch.cat`` of every ``.grad`` into a fresh flat buffer, one
+``all_reduce(SUM)`` per 2**23-element shard, ``/ world_size * gain``, ``nan_to_num(nan=0,
+posinf=1e5, neginf=-1e5)``, ``split`` and copy back -- four extra passes over the buffer
+around the collective.
+
+Here the flat fp32 buffer is persistent and the parameters' ``.grad`` tensors are views into
+it, so backward writes gradients in place; the exchange is ONE NCCL all-reduce over
+NVLink 5 / NVSwitch (in-switch NVLS reduction when NCCL enables it) followed by ONE in-place
+kernel (``lvg_grad_postprocess``: scale + NaN/Inf clamp). Same results as the reference's
+``sync_grads`` (up to the summation order inside NCCL).
+"""
+import ctypes
+
+import torch
+import torch.distributed as dist
+
+_GRAD_LIMIT = 1e5     # utils.py:121
+
+
+class FlatGradSync:
+    """Owns one flat fp32 gradient buffer for a module and exchanges it across ranks.
+
+    >>> sync = FlatGradSync(G)            # once, after building the module
+    >>> loss.backward()                   # grads land in sync.flat through the .grad views
+    >>> sync.sync(gain=1.0)               # all-reduce mean, sanitise -- replaces utils.sync_grads(G)
+    """
+
+    def __init__(self, module, group=None):
+        self.params = [p for p in module.parameters() if p.requires_grad]
+        self.group = group
+        if not self.params:
+            self.flat = torch.zeros(0)
+            return
+        device = self.params[0].device
+        total = sum(p.numel() for p in self.params)
+        self.flat = torch.zeros(total, dtype=torch.float32, device=device)
+        self._views = []
+        ofs = 0
+        for p in self.params:
+            if p.dtype != torch.float32:
+                raise RuntimeError('FlatGradSync expects fp32 master parameters (as the reference trains)')
+            view = self.flat[ofs:ofs + p.numel()].view_as(p)
+            p.grad = view
+            self._views.append(view)
+            ofs += p.numel()
+
+    def zero_grad(self):
+        """Zero in place (``set_to_none`` would detach the views from the flat buffer)."""
+        self.flat.zero_()
+
+    def _reattach(self):
+        # optimizers / user code may have replaced p.grad: fold such gradients back into the flat buffer
+        for p, view in zip(self.params, self._views):
+            if p.grad is None:
+                view.zero_()
+                p.grad = view
+            elif p.grad.data_ptr() != view.data_ptr():
+                view.copy_(p.grad)
+                p.grad = view
+
+    def sync(self, gain=1.0):
+        """Average the gradients over the process group, scale by `gain`, sanitise NaN/Inf."""
+        if self.flat.numel() == 0:
+            return
+        self._reattach()
+        world = dist.get_world_size(self.group) if dist.is_available() and dist.is_initialized() else 1
+        if world > 1:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
+        postprocess_(self.flat, scale=float(gain) / world, limit=_GRAD_LIMIT)
+
+
+def postprocess_(flat, scale, limit=_GRAD_LIMIT):
+    """In place: ``flat *= scale`` then NaN -> 0, +-inf -> +-limit (``torch.nan_to_num`` semantics)."""
+    if flat.is_cuda:
+        from torch_utils import custom_ops
+        lib = custom_ops.load_library()
+        with torch.cuda.device(flat.device):
+            rc = lib.lvg_grad_postprocess(ctypes.c_void_p(flat.data_ptr()), flat.numel(), float(scale), float(limit),
+                                          ctypes.c_void_p(torch.cuda.current_stream(flat.device).cuda_stream))
+        if rc != 0:
+            raise RuntimeError('grad_postprocess: ' + lib.lvg_last_error().decode())
+    else:
+        # CPU tensors only occur in the gloo tests of the host logic
+        flat.mul_(scale)
+        torch.nan_to_num(flat, nan=0.0, posinf=limit, neginf=-limit, out=flat)
+    return flat
+
+
+def sync_grads(module, gain=1.0, _cache={}):
+    """Drop-in for ``utils.sync_grads(network, gain)`` (utils.py:116): keeps one FlatGradSync per module."""
+    key = id(module)
+    if key not in _cache:
+        _cache[key] = FlatGradSync(module)
+    _cache[key].sync(gain)
+    return _cache[key]

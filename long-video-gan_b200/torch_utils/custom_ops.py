@@ -41,6 +41,8 @@ _SIGNATURES = {
     'lvg_abi_version': (_c_int, []),
     'lvg_last_error': (ctypes.c_char_p, []),
     'lvg_build_info': (ctypes.c_char_p, []),
+    'lvg_launch_count': (_c_i64, []),
+    'lvg_grad_postprocess': (_c_int, [_c_void_p, _c_i64, _c_float, _c_float, _c_void_p]),
     'lvg_bias_act': (_c_int, [_c_void_p] * 6 + [_c_int, _c_i64, _c_i64, _c_i64, _c_int, _c_int, _c_float, _c_float, _c_float, _c_void_p]),
     'lvg_bias_act_grad_db': (_c_int, [_c_void_p] * 6 + [_c_int, _c_i64, _c_i64, _c_i64, _c_int, _c_float, _c_float, _c_float, _c_void_p]),
     'lvg_upfirdn2d': (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _I64x4, _I64x4, _I64x4, _I64x4, _c_int, _c_int, _c_i64, _c_i64]
@@ -85,6 +87,11 @@ def load_library():
 
 def exported_symbols():
     return sorted(_SIGNATURES)
+
+
+def launch_count():
+    """Kernels launched by liblvg_ops in this process so far."""
+    return int(load_library().lvg_launch_count())
 
 
 def _check(rc, what):
@@ -395,7 +402,7 @@ class FmaPlugin:
     def fma(self, a, b, c):
         if not (a.is_cuda and b.device == a.device and c.device == a.device):
             raise RuntimeError('fma operands must reside on one CUDA device')
-        dtype = torch.result_type(torch.result_type(a, b), c)
+        dtype = torch.promote_types(torch.promote_types(a.dtype, b.dtype), c.dtype)
         a, b, c = a.to(dtype), b.to(dtype), c.to(dtype)
         code = _dtype_code(a, 'fma')
         shape = torch.broadcast_shapes(a.shape, b.shape, c.shape)

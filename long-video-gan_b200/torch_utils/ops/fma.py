@@ -33,7 +33,7 @@ class _FusedMultiplyAdd(torch.autograd.Function):
     @staticmethod
     def forward(ctx, a, b, c):
         if a.device.type == 'cuda' and _init() and max(a.ndim, b.ndim, c.ndim) <= 6 \
-                and torch.result_type(torch.result_type(a, b), c) in (torch.float16, torch.float32, torch.float64):
+                and torch.promote_types(torch.promote_types(a.dtype, b.dtype), c.dtype) in (torch.float16, torch.float32, torch.float64):
             out = _plugin.fma(a, b, c)
         else:
             out = torch.addcmul(c, a, b)

@@ -1,0 +1,92 @@
+"""Host logic of the data-parallel gradient exchange on CPU: world_size 2, gloo backend.
+
+FlatGradSync (lvg_dist/grad_sync.py) must give what the reference's utils.sync_grads gives
+(utils.py:104-125): the mean over ranks, times gain, NaN -> 0, +-inf -> +-1e5."""
+import os
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _reference_sync(grads_per_rank, gain):
+    """What utils.sync_grads computes, restated on plain tensors."""
+    world = len(grads_per_rank)
+    flat = torch.stack([torch.cat([g.flatten() for g in gs]) for gs in grads_per_rank]).sum(0)
+    flat = flat / world
+    flat = flat * gain
+    return torch.nan_to_num(flat, nan=0, posinf=1e5, neginf=-1e5)
+
+
+def _make_grads(rank):
+    gen = torch.Generator().manual_seed(100 + rank)
+    gs = [torch.randn(5, 3, generator=gen), torch.randn(7, generator=gen), torch.randn(2, 2, 2, generator=gen)]
+    if rank == 0:
+        gs[1][2] = float('nan')
+        gs[0][0, 0] = float('inf')
+        gs[2][1, 1, 1] = -float('inf')
+    gs[0][1, 1] = 3e5 * (1 if rank == 0 else 1)      # finite but beyond the clamp after averaging
+    return gs
+
+
+def _worker(rank, world, port, ret):
+    sys.path.insert(0, os.path.join(ROOT, 'long-video-gan_b200'))
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        from lvg_dist.grad_sync import FlatGradSync, sync_grads
+        torch.manual_seed(0)
+        net = torch.nn.Module()
+        net.ps = torch.nn.ParameterList([torch.nn.Parameter(torch.zeros(5, 3)), torch.nn.Parameter(torch.zeros(7)),
+                                         torch.nn.Parameter(torch.zeros(2, 2, 2))])
+        sync = FlatGradSync(net)
+        assert sync.flat.numel() == 15 + 7 + 8
+        for p, g in zip(sync.params, _make_grads(rank)):
+            p.grad.copy_(g.reshape(p.shape))                 # what backward() does: write through the view
+        assert all(p.grad.data_ptr() >= sync.flat.data_ptr() for p in sync.params)
+        sync.sync(gain=0.5)
+        out1 = sync.flat.clone()
+        # a replaced .grad (e.g. optimizer.zero_grad(set_to_none=True) followed by backward) is folded back in
+        for p, g in zip(sync.params, _make_grads(rank)):
+            p.grad = g.reshape(p.shape).clone()
+        sync.sync(gain=0.5)
+        out2 = sync.flat.clone()
+        # functional form keeps one buffer per module
+        s2 = sync_grads(net, gain=1.0)
+        assert s2 is sync_grads(net, gain=1.0)
+        ret[rank] = (out1, out2)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_flat_grad_sync_world2():
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    port = 29500 + (os.getpid() % 2000)
+    mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
+    expect = _reference_sync([_make_grads(r) for r in range(world)], gain=0.5)
+    for r in range(world):
+        out1, out2 = ret[r]
+        assert torch.equal(out1, out2)
+        assert torch.allclose(out1, expect, rtol=1e-6, atol=0), (out1, expect)
+    assert expect[0] == 1e5 and expect[15 + 2] == 0 and expect[-1] == -1e5 and expect[4] == 1.5e5   # finite values are not clamped
+
+
+def test_single_process_is_a_plain_postprocess():
+    sys.path.insert(0, os.path.join(ROOT, 'long-video-gan_b200'))
+    from lvg_dist.grad_sync import FlatGradSync
+    lin = torch.nn.Linear(4, 4)
+    sync = FlatGradSync(lin)
+    lin(torch.ones(2, 4)).sum().backward()
+    assert lin.weight.grad.data_ptr() == sync.flat.data_ptr()          # backward accumulated into the flat buffer
+    before = sync.flat.clone()
+    sync.sync(gain=2.0)
+    assert torch.allclose(sync.flat, before * 2.0)
+    sync.zero_grad()
+    assert float(sync.flat.abs().sum()) == 0 and lin.weight.grad.data_ptr() == sync.flat.data_ptr()

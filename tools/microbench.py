@@ -97,6 +97,18 @@ def main():
             y = filtered_lrelu.filtered_lrelu(x, fu, fd, b, clamp=256, **kw)
             run(f'filtered_lrelu {name} {tag}', lambda: filtered_lrelu.filtered_lrelu(x, fu, fd, b, clamp=256, **kw), (x.numel() + y.numel()) * sz)
             del x, y
+    # the conv boundary as the reference runs it today (cuDNN grouped conv through F.conv2d), for orientation
+    for name, nt, cin, cout, h, w in (('L4 539->512 38x52', 64, 539, 512, 38, 52), ('L8 539->512 92x148', 16, 539, 512, 92, 148),
+                                      ('L12 208->128 164x276', 16, 208, 128, 164, 276)):
+        if pat not in 'conv2d cudnn':
+            continue
+        x = torch.randn(1, nt * cin, h, w, device=DEV, dtype=torch.float16)
+        wt = torch.randn(nt * cout, cin, 3, 3, device=DEV, dtype=torch.float16) / 70
+        fn = lambda: torch.nn.functional.conv2d(x, wt, padding=2, groups=nt)
+        ms = timeit(fn)
+        flops = 2.0 * nt * cout * cin * 9 * (h + 2) * (w + 2)
+        print(f'conv2d cudnn grouped fp16 {name} NT={nt}: {ms:8.3f} ms {flops / ms / 1e9:8.1f} TFLOP/s', flush=True)
+        del x, wt
     os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
     json.dump(rows, open(os.path.join(ROOT, 'gpurun_out', 'microbench.json'), 'w'), indent=1)
 
