@@ -190,6 +190,8 @@ __global__ void __launch_bounds__(kThreads, (G == 2 ? 2 : 4)) bias_act_vec_kerne
 #pragma unroll
         for (int u = 0; u < kUnroll; u++) {
             const int64_t pk = base + (int64_t)u * kThreads + threadIdx.x;
+            int64_t db_rel = -1, db_idx = 0;      // fused bias gradient of this pack (row relative to the tile, value, bias index)
+            float db_val = 0.f;
             if (pk < n_pack) {
                 const int64_t e0 = pk * N;
                 S bias[N];
@@ -217,21 +219,23 @@ __global__ void __launch_bounds__(kThreads, (G == 2 ? 2 : 4)) bias_act_vec_kerne
                 }
                 store_pack(py + e0, out);
 
-                if (FUSE_DB && bmode == BIAS_PER_PACK) {
-                    const int64_t rel = e0 / p.step_b - row0;
-                    // combine lanes that share a row before touching shared memory
-                    const unsigned active = __activemask();
-                    const unsigned peers = __match_any_sync(active, rel);
-                    float ssum = (float)dbsum;
-                    if (peers == 0xffffffffu) {
+                if (FUSE_DB && bmode == BIAS_PER_PACK) { db_rel = e0 / p.step_b - row0; db_val = (float)dbsum; db_idx = bidx; }
+            }
+            if (FUSE_DB && bmode == BIAS_PER_PACK) {
+                // whole-warp combine (lanes past the end contribute 0): lane 0 holds the smallest pack index,
+                // so if it is past the end every lane is
+                const unsigned full = 0xffffffffu;
+                const int64_t rel0 = __shfl_sync(full, db_rel, 0);
+                const bool uniform = __all_sync(full, db_rel < 0 || db_rel == rel0);
+                if (uniform) {
+                    float ssum = db_val;
 #pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) ssum += __shfl_xor_sync(0xffffffffu, ssum, o);
-                        if ((threadIdx.x & 31) == 0) {
-                            if (rel < kBins) atomicAdd(&s_bins[rel], ssum); else atomicAdd(p.db + bidx, ssum);
-                        }
-                    } else {
-                        if (rel < kBins) atomicAdd(&s_bins[rel], ssum); else atomicAdd(p.db + bidx, ssum);
+                    for (int o = 16; o > 0; o >>= 1) ssum += __shfl_xor_sync(full, ssum, o);
+                    if ((threadIdx.x & 31) == 0 && rel0 >= 0) {
+                        if (rel0 < kBins) atomicAdd(&s_bins[rel0], ssum); else atomicAdd(p.db + db_idx, ssum);
                     }
+                } else if (db_rel >= 0) {
+                    if (db_rel < kBins) atomicAdd(&s_bins[db_rel], db_val); else atomicAdd(p.db + db_idx, db_val);
                 }
             }
         }

@@ -19,6 +19,7 @@
 
 #include "common.cuh"
 #include "fir_passes.cuh"
+#include <stdlib.h>
 
 namespace lvg {
 namespace {
@@ -146,7 +147,7 @@ __global__ void __launch_bounds__(kThreads, 2) filtered_lrelu_kernel(FlParams p)
         const int s_w = p.s_wb * 4;
         const int cols = nqx_e * UP;
         fir::up_y<UP, FU, kR, kThreads>(bufB, G::P_UX, cols, nqy_e, s_fu,
-            [&](int row, int col, float acc) {
+            [&](int, int row, int col, float acc) {
                 float v = acc * scale;
                 if (MODE == SIGN_READ) {
                     const int qx = Uax + col + p.sx, qy = Vay + row + p.sy;
@@ -156,10 +157,12 @@ __global__ void __launch_bounds__(kThreads, 2) filtered_lrelu_kernel(FlParams p)
                         if (s & 2u) v = 0.f;
                     }
                 } else {
-                    unsigned code = 0;
-                    if (v < 0.f) { v *= slope; code = 1; }
-                    if (fabsf(v) > clamp) { v = v < 0.f ? -clamp : clamp; code = 2; }
-                    if (MODE == SIGN_WRITE) s_code[row * G::TUWA + col] = (uint8_t)code;
+                    // branch-free: selects only (the sign code is 2 if clamped, else 1 if negative)
+                    const bool neg = v < 0.f;
+                    v = neg ? v * slope : v;
+                    const bool sat = fabsf(v) > clamp;
+                    v = sat ? copysignf(clamp, v) : v;
+                    if (MODE == SIGN_WRITE) s_code[row * G::TUWA + col] = (uint8_t)(sat ? 2 : (neg ? 1 : 0));
                 }
                 bufA[row * G::P_UXY + col] = v;
             });
@@ -199,7 +202,7 @@ __global__ void __launch_bounds__(kThreads, 2) filtered_lrelu_kernel(FlParams p)
     {
         T* yp = (T*)p.y + (int64_t)nn * p.ys[0] + (int64_t)cc * p.ys[1];
         fir::down_y<DOWN, FD, kR, kThreads>(bufB, G::P_DX, 0, tow_e, toh_e, s_fd,
-            [&](int o, int col, float acc) {
+            [&](int, int o, int col, float acc) {
                 yp[(int64_t)(oy0 + o) * p.ys[2] + (int64_t)(ox0 + col) * p.ys[3]] = from_acc<T>(acc);
             });
     }
@@ -299,13 +302,21 @@ Cfg pick(int fu_w, int fu_h, int fd_w, int fd_h, int up, int down)
     return CFG_NONE;
 }
 
+// tile height experiment switch: LVG_FL_TOH=32 selects the 64x32 tiles (2 CTAs/SM), default 64x16 (4 CTAs/SM)
+bool tall_tiles()
+{
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("LVG_FL_TOH"); v = (e && atoi(e) == 32) ? 1 : 0; }
+    return v == 1;
+}
+
 template <class T>
 int dispatch(Cfg cfg, FlParams& p, int mode, cudaStream_t s)
 {
     switch (cfg) {
         case CFG_1x1:  return launch_1x1<T>(p, mode, s);
-        case CFG_U2D2: return launch_cfg<T, 2, 12, 2, 12, 64, 32>(p, mode, s);
-        case CFG_U4D2: return launch_cfg<T, 4, 24, 2, 12, 64, 32>(p, mode, s);
+        case CFG_U2D2: return tall_tiles() ? launch_cfg<T, 2, 12, 2, 12, 64, 32>(p, mode, s) : launch_cfg<T, 2, 12, 2, 12, 64, 16>(p, mode, s);
+        case CFG_U4D2: return tall_tiles() ? launch_cfg<T, 4, 24, 2, 12, 64, 32>(p, mode, s) : launch_cfg<T, 4, 24, 2, 12, 64, 16>(p, mode, s);
         case CFG_U2D4: return launch_cfg<T, 2, 12, 4, 24, 32, 16>(p, mode, s);
         default: break;
     }

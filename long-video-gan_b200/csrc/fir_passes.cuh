@@ -28,6 +28,15 @@ namespace fir {
 
 constexpr int kWarp = 32;
 
+// n / d for small non-negative n without the integer-division sequence
+struct FastDiv {
+    unsigned magic;   // ceil(2^32 / d); exact for n * d < 2^32
+    int d;
+    __host__ __device__ explicit FastDiv(int d_ = 1) : magic(d_ > 1 ? (unsigned)((0x100000000ull + (unsigned)d_ - 1) / (unsigned)d_) : 0u), d(d_) {}
+    __device__ __forceinline__ int div(int n) const { return d > 1 ? (int)__umulhi((unsigned)n, magic) : n; }
+};
+
+
 // ---------------------------------------------------------------------------
 // up-sampling along x.  in: [rows][pin], out: [rows][pout] (phase-aligned axis)
 // groups = number of input-aligned groups to produce per row (each UP outputs).
@@ -45,8 +54,9 @@ __device__ __forceinline__ void up_x(const float* __restrict__ in, int pin, floa
     const int warp = threadIdx.x / kWarp, lane = threadIdx.x % kWarp;
     const int gthreads = (groups + R - 1) / R;                 // thread-level groups per row
     const int n_rt = (rows + RW - 1) / RW, n_gt = (gthreads + GW - 1) / GW;
+    const FastDiv by_gt(n_gt);
     for (int wi = warp; wi < n_rt * n_gt; wi += NTHREADS / kWarp) {
-        const int rt = wi / n_gt, gt = wi - rt * n_gt;
+        const int rt = by_gt.div(wi), gt = wi - rt * n_gt;
         const int r = rt * RW + lane % RW;
         const int tg = gt * GW + lane / RW;
         if (r < rows && tg < gthreads) {
@@ -71,11 +81,13 @@ __device__ __forceinline__ void up_x(const float* __restrict__ in, int pin, floa
 }
 
 // ---------------------------------------------------------------------------
-// up-sampling along y.  in: [in_rows][pin]; produces rows a = UP*q + r for
-// q < groups, every column < cols, and hands (row a, col, value) to `emit`.
+// up-sampling along y.  in: [nplanes][plane_rows][pin]; for every plane produces rows a = UP*q + r
+// for q < groups and every column < cols, and hands (plane, row a, col, value) to `emit`.
+// Lanes run over the flattened (plane, column) index so narrow planes still fill a warp.
+
 template <int UP, int F, int R, int NTHREADS, class Emit>
 __device__ __forceinline__ void up_y(const float* __restrict__ in, int pin, int cols, int groups,
-                                     const float* __restrict__ s_taps, Emit emit)
+                                     const float* __restrict__ s_taps, Emit emit, int nplanes = 1, int plane_rows = 0)
 {
     static_assert(F % UP == 0, "filter length must be a multiple of the up-sampling factor");
     constexpr int K = F / UP;
@@ -84,12 +96,16 @@ __device__ __forceinline__ void up_y(const float* __restrict__ in, int pin, int 
     for (int i = 0; i < F; i++) g[i] = s_taps[i];
     const int warp = threadIdx.x / kWarp, lane = threadIdx.x % kWarp;
     const int gthreads = (groups + R - 1) / R;
-    const int n_cc = (cols + kWarp - 1) / kWarp;
+    const int vcols = nplanes * cols;
+    const int n_cc = (vcols + kWarp - 1) / kWarp;
+    const FastDiv by_cols(cols), by_cc(n_cc);
     for (int wi = warp; wi < gthreads * n_cc; wi += NTHREADS / kWarp) {
-        const int tg = wi / n_cc, cc = wi - tg * n_cc;
-        const int col = cc * kWarp + lane;
-        if (col < cols) {
-            const float* src = in + (tg * R) * pin + col;
+        const int tg = by_cc.div(wi), cc = wi - tg * n_cc;
+        const int vc = cc * kWarp + lane;
+        if (vc < vcols) {
+            const int pl = nplanes > 1 ? by_cols.div(vc) : 0;
+            const int col = vc - pl * cols;
+            const float* src = in + (pl * plane_rows + tg * R) * pin + col;
             float v[K + R];
 #pragma unroll
             for (int i = 0; i < K + R; i++) v[i] = src[i * pin];
@@ -101,7 +117,7 @@ __device__ __forceinline__ void up_y(const float* __restrict__ in, int pin, int 
 #pragma unroll
                     for (int k = 0; k < K; k++)
                         acc = fmaf(g[(UP - ph) % UP + k * UP], v[j + (ph > 0 ? 1 : 0) + k], acc);
-                    emit((tg * R + j) * UP + ph, col, acc);
+                    emit(pl, (tg * R + j) * UP + ph, col, acc);
                 }
             }
         }
@@ -125,8 +141,9 @@ __device__ __forceinline__ void down_x(const float* __restrict__ in, int pin, in
     const int warp = threadIdx.x / kWarp, lane = threadIdx.x % kWarp;
     const int gthreads = (outs + R - 1) / R;
     const int n_rt = (rows + RW - 1) / RW, n_gt = (gthreads + GW - 1) / GW;
+    const FastDiv by_gt(n_gt);
     for (int wi = warp; wi < n_rt * n_gt; wi += NTHREADS / kWarp) {
-        const int rt = wi / n_gt, gt = wi - rt * n_gt;
+        const int rt = by_gt.div(wi), gt = wi - rt * n_gt;
         const int r = rt * RW + lane % RW;
         const int tg = gt * GW + lane / RW;
         if (r < rows && tg < gthreads) {
@@ -147,11 +164,11 @@ __device__ __forceinline__ void down_x(const float* __restrict__ in, int pin, in
 }
 
 // ---------------------------------------------------------------------------
-// down-sampling along y.  in: [.][pin] read from row offset `yoff`;
-// value(o, col) = sum_t g[t] * in[yoff + o*DOWN + t][col] for o < outs, handed to `emit`.
+// down-sampling along y.  in: [nplanes][plane_rows][pin] read from row offset `yoff` of each plane;
+// value(plane, o, col) = sum_t g[t] * in[plane][yoff + o*DOWN + t][col] for o < outs, handed to `emit`.
 template <int DOWN, int F, int R, int NTHREADS, class Emit>
 __device__ __forceinline__ void down_y(const float* __restrict__ in, int pin, int yoff, int cols, int outs,
-                                       const float* __restrict__ s_taps, Emit emit)
+                                       const float* __restrict__ s_taps, Emit emit, int nplanes = 1, int plane_rows = 0)
 {
     constexpr int NIN = (R - 1) * DOWN + F;
     float g[F];
@@ -159,12 +176,16 @@ __device__ __forceinline__ void down_y(const float* __restrict__ in, int pin, in
     for (int i = 0; i < F; i++) g[i] = s_taps[i];
     const int warp = threadIdx.x / kWarp, lane = threadIdx.x % kWarp;
     const int gthreads = (outs + R - 1) / R;
-    const int n_cc = (cols + kWarp - 1) / kWarp;
+    const int vcols = nplanes * cols;
+    const int n_cc = (vcols + kWarp - 1) / kWarp;
+    const FastDiv by_cols(cols), by_cc(n_cc);
     for (int wi = warp; wi < gthreads * n_cc; wi += NTHREADS / kWarp) {
-        const int tg = wi / n_cc, cc = wi - tg * n_cc;
-        const int col = cc * kWarp + lane;
-        if (col < cols) {
-            const float* src = in + (yoff + tg * R * DOWN) * pin + col;
+        const int tg = by_cc.div(wi), cc = wi - tg * n_cc;
+        const int vc = cc * kWarp + lane;
+        if (vc < vcols) {
+            const int pl = nplanes > 1 ? by_cols.div(vc) : 0;
+            const int col = vc - pl * cols;
+            const float* src = in + (pl * plane_rows + yoff + tg * R * DOWN) * pin + col;
             float v[NIN];
 #pragma unroll
             for (int i = 0; i < NIN; i++) v[i] = src[i * pin];
@@ -173,7 +194,7 @@ __device__ __forceinline__ void down_y(const float* __restrict__ in, int pin, in
                 float acc = 0.f;
 #pragma unroll
                 for (int t = 0; t < F; t++) acc = fmaf(g[t], v[j * DOWN + t], acc);
-                if (tg * R + j < outs) emit(tg * R + j, col, acc);
+                if (tg * R + j < outs) emit(pl, tg * R + j, col, acc);
             }
         }
     }

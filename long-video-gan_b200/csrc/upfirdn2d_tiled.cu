@@ -39,8 +39,10 @@ struct TiledParams {
     int flip;
     float gain;
     int tow, toh, tiles_x, tiles_y;
+    int pb;               // planes per CTA (> 1 only when one tile covers the whole plane)
+    int64_t planes;       // n * c
     int p_in, p_mid;      // row pitches (odd)
-    int a_size;           // floats reserved for the input tile
+    int a_size;           // floats reserved for the input tile(s)
 };
 
 constexpr int kThreads = 256;
@@ -69,17 +71,21 @@ __global__ void __launch_bounds__(kThreads) upfirdn2d_tiled_kernel(TiledParams p
     constexpr bool kHasMid = (KX != AX_ID);
     float* tin = smem;
     float* tmid = kHasMid ? smem + p.a_size : tin;
-    const int mid_size = kHasMid ? in_extent<KY, SY, FY>(p.toh) * p.p_mid : 0;
+    const int mid_size = kHasMid ? p.pb * in_extent<KY, SY, FY>(p.toh) * p.p_mid : 0;
     float* s_fx = smem + p.a_size + mid_size;
     float* s_fy = s_fx + FX;
 
+    // CTA -> (first plane, tile). With pb > 1 the CTA owns pb whole planes (tiles_x == tiles_y == 1).
     const int tiles = p.tiles_x * p.tiles_y;
-    const int64_t plane = blockIdx.x / tiles;
-    const int tile = (int)(blockIdx.x - plane * tiles);
+    const int64_t plane0 = (p.pb > 1) ? (int64_t)blockIdx.x * p.pb : (int64_t)(blockIdx.x / tiles);
+    const int tile = (p.pb > 1) ? 0 : (int)(blockIdx.x - plane0 * tiles);
+    const int npl = (p.pb > 1) ? (int)min((int64_t)p.pb, p.planes - plane0) : 1;
     const int ty = tile / p.tiles_x, tx = tile - ty * p.tiles_x;
     const int ox0 = tx * p.tow, oy0 = ty * p.toh;
     const int tow_e = min(p.tow, p.ow - ox0), toh_e = min(p.toh, p.oh - oy0);
-    const int cc = (int)(plane % p.c), nn = (int)(plane / p.c);
+    // plane -> memory offset: pb > 1 requires stride[0] == C * stride[1] (checked on the host)
+    const int64_t xoff0 = (p.pb > 1) ? plane0 * p.xs[1] : (plane0 / p.c) * p.xs[0] + (plane0 % p.c) * p.xs[1];
+    const int64_t yoff0 = (p.pb > 1) ? plane0 * p.ys[1] : (plane0 / p.c) * p.ys[0] + (plane0 % p.c) * p.ys[1];
 
     if (KX != AX_ID) for (int i = threadIdx.x; i < FX; i += kThreads) s_fx[i] = p.flip ? p.fx[i * p.fsx] : p.fx[(FX - 1 - i) * p.fsx];
     if (KY != AX_ID) for (int i = threadIdx.x; i < FY; i += kThreads) s_fy[i] = p.flip ? p.fy[i * p.fsy] : p.fy[(FY - 1 - i) * p.fsy];
@@ -112,32 +118,33 @@ __global__ void __launch_bounds__(kThreads) upfirdn2d_tiled_kernel(TiledParams p
         in_h = toh_e;
     }
 
-    // ---- input tile, zero outside the image. Loads are issued in batches of 8 per thread before
+    // ---- input tile(s), zero outside the image. Loads are issued in batches of 8 per thread before
     // any shared-memory store so that the whole tile is in flight at once.
     {
-        const T* xp = (const T*)p.x + (int64_t)nn * p.xs[0] + (int64_t)cc * p.xs[1];
-        const int total = in_h * in_w;
-        const unsigned magic = in_w > 1 ? (unsigned)((0x100000000ull + (unsigned)in_w - 1) / (unsigned)in_w) : 0u;   // idx / in_w for idx < 2^20
+        const T* xp = (const T*)p.x + xoff0;
+        const int per_plane = in_h * in_w;
+        const int total = npl * per_plane;
+        const fir::FastDiv by_w(in_w), by_plane(per_plane);
         constexpr int kBatch = 8;
         for (int base = threadIdx.x; base < total; base += kThreads * kBatch) {
             float v[kBatch];
+            int dst[kBatch];
 #pragma unroll
             for (int j = 0; j < kBatch; j++) {
                 const int idx = base + j * kThreads;
-                const int iy = in_w > 1 ? (int)__umulhi((unsigned)idx, magic) : idx;
-                const int ix = idx - iy * in_w;
+                const int pl = npl > 1 ? by_plane.div(idx) : 0;
+                const int rem = idx - pl * per_plane;
+                const int iy = by_w.div(rem);
+                const int ix = rem - iy * in_w;
                 const int gy = in_y0 + iy, gx = in_x0 + ix;
                 v[j] = 0.f;
+                dst[j] = (pl * in_h + iy) * p.p_in + ix;
                 if (idx < total && gy >= 0 && gy < p.ih && gx >= 0 && gx < p.iw)
-                    v[j] = to_acc(xp[(int64_t)gy * p.xs[2] + (int64_t)gx * p.xs[3]]);
+                    v[j] = to_acc(xp[(int64_t)pl * p.xs[1] + (int64_t)gy * p.xs[2] + (int64_t)gx * p.xs[3]]);
             }
 #pragma unroll
-            for (int j = 0; j < kBatch; j++) {
-                const int idx = base + j * kThreads;
-                const int iy = in_w > 1 ? (int)__umulhi((unsigned)idx, magic) : idx;
-                const int ix = idx - iy * in_w;
-                if (idx < total) tin[iy * p.p_in + ix] = v[j];
-            }
+            for (int j = 0; j < kBatch; j++)
+                if (base + j * kThreads < total) tin[dst[j]] = v[j];
         }
     }
     __syncthreads();
@@ -145,36 +152,41 @@ __global__ void __launch_bounds__(kThreads) upfirdn2d_tiled_kernel(TiledParams p
     // ---- x pass
     int pmid = p.p_in;
     if constexpr (KX == AX_UP) {
-        fir::up_x<SX, FX, kR, kThreads>(tin, p.p_in, tmid, p.p_mid, in_h, nqx, s_fx);
+        fir::up_x<SX, FX, kR, kThreads>(tin, p.p_in, tmid, p.p_mid, npl * in_h, nqx, s_fx);
         pmid = p.p_mid;
         __syncthreads();
     } else if constexpr (KX == AX_DOWN) {
-        fir::down_x<SX, FX, kR, kThreads>(tin, p.p_in, 0, tmid, p.p_mid, in_h, tow_e, s_fx);
+        fir::down_x<SX, FX, kR, kThreads>(tin, p.p_in, 0, tmid, p.p_mid, npl * in_h, tow_e, s_fx);
         pmid = p.p_mid;
         __syncthreads();
     }
 
     // ---- y pass -> global
-    T* yp = (T*)p.y + (int64_t)nn * p.ys[0] + (int64_t)cc * p.ys[1];
+    T* yp = (T*)p.y + yoff0;
     const float gain = p.gain;
     const float* src = tmid + dxo;
     if constexpr (KY == AX_UP) {
         fir::up_y<SY, FY, kR, kThreads>(src, pmid, tow_e, nqy, s_fy,
-            [&](int a, int col, float acc) {
+            [&](int pl, int a, int col, float acc) {
                 const int o = a - dyo;
                 if (o >= 0 && o < toh_e)
-                    yp[(int64_t)(oy0 + o) * p.ys[2] + (int64_t)(ox0 + col) * p.ys[3]] = from_acc<T>(acc * gain);
-            });
+                    yp[(int64_t)pl * p.ys[1] + (int64_t)(oy0 + o) * p.ys[2] + (int64_t)(ox0 + col) * p.ys[3]] = from_acc<T>(acc * gain);
+            }, npl, in_h);
     } else if constexpr (KY == AX_DOWN) {
         fir::down_y<SY, FY, kR, kThreads>(src, pmid, 0, tow_e, toh_e, s_fy,
-            [&](int o, int col, float acc) {
-                yp[(int64_t)(oy0 + o) * p.ys[2] + (int64_t)(ox0 + col) * p.ys[3]] = from_acc<T>(acc * gain);
-            });
+            [&](int pl, int o, int col, float acc) {
+                yp[(int64_t)pl * p.ys[1] + (int64_t)(oy0 + o) * p.ys[2] + (int64_t)(ox0 + col) * p.ys[3]] = from_acc<T>(acc * gain);
+            }, npl, in_h);
     } else {
-        const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-        for (int o = warp; o < toh_e; o += kThreads / 32)
-            for (int col = lane; col < tow_e; col += 32)
-                yp[(int64_t)(oy0 + o) * p.ys[2] + (int64_t)(ox0 + col) * p.ys[3]] = from_acc<T>(src[o * pmid + col] * gain);
+        const int per = toh_e * tow_e;
+        const fir::FastDiv by_w(tow_e), by_per(per);
+        for (int idx = threadIdx.x; idx < npl * per; idx += kThreads) {
+            const int pl = npl > 1 ? by_per.div(idx) : 0;
+            const int rem = idx - pl * per;
+            const int o = by_w.div(rem), col = rem - o * tow_e;
+            yp[(int64_t)pl * p.ys[1] + (int64_t)(oy0 + o) * p.ys[2] + (int64_t)(ox0 + col) * p.ys[3]] =
+                from_acc<T>(src[(pl * in_h + o) * pmid + col] * gain);
+        }
     }
 }
 
@@ -195,27 +207,42 @@ int pick_tow(int ow)
 template <class T, int KX, int SX, int FX, int KY, int SY, int FY>
 int launch_tiled(TiledParams& p, cudaStream_t s)
 {
-    // tile: as wide as reasonable, tall enough for ~4K outputs, input + mid tiles within ~56 KB
+    constexpr int kTargetOutputs = 4096;        // outputs per CTA the tile/plane batching aims for
+    constexpr size_t kSmemBudget = 56 * 1024;   // keeps 4 CTAs resident per SM
     p.tow = pick_tow(p.ow);
-    int toh = 4096 / (p.tow > 0 ? p.tow : 1);
+    int toh = kTargetOutputs / (p.tow > 0 ? p.tow : 1);
     toh = fir::round_up(toh < 4 ? 4 : toh, 4);
     if (toh > p.oh) toh = p.oh;
-    size_t smem = 0;
-    for (;;) {
-        const int in_w = in_extent<KX, SX, FX>(p.tow), in_h = in_extent<KY, SY, FY>(toh);
+    p.pb = 1;
+    auto smem_for = [&](int toh_, int pb_) {
+        const int in_w = in_extent<KX, SX, FX>(p.tow), in_h = in_extent<KY, SY, FY>(toh_);
         p.p_in = fir::odd_pitch(in_w);
         p.p_mid = fir::odd_pitch(mid_extent<KX, SX, FX>(p.tow) + (KX == AX_UP ? SX : 0));
-        p.a_size = in_h * p.p_in;
-        const int mid = (KX == AX_ID) ? 0 : in_h * p.p_mid;
-        smem = (size_t)(p.a_size + mid + FX + FY) * sizeof(float);
-        if (smem <= 56 * 1024 || toh <= 4) break;
+        p.a_size = pb_ * in_h * p.p_in;
+        const int mid = (KX == AX_ID) ? 0 : pb_ * in_h * p.p_mid;
+        return (size_t)(p.a_size + mid + FX + FY) * sizeof(float);
+    };
+    size_t smem = smem_for(toh, 1);
+    while (smem > kSmemBudget && toh > 4) {
         toh = fir::round_up(toh / 2, 4);
+        smem = smem_for(toh, 1);
     }
     if (smem > 200 * 1024) return LVG_UNSUPPORTED;
     p.toh = toh;
     p.tiles_x = (p.ow + p.tow - 1) / p.tow;
     p.tiles_y = (p.oh + p.toh - 1) / p.toh;
-    const int64_t blocks = (int64_t)p.n * p.c * p.tiles_x * p.tiles_y;
+    // small planes: several whole planes per CTA (needs planes to be equally spaced in memory)
+    const bool uniform = (p.xs[0] == (int64_t)p.c * p.xs[1]) && (p.ys[0] == (int64_t)p.c * p.ys[1]);
+    if (p.tiles_x == 1 && p.tiles_y == 1 && uniform && p.planes > 1) {
+        int pb = kTargetOutputs / (p.ow * p.oh);
+        if (pb > 64) pb = 64;
+        if ((int64_t)pb > p.planes) pb = (int)p.planes;
+        while (pb > 1 && smem_for(p.toh, pb) > kSmemBudget) pb--;
+        if (pb < 1) pb = 1;
+        p.pb = pb;
+        smem = smem_for(p.toh, p.pb);
+    }
+    const int64_t blocks = p.pb > 1 ? (p.planes + p.pb - 1) / p.pb : p.planes * p.tiles_x * p.tiles_y;
     if (blocks > INT32_MAX) return LVG_UNSUPPORTED;
     auto k = upfirdn2d_tiled_kernel<T, KX, SX, FX, KY, SY, FY>;
     if (smem > 48 * 1024) LVG_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -270,14 +297,13 @@ int upfirdn2d_tiled(const void* x, const float* fx, int64_t fsx, const float* fy
     if (dtype != LVG_F32 && dtype != LVG_F16) return LVG_UNSUPPORTED;
     const Axis ax = classify(fx != nullptr, upx, downx, fw), ay = classify(fy != nullptr, upy, downy, fh);
     if (ax.kind < 0 || ay.kind < 0) return LVG_UNSUPPORTED;
-    // small planes: the tile machinery has nothing to amortise over, the general kernel does better
-    if (ysh[2] * ysh[3] < 256) return LVG_UNSUPPORTED;
     TiledParams p;
     p.x = x; p.fx = fx; p.fy = fy; p.y = y;
     for (int i = 0; i < 4; i++) { p.xs[i] = xst[i]; p.ys[i] = yst[i]; }
     p.fsx = fsx; p.fsy = fsy;
     p.n = (int)xsh[0]; p.c = (int)xsh[1]; p.ih = (int)xsh[2]; p.iw = (int)xsh[3];
     p.oh = (int)ysh[2]; p.ow = (int)ysh[3];
+    p.planes = (int64_t)p.n * p.c;
     p.padx0 = padx0; p.pady0 = pady0; p.flip = flip ? 1 : 0; p.gain = gain;
     return dtype == LVG_F32 ? dispatch<float>(ax, ay, p, s) : dispatch<__half>(ax, ay, p, s);
 }
