@@ -173,41 +173,50 @@ class KernelTimer:
 
 
 class ClockSampler:
-    FIELDS = 'clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
-             'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+    """Samples SM clock and throttle reasons through NVML every 100 ms while the timed region runs."""
+    REASONS = {0x8: 'hw_slowdown', 0x40: 'hw_thermal_slowdown', 0x20: 'sw_thermal_slowdown', 0x4: 'sw_power_cap'}
 
     def __init__(self, index):
-        self.proc = None
+        import threading
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
         try:
-            self.proc = subprocess.Popen(['nvidia-smi', f'--id={index}', f'--query-gpu={self.FIELDS}', '--format=csv,noheader,nounits', '-lms', '100'],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            import pynvml
+            pynvml.nvmlInit()
+            self._nv = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
         except Exception:
-            self.proc = None
+            self._thread = None
+
+    def _run(self):
+        nv = self._nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self._h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+                for bit, name in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.1)
 
     def finish(self):
-        if self.proc is None:
+        if self._thread is None:
             return None
-        self.proc.terminate()
-        try:
-            out, _ = self.proc.communicate(timeout=5)
-        except Exception:
-            self.proc.kill()
+        self._stop.set()
+        self._thread.join(timeout=2)
+        if not self.samples:
             return None
-        sm, mx, reasons = [], [], set()
-        for line in out.strip().splitlines():
-            parts = [p.strip() for p in line.split(',')]
-            if len(parts) < 6:
-                continue
-            try:
-                sm.append(float(parts[0])); mx.append(float(parts[1]))
-            except ValueError:
-                continue
-            for name, val in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), parts[2:6]):
-                if val.lower().startswith('active'):
-                    reasons.add(name)
-        if not sm:
-            return None
-        return {'sm_mhz': float(np.median(sm)), 'sm_max_mhz': float(max(mx)), 'reasons': sorted(reasons), 'samples': len(sm)}
+        return {'sm_mhz': float(np.median(self.samples)), 'sm_max_mhz': self.max_mhz, 'reasons': sorted(self.reasons),
+                'samples': len(self.samples)}
 
 
 def measured_peak():
@@ -221,46 +230,48 @@ def measured_peak():
 # CPU arm: the oracle (port of the reference's _ref path) on a bounded sample of the same trace
 
 def cpu_sample(workload, budget_s=20.0):
-    """Forward of every hot-path op of one G+D pass at batch 1 through the CPU oracle, stopping
-    at the time budget. Returns (frames/s equivalent, description, threads)."""
+    """The CPU oracle on a bounded sample of the same trace: repeated forward passes of every hot-path
+    op call of one G+D pass at batch 1 (fresh synthetic inputs of the recorded shapes) until the time
+    budget is used. Returns (frames/s equivalent for a whole training step, description, threads)."""
     from oracle import oracle as orc
     g_calls, d_calls, batch, frames = load_trace(workload)
     gen = torch.Generator().manual_seed(0)
-    t_used, bytes_done, calls_done = 0.0, 0, 0
-    total_bytes = 0
-    per_call = []
-    for c in g_calls + d_calls:
-        n_in = int(np.prod(c['x']))
-        per_call.append((c, n_in))
-        total_bytes += n_in * 4 * 2
-    for c, n_in in per_call:
-        if t_used > budget_s:
-            break
-        if c['op'] == 'conv2d_resample':
-            continue
-        x = np.random.default_rng(0).standard_normal(c['x'], dtype=np.float32)
-        t0 = time.perf_counter()
+    rng = np.random.default_rng(0)
+    calls = [c for c in g_calls + d_calls if c['op'] != 'conv2d_resample']
+    prepared = []
+    for c in calls:
+        item = {'c': c, 'x': rng.standard_normal(c['x'], dtype=np.float32)}
         if c['op'] == 'bias_act':
-            b = np.zeros(c['x'][c['dim']], np.float32) if c['b'] else None
-            orc.bias_act(x, b, c['dim'], c['act'], c['alpha'], c['gain'], c['clamp'])
+            item['b'] = np.zeros(c['x'][c['dim']], np.float32) if c['b'] else None
         elif c['op'] == 'upfirdn2d':
-            f = None if c['f'] is None else make_filter(c['f'], gen).numpy()
-            orc.upfirdn2d(x, f, c['up'], c['down'], c['padding'], c['flip_filter'], c['gain'])
+            item['f'] = None if c['f'] is None else make_filter(c['f'], gen).numpy()
         elif c['op'] == 'filtered_lrelu':
-            fu = None if c['fu'] is None else make_filter(c['fu'], gen).numpy()
-            fd = None if c['fd'] is None else make_filter(c['fd'], gen).numpy()
-            orc.filtered_lrelu(x, fu, fd, np.zeros(c['x'][1], np.float32), c['up'], c['down'], c['padding'], c['gain'], c['slope'],
-                               c['clamp'], c['flip_filter'])
+            item['fu'] = None if c['fu'] is None else make_filter(c['fu'], gen).numpy()
+            item['fd'] = None if c['fd'] is None else make_filter(c['fd'], gen).numpy()
+            item['b'] = np.zeros(c['x'][1], np.float32)
+        prepared.append(item)
+    t_used, passes = 0.0, 0
+    while True:
+        t0 = time.perf_counter()
+        for it in prepared:
+            c = it['c']
+            if c['op'] == 'bias_act':
+                orc.bias_act(it['x'], it['b'], c['dim'], c['act'], c['alpha'], c['gain'], c['clamp'])
+            elif c['op'] == 'upfirdn2d':
+                orc.upfirdn2d(it['x'], it['f'], c['up'], c['down'], c['padding'], c['flip_filter'], c['gain'])
+            elif c['op'] == 'filtered_lrelu':
+                orc.filtered_lrelu(it['x'], it['fu'], it['fd'], it['b'], c['up'], c['down'], c['padding'], c['gain'], c['slope'],
+                                   c['clamp'], c['flip_filter'])
         t_used += time.perf_counter() - t0
-        bytes_done += n_in * 4 * 2
-        calls_done += 1
-    # one training step = (2 fwd + 1 bwd) of G ops + 3 (fwd + bwd) of D ops ~ 7.5 forward-equivalents of the
-    # part sampled here; scale the sampled forward time to a whole step at batch 1 by bytes covered
-    frac = bytes_done / max(total_bytes, 1)
-    step_s_batch1 = (t_used / max(frac, 1e-9)) * 4.5
+        passes += 1
+        if t_used >= budget_s or passes >= 64:
+            break
+    # one training step = (2 fwd + 1 bwd) of the G ops + 3 (fwd + bwd) of the D ops; a backward op costs about
+    # a forward (same stencil transposed) -> ~4.5 forward-equivalents of the sampled G+D forward per step
+    step_s_batch1 = (t_used / passes) * 4.5
     fps = frames / step_s_batch1
-    desc = (f'{calls_done} of {len(per_call)} op calls of one G+D forward at batch 1 ({frac:.0%} of the bytes) through the oracle, '
-            f'{t_used:.1f} s; extrapolated x4.5 (2 fwd+1 bwd of G, 3 fwd+bwd of D) to a step')
+    desc = (f'{passes} forward passes of all {len(prepared)} hot-path op calls of one G+D pass at batch 1 (of {batch}) through the '
+            f'CPU oracle, {t_used:.1f} s; x4.5 forward-equivalents per training step')
     return fps, desc, orc.num_threads()
 
 

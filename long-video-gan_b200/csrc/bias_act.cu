@@ -55,13 +55,13 @@ template <> __device__ __forceinline__ double ftanh<double>(double v) { return t
 // One element. `v` is x (grad 0) or the incoming gradient (grad>0); xr = xref + b;
 // yr = yref; dyv = dy (grad 2) or 1.
 template <class S, int A>
-__device__ __forceinline__ S bias_act_elem(S v, S xr, S yr, S dyv, int G, S alpha, S gain, S clamp)
+__device__ __forceinline__ S bias_act_elem(S v, S xr, S yr, S dyv, int G, S alpha, S gain, S inv_gain, S clamp)
 {
     const S one = (S)1, two = (S)2;
     const S kExpRange = (S)80, kHalfExpRange = (S)40;
     const S kSeluScale = (S)1.0507009873554804934193349852946;
     const S kSeluAlpha = (S)1.6732632423543772848170429916717;
-    const S r = (gain != (S)0) ? yr / gain : (S)0;   // activation output before gain
+    const S r = yr * inv_gain;   // activation output before gain (inv_gain = 1/gain, 0 when gain is 0)
     S out = (S)0;
 
     if (A == LVG_ACT_LINEAR) {
@@ -156,6 +156,7 @@ __global__ void __launch_bounds__(kThreads, (G == 2 ? 2 : 4)) bias_act_vec_kerne
     constexpr bool kUseY = (G > 0) && (A != LVG_ACT_SWISH);       // saved output
     constexpr bool kUseDy = (G == 2);
     const S alpha = (S)p.alpha, gain = (S)p.gain, clamp = (S)p.clamp;
+    const S inv_gain = gain != (S)0 ? (S)1 / gain : (S)0;
     const T* __restrict__ px = (const T*)p.x;
     const T* __restrict__ pb = (const T*)p.b;
     const T* __restrict__ pxr = kUseX ? (const T*)p.xref : nullptr;
@@ -207,7 +208,7 @@ __global__ void __launch_bounds__(kThreads, (G == 2 ? 2 : 4)) bias_act_vec_kerne
                     S yr = (kUseY && pref) ? to_acc(vref[u].v[k]) : (S)0;
                     S dyv = (kUseDy && pdy) ? to_acc(vdy[u].v[k]) : (S)1;
                     if (G == 0) v += bias[k]; else xr += bias[k];
-                    S o = bias_act_elem<S, A>(v, xr, yr, dyv, G, alpha, gain, clamp);
+                    S o = bias_act_elem<S, A>(v, xr, yr, dyv, G, alpha, gain, inv_gain, clamp);
                     out.v[k] = from_acc<T>(o);
                     if (FUSE_DB) {
                         // accumulate what was actually stored, like dx.sum() would see it
@@ -257,6 +258,7 @@ __global__ void __launch_bounds__(kThreads) bias_act_scalar_kernel(BiasActParams
     typedef typename Acc<T>::type S;
     const int G = p.grad;
     const S alpha = (S)p.alpha, gain = (S)p.gain, clamp = (S)p.clamp;
+    const S inv_gain = gain != (S)0 ? (S)1 / gain : (S)0;
     for (int64_t i = first + (int64_t)blockIdx.x * kThreads + threadIdx.x; i < p.n; i += (int64_t)gridDim.x * kThreads) {
         S v = to_acc(((const T*)p.x)[i]);
         int64_t bidx = (p.b || FUSE_DB) ? (i / p.step_b) % p.size_b : 0;
@@ -265,7 +267,7 @@ __global__ void __launch_bounds__(kThreads) bias_act_scalar_kernel(BiasActParams
         S yr = p.yref ? to_acc(((const T*)p.yref)[i]) : (S)0;
         S dyv = p.dy ? to_acc(((const T*)p.dy)[i]) : (S)1;
         if (G == 0) v += bias; else xr += bias;
-        T o = from_acc<T>(bias_act_elem<S, A>(v, xr, yr, dyv, G, alpha, gain, clamp));
+        T o = from_acc<T>(bias_act_elem<S, A>(v, xr, yr, dyv, G, alpha, gain, inv_gain, clamp));
         ((T*)p.y)[i] = o;
         if (FUSE_DB) atomicAdd(p.db + bidx, (float)to_acc(o));
     }

@@ -118,33 +118,39 @@ __global__ void __launch_bounds__(kThreads) upfirdn2d_tiled_kernel(TiledParams p
         in_h = toh_e;
     }
 
-    // ---- input tile(s), zero outside the image. Loads are issued in batches of 8 per thread before
-    // any shared-memory store so that the whole tile is in flight at once.
+    // ---- input tile(s), zero outside the image. One warp per row, lanes along the row (coalesced);
+    // kRows rows are in flight per warp before the first shared-memory store, and all the per-row
+    // index arithmetic is warp-uniform (one division per row, not per element).
     {
         const T* xp = (const T*)p.x + xoff0;
-        const int per_plane = in_h * in_w;
-        const int total = npl * per_plane;
-        const fir::FastDiv by_w(in_w), by_plane(per_plane);
-        constexpr int kBatch = 8;
-        for (int base = threadIdx.x; base < total; base += kThreads * kBatch) {
-            float v[kBatch];
-            int dst[kBatch];
+        const int rows = npl * in_h;
+        const fir::FastDiv by_h(in_h);
+        constexpr int kRows = 8;
+        const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+        for (int r0 = warp * kRows; r0 < rows; r0 += (kThreads / 32) * kRows) {
+            const T* src[kRows];
+            bool ok[kRows];
 #pragma unroll
-            for (int j = 0; j < kBatch; j++) {
-                const int idx = base + j * kThreads;
-                const int pl = npl > 1 ? by_plane.div(idx) : 0;
-                const int rem = idx - pl * per_plane;
-                const int iy = by_w.div(rem);
-                const int ix = rem - iy * in_w;
-                const int gy = in_y0 + iy, gx = in_x0 + ix;
-                v[j] = 0.f;
-                dst[j] = (pl * in_h + iy) * p.p_in + ix;
-                if (idx < total && gy >= 0 && gy < p.ih && gx >= 0 && gx < p.iw)
-                    v[j] = to_acc(xp[(int64_t)pl * p.xs[1] + (int64_t)gy * p.xs[2] + (int64_t)gx * p.xs[3]]);
+            for (int j = 0; j < kRows; j++) {
+                const int r = r0 + j;
+                const int pl = npl > 1 ? by_h.div(r) : 0;
+                const int gy = in_y0 + (r - pl * in_h);
+                ok[j] = r < rows && gy >= 0 && gy < p.ih;
+                src[j] = xp + (int64_t)pl * p.xs[1] + (int64_t)gy * p.xs[2];
             }
+            for (int ix = lane; ix < in_w; ix += 32) {
+                const int gx = in_x0 + ix;
+                const bool colok = gx >= 0 && gx < p.iw;
+                float v[kRows];
 #pragma unroll
-            for (int j = 0; j < kBatch; j++)
-                if (base + j * kThreads < total) tin[dst[j]] = v[j];
+                for (int j = 0; j < kRows; j++) {
+                    v[j] = 0.f;
+                    if (ok[j] && colok) v[j] = to_acc(src[j][(int64_t)gx * p.xs[3]]);
+                }
+#pragma unroll
+                for (int j = 0; j < kRows; j++)
+                    if (r0 + j < rows) tin[(r0 + j) * p.p_in + ix] = v[j];
+            }
         }
     }
     __syncthreads();
