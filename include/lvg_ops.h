@@ -166,8 +166,9 @@ int lvg_fma(const void* a, const void* b, const void* c, void* out, int dtype,
  * "modulated" convolutions (model/generator_sres.py:63-65) and the
  * discriminator convolutions (conv2d_resample.py:29-41).
  *   x [N][G*Cin][H][W]  w [G*Cout][Cin][kh][kw]  y [N][G*Cout][Ho][Wo]
- * NCHW-contiguous operands, fp16 storage with fp32 accumulation, or fp32
- * storage computed as split-tf32 (3 MMAs per product, fp32-level accuracy).
+ * NCHW-contiguous fp16 operands, fp32 accumulation in tensor memory, stride 1, 3x3 or 1x1,
+ * any batch n (samples share the weights of their group). `workspace` holds the
+ * re-tiled weights (lvg_conv2d_fprop_workspace bytes, 16-byte aligned).
  * Returns LVG_UNSUPPORTED outside the covered envelope.
  */
 int lvg_conv2d_fprop(const void* x, const void* w, void* y, int dtype,
@@ -177,6 +178,15 @@ int lvg_conv2d_fprop(const void* x, const void* w, void* y, int dtype,
 int64_t lvg_conv2d_fprop_workspace(int dtype, int n, int groups, int cin, int cout,
                                    int h, int wd, int kh, int kw, int stride,
                                    int pad_h, int pad_w);
+/*
+ * Gradient of the convolution above with respect to its input (same kernel, the weights
+ * repacked channel-transposed and spatially mirrored, padding k-1-pad): dx [N][G*Cin][H][W] from
+ * dy [N][G*Cout][Ho][Wo]. The argument list describes the FORWARD convolution. Same workspace.
+ */
+int lvg_conv2d_dgrad(const void* dy, const void* w, void* dx, int dtype,
+                     int n, int groups, int cin, int cout, int h, int wd,
+                     int kh, int kw, int stride, int pad_h, int pad_w,
+                     void* workspace, int64_t workspace_bytes, void* stream);
 
 /*
  * Post-processing of an all-reduced flat gradient buffer, in place and in one pass:

@@ -1,0 +1,416 @@
+// Grouped 2-D convolution (cross-correlation) as an implicit GEMM on the 5th-generation tensor
+// cores: tcgen05.mma with fp16 operands from shared memory and fp32 accumulators in tensor memory.
+//
+// This is the kernel behind conv2d_gradfix.conv2d (torch_utils/ops/conv2d_gradfix.py:37-40) for the
+// per-sample-weight "modulated" convolutions of the super-res generator
+// (model/generator_sres.py:63-65: x [1, G*Cin, H, W], w [G*Cout, Cin, 3, 3], padding 2, groups G = N*T)
+// and for the stride-1 discriminator convolutions. The reference hands these to cuDNN.
+//
+// GEMM view, per group g:   D[co][pix] = sum_tap sum_ci  W_tap[co][ci] * X[ci][pix + tap]
+//   M = Cout (tiles of 128 = one UMMA M), N = a TH x WT patch of output pixels (<= 256 columns of
+//   TMEM), K = Cin in chunks of 16 (one UMMA K step) times the kh*kw taps, all accumulated into the
+//   same TMEM tile.
+//
+// Operand staging (no swizzle, "interleaved" canonical layouts of the UMMA shared-memory descriptor):
+//   A  weights, K-major.  A pre-pass (conv_pack_weights_kernel) rewrites the [Cout][Cin][kh*kw]
+//      weights once per call into ready-made 128 x 16 tile images, one per (m-tile, k-chunk, tap),
+//      so the main kernel stages A with plain 16-byte copies. The fp16 NCHW activations cannot be
+//      addressed by tiled TMA (row pitches of the sres layers are 4 mod 8 elements, not multiples of
+//      16 bytes), hence software staging for both operands.
+//   B  activations, MN-major (pixels contiguous, exactly as they sit in NCHW memory). The tile is
+//      staged as [kw x-shifted copies][16 channels][(TH + kh - 1) rows x WT pixels]; a tap (ky, kx)
+//      is then just a different descriptor start address: copy kx, advanced by ky rows. A shift by
+//      one pixel cannot be expressed in a descriptor (16-byte granularity), a shift by one row can.
+//
+// One CTA = one (pixel tile, 128-channel m-tile, group). Per k-chunk: all threads stage A and B,
+// fence to the async proxy, one thread issues kh*kw MMAs and commits them to an mbarrier that gates
+// the next staging round. Two CTAs are resident per SM (<= 72 KB shared memory, 256 TMEM columns
+// each), so one CTA's staging overlaps the other's MMAs. Epilogue: tcgen05.ld -> fp16 -> global.
+
+#include "common.cuh"
+
+namespace lvg {
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kBM = 128;          // UMMA M
+constexpr int kBK = 16;           // channels per k-chunk (= UMMA K for fp16)
+constexpr int kATileBytes = kBM * kBK * 2;   // 4096
+
+struct ConvParams {
+    const __half* x;
+    const __half* wp;        // packed weights
+    __half* y;
+    int groups;              // instances = N * G (grid.z)
+    int wgroups;             // weight groups G: instance i uses the weights of group i % G
+    int cin, cout;           // per group
+    int h, w, ho, wo;
+    int kh, kw, pad_h, pad_w;
+    int th, wt;              // output tile: th rows x wt pixels (wt % 8 == 0, th * wt % 16 == 0, <= 256)
+    int tiles_x, tiles_y;
+    int kc, mt;              // k-chunks, m-tiles
+};
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n"
+            " .reg .pred p;\n"
+            " mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            " selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+    }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols)
+{
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols)
+{
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+// shared-memory matrix descriptor, no swizzle: start address, leading / stride byte offsets (all >> 4), version 1
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3fff);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;
+    d |= (uint64_t)1 << 46;
+    return d;
+}
+
+// D[tmem] (+)= A[smem] * B[smem], fp16 x fp16 -> fp32, issued by ONE thread
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n"
+        " .reg .pred p;\n"
+        " setp.ne.b32 p, %4, 0;\n"
+        " tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
+// weights -> tile images.  Element (m, k, tap) of the logical A matrix of group g sits at
+//   w[g * gstride + m * sm + k * sk + (flip ? taps-1-tap : tap)]
+// fprop: m = co, k = ci (sm = cin*taps, sk = taps); dgrad: m = ci, k = co (sm = taps, sk = cin*taps), flipped taps.
+// Image of one 128 x 16 tile (K-major, no swizzle): byte offset(m, k) = (k/8)*2048 + (m/8)*128 + (m%8)*16 + (k%8)*2.
+__global__ void __launch_bounds__(256) conv_pack_weights_kernel(const __half* __restrict__ w, __half* __restrict__ wp, int groups,
+                                                                 int m_total, int k_total, int taps, int64_t gstride,
+                                                                 int64_t sm, int64_t sk, int flip, int mt, int kc)
+{
+    // one thread = one 16-byte row of a core matrix (8 consecutive k of one m, one tap)
+    const int64_t total = (int64_t)groups * mt * kc * taps * (kATileBytes / 16);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        // decode with tap fastest so that neighbouring threads read neighbouring weights
+        int64_t r = i;
+        const int tap = (int)(r % taps); r /= taps;
+        const int k8 = (int)(r % 2); r /= 2;
+        const int mrow = (int)(r % kBM); r /= kBM;
+        const int kci = (int)(r % kc); r /= kc;
+        const int mti = (int)(r % mt);
+        const int g = (int)(r / mt);
+        const int m = mti * kBM + mrow;
+        const int k0 = kci * kBK + k8 * 8;
+        const int wtap = flip ? taps - 1 - tap : tap;
+        alignas(16) __half v[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const int k = k0 + j;
+            v[j] = (m < m_total && k < k_total) ? w[(int64_t)g * gstride + (int64_t)m * sm + (int64_t)k * sk + wtap] : __float2half(0.f);
+        }
+        const int64_t tile = (((int64_t)g * mt + mti) * kc + kci) * taps + tap;
+        char* dst = reinterpret_cast<char*>(wp) + tile * kATileBytes + k8 * 2048 + (mrow / 8) * 128 + (mrow % 8) * 16;
+        *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(v);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+
+template <int KH, int KW>
+__global__ void __launch_bounds__(kThreads, 2) conv_fprop_tc_kernel(ConvParams p)
+{
+    constexpr int TAPS = KH * KW;
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint64_t mma_bar;
+    __shared__ uint32_t tmem_base_slot;
+
+    const int nch_row = p.wt / 8;                          // 16-byte chunks per tile row
+    const int nch = (p.th + KH - 1) * nch_row;             // chunks per (copy, k-group)
+    unsigned char* sA = smem;                              // [TAPS][4096]
+    unsigned char* sB = smem + TAPS * kATileBytes;         // [KW copies][2 k-groups][nch][128]
+    const uint32_t lbo_b = (uint32_t)nch * 128;            // between the two 8-channel groups
+    const int N = p.th * p.wt;
+
+    const int tile = blockIdx.x;
+    const int ty = tile / p.tiles_x, tx = tile - ty * p.tiles_x;
+    const int mti = blockIdx.y;
+    const int g = blockIdx.z;
+    const int oy0 = ty * p.th, ox0 = tx * p.wt;
+    const int iy0 = oy0 - p.pad_h, ix0 = ox0 - p.pad_w;
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+
+    if (threadIdx.x == 0) {
+        mbar_init(&mma_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) tmem_alloc(&tmem_base_slot, 256);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_d = tmem_base_slot;
+
+    // instruction descriptor: D = f32, A = B = f16, A K-major, B MN-major, N >> 3, M >> 4
+    const uint32_t idesc = (1u << 4) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+
+    const __half* xg = p.x + (int64_t)g * p.cin * p.h * p.w;
+    const unsigned char* wpg = reinterpret_cast<const unsigned char*>(p.wp) + (((int64_t)(g % p.wgroups) * p.mt + mti) * p.kc) * TAPS * kATileBytes;
+
+    for (int kci = 0; kci < p.kc; kci++) {
+        if (kci > 0) mbar_wait(&mma_bar, (uint32_t)((kci - 1) & 1));   // the MMAs of the previous chunk have consumed the buffers
+
+        // ---- A: TAPS ready-made tile images, straight 16-byte copies
+        {
+            const uint4* src = reinterpret_cast<const uint4*>(wpg + (int64_t)kci * TAPS * kATileBytes);
+            uint4* dst = reinterpret_cast<uint4*>(sA);
+            for (int i = threadIdx.x; i < TAPS * kATileBytes / 16; i += kThreads) dst[i] = __ldg(src + i);
+        }
+        // ---- B: item = (channel, row, chunk): 8 + KW - 1 pixels in, KW shifted 8-pixel chunks out
+        {
+            const int rows = p.th + KH - 1;
+            const int items = kBK * rows * nch_row;
+            for (int it = threadIdx.x; it < items; it += kThreads) {
+                const int c = it % nch_row;
+                const int rr = (it / nch_row) % rows;
+                const int ch = it / (nch_row * rows);
+                const int ci = kci * kBK + ch;
+                const int gy = iy0 + rr;
+                __half px[8 + KW - 1];
+                const bool rowok = ci < p.cin && gy >= 0 && gy < p.h;
+                const __half* row = xg + ((int64_t)ci * p.h + gy) * p.w;
+#pragma unroll
+                for (int i = 0; i < 8 + KW - 1; i++) {
+                    const int gx = ix0 + c * 8 + i;
+                    px[i] = (rowok && gx >= 0 && gx < p.w) ? row[gx] : __float2half(0.f);
+                }
+#pragma unroll
+                for (int v = 0; v < KW; v++) {
+                    alignas(16) __half o[8];
+#pragma unroll
+                    for (int i = 0; i < 8; i++) o[i] = px[i + v];
+                    unsigned char* dst = sB + ((size_t)((v * 2 + ch / 8) * nch + rr * nch_row + c)) * 128 + (ch % 8) * 16;
+                    *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(o);
+                }
+            }
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        __syncthreads();
+
+        if (threadIdx.x == 0) {
+            tc_fence_after();
+#pragma unroll
+            for (int tap = 0; tap < TAPS; tap++) {
+                const int ky = tap / KW, kx = tap % KW;
+                const uint64_t adesc = make_desc(smem_u32(sA + tap * kATileBytes), 2048, 128);
+                const uint64_t bdesc = make_desc(smem_u32(sB + ((size_t)(kx * 2) * nch + ky * nch_row) * 128), lbo_b, 128);
+                umma_f16(tmem_d, adesc, bdesc, idesc, (kci > 0 || tap > 0) ? 1u : 0u);
+            }
+            umma_commit(&mma_bar);
+        }
+    }
+
+    // ---- epilogue: TMEM -> registers -> fp16 -> global (half2 stores along the pixel axis)
+    mbar_wait(&mma_bar, (uint32_t)((p.kc - 1) & 1));
+    tc_fence_after();
+    {
+        const int q = warp % 4;                 // TMEM lane quadrant this warp may read
+        const int m = mti * kBM + q * 32 + lane;
+        __half* yrow = p.y + ((int64_t)g * p.cout + m) * p.ho * p.wo;
+        for (int n0 = (warp / 4) * 32; n0 < N; n0 += 64) {
+            uint32_t acc[32];
+            tmem_ld32(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)n0, acc);
+            if (m < p.cout) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 2) {
+                    const int n = n0 + j;
+                    const int r = n / p.wt, c = n - r * p.wt;       // wt is even: the pair stays in one row
+                    const int oy = oy0 + r, ox = ox0 + c;
+                    if (n < N && oy < p.ho && ox < p.wo) {
+                        __half* dst = yrow + (int64_t)oy * p.wo + ox;
+                        const __half2 v = __floats2half2_rn(__uint_as_float(acc[j]), __uint_as_float(acc[j + 1]));
+                        if (ox + 1 < p.wo && ((reinterpret_cast<uintptr_t>(dst) & 3) == 0)) {
+                            *reinterpret_cast<__half2*>(dst) = v;
+                        } else {
+                            dst[0] = __low2half(v);
+                            if (ox + 1 < p.wo) dst[1] = __high2half(v);
+                        }
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_d, 256);
+}
+
+// tile geometry for an output of ho x wo pixels
+void pick_tile(int ho, int wo, int& th, int& wt, int& tiles_x, int& tiles_y)
+{
+    tiles_x = (wo + 63) / 64;
+    wt = ((wo + tiles_x - 1) / tiles_x + 7) / 8 * 8;
+    th = (256 / wt) & ~1;
+    if (th < 2) th = 2;
+    if (th > ho + (ho & 1)) th = ho + (ho & 1);       // no taller than the (even-rounded) image
+    tiles_y = (ho + th - 1) / th;
+}
+
+size_t smem_bytes(int taps, int kh, int kw, int th, int wt)
+{
+    return (size_t)taps * kATileBytes + (size_t)kw * 2 * (th + kh - 1) * (wt / 8) * 128;
+}
+
+bool supported(int dtype, int kh, int kw, int stride)
+{
+    return dtype == LVG_F16 && stride == 1 && ((kh == 3 && kw == 3) || (kh == 1 && kw == 1));
+}
+
+int64_t packed_bytes(int groups, int m_total, int k_total, int taps)
+{
+    const int mt = (m_total + kBM - 1) / kBM, kc = (k_total + kBK - 1) / kBK;
+    return (int64_t)groups * mt * kc * taps * kATileBytes;
+}
+
+// shared driver: packs `w` (viewed as A[m][k][tap]) and runs the GEMM-conv of x into y
+int run_conv(const __half* x, const __half* w, __half* y, int n, int groups, int cin_x, int cout_y, int h, int wd, int kh, int kw,
+             int pad_h, int pad_w, int64_t w_gstride, int64_t w_sm, int64_t w_sk, int flip, void* workspace,
+             int64_t workspace_bytes, cudaStream_t s)
+{
+    const int taps = kh * kw;
+    ConvParams p;
+    p.x = x; p.y = y;
+    p.groups = n * groups; p.wgroups = groups; p.cin = cin_x; p.cout = cout_y;
+    p.h = h; p.w = wd; p.kh = kh; p.kw = kw; p.pad_h = pad_h; p.pad_w = pad_w;
+    p.ho = h + 2 * pad_h - kh + 1;
+    p.wo = wd + 2 * pad_w - kw + 1;
+    LVG_REQUIRE(p.ho >= 1 && p.wo >= 1, "conv2d: empty output");
+    p.mt = (cout_y + kBM - 1) / kBM;
+    p.kc = (cin_x + kBK - 1) / kBK;
+    const int64_t need = packed_bytes(groups, cout_y, cin_x, taps);
+    LVG_REQUIRE(workspace && workspace_bytes >= need, "conv2d: workspace too small (%lld < %lld bytes)", (long long)workspace_bytes, (long long)need);
+    LVG_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "conv2d: workspace must be 16-byte aligned");
+    p.wp = reinterpret_cast<const __half*>(workspace);
+    pick_tile(p.ho, p.wo, p.th, p.wt, p.tiles_x, p.tiles_y);
+    LVG_REQUIRE((int64_t)n * groups <= 65535 && p.mt <= 65535, "conv2d: too many groups / channel tiles for one launch");
+
+    {
+        const int64_t total = need / 16;
+        int64_t blocks = (total + 255) / 256;
+        const int64_t cap = (int64_t)num_sms() * 32;
+        if (blocks > cap) blocks = cap;
+        conv_pack_weights_kernel<<<(unsigned)blocks, 256, 0, s>>>(w, reinterpret_cast<__half*>(workspace), groups, cout_y, cin_x, taps,
+                                                                  w_gstride, w_sm, w_sk, flip, p.mt, p.kc);
+        LVG_LAUNCH_CHECK();
+    }
+    const size_t smem = smem_bytes(taps, kh, kw, p.th, p.wt);
+    LVG_REQUIRE(smem <= 100 * 1024, "conv2d: tile does not fit shared memory");
+    dim3 grid((unsigned)(p.tiles_x * p.tiles_y), (unsigned)p.mt, (unsigned)p.groups);
+    if (kh == 3) {
+        LVG_CUDA(cudaFuncSetAttribute(conv_fprop_tc_kernel<3, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        conv_fprop_tc_kernel<3, 3><<<grid, kThreads, smem, s>>>(p);
+    } else {
+        LVG_CUDA(cudaFuncSetAttribute(conv_fprop_tc_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        conv_fprop_tc_kernel<1, 1><<<grid, kThreads, smem, s>>>(p);
+    }
+    LVG_LAUNCH_CHECK();
+    return LVG_OK;
+}
+
+}  // namespace
+}  // namespace lvg
+
+using namespace lvg;
+
+extern "C" int64_t lvg_conv2d_fprop_workspace(int dtype, int n, int groups, int cin, int cout, int h, int wd, int kh, int kw,
+                                              int stride, int pad_h, int pad_w)
+{
+    (void)h; (void)wd; (void)pad_h; (void)pad_w;
+    if (!supported(dtype, kh, kw, stride) || n < 1) return -1;
+    // enough for either direction (fprop packs [cout][cin], dgrad packs [cin][cout])
+    const int64_t a = packed_bytes(groups, cout, cin, kh * kw), b = packed_bytes(groups, cin, cout, kh * kw);
+    return a > b ? a : b;
+}
+
+extern "C" int lvg_conv2d_fprop(const void* x, const void* w, void* y, int dtype, int n, int groups, int cin, int cout,
+                                int h, int wd, int kh, int kw, int stride, int pad_h, int pad_w, void* workspace,
+                                int64_t workspace_bytes, void* stream)
+{
+    LVG_REQUIRE(x && w && y, "conv2d_fprop: x, w, y must not be NULL");
+    if (!supported(dtype, kh, kw, stride) || n < 1 || pad_h < 0 || pad_w < 0) {
+        set_error("conv2d_fprop: outside the tensor-core kernel's envelope (fp16, stride 1, 3x3 or 1x1)");
+        return LVG_UNSUPPORTED;
+    }
+    const int taps = kh * kw;
+    return run_conv((const __half*)x, (const __half*)w, (__half*)y, n, groups, cin, cout, h, wd, kh, kw, pad_h, pad_w,
+                    (int64_t)cout * cin * taps, (int64_t)cin * taps, taps, 0, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int lvg_conv2d_dgrad(const void* dy, const void* w, void* dx, int dtype, int n, int groups, int cin, int cout,
+                                int h, int wd, int kh, int kw, int stride, int pad_h, int pad_w, void* workspace,
+                                int64_t workspace_bytes, void* stream)
+{
+    LVG_REQUIRE(dy && w && dx, "conv2d_dgrad: dy, w, dx must not be NULL");
+    if (!supported(dtype, kh, kw, stride) || n < 1 || pad_h > kh - 1 || pad_w > kw - 1 || pad_h < 0 || pad_w < 0) {
+        set_error("conv2d_dgrad: outside the tensor-core kernel's envelope");
+        return LVG_UNSUPPORTED;
+    }
+    // dx = correlation of dy (ho x wo, cout channels) with the channel-transposed, spatially mirrored weights, padding k-1-pad
+    const int taps = kh * kw;
+    const int ho = h + 2 * pad_h - kh + 1, wo = wd + 2 * pad_w - kw + 1;
+    return run_conv((const __half*)dy, (const __half*)w, (__half*)dx, n, groups, cout, cin, ho, wo, kh, kw, kh - 1 - pad_h, kw - 1 - pad_w,
+                    (int64_t)cout * cin * taps, taps, (int64_t)cin * taps, 1, workspace, workspace_bytes, (cudaStream_t)stream);
+}

@@ -55,6 +55,7 @@ _SIGNATURES = {
     'lvg_fma': (_c_int, [_c_void_p] * 4 + [_c_int, _c_int, _I64x6, _I64x6, _I64x6, _I64x6, _c_void_p]),
     'lvg_conv2d_fprop': (_c_int, [_c_void_p] * 3 + [_c_int] * 12 + [_c_void_p, _c_i64, _c_void_p]),
     'lvg_conv2d_fprop_workspace': (_c_i64, [_c_int] * 12),
+    'lvg_conv2d_dgrad': (_c_int, [_c_void_p] * 3 + [_c_int] * 12 + [_c_void_p, _c_i64, _c_void_p]),
 }
 
 LVG_UNSUPPORTED = -1
@@ -421,7 +422,69 @@ class FmaPlugin:
         return out
 
 
+class Conv2dPlugin:
+    """Tensor-core convolution behind conv2d_gradfix.conv2d (no reference plugin: the reference calls cuDNN)."""
+
+    def __init__(self, lib):
+        self._lib = lib
+        self._ws = {}
+
+    def supported(self, x, w, stride, padding, dilation, groups):
+        if not (x.is_cuda and x.dtype == torch.float16 and w.dtype == torch.float16 and x.ndim == 4 and w.ndim == 4):
+            return False
+        if tuple(stride) != (1, 1) or tuple(dilation) != (1, 1):
+            return False
+        kh, kw = w.shape[2], w.shape[3]
+        if (kh, kw) not in ((3, 3), (1, 1)) or min(padding) < 0:
+            return False
+        if x.shape[1] != w.shape[1] * groups or w.shape[0] % groups != 0:
+            return False
+        return x.shape[0] * groups <= 65535 and x.shape[2] + 2 * padding[0] >= kh and x.shape[3] + 2 * padding[1] >= kw
+
+    def _workspace(self, x, n, groups, cin, cout, h, wd, kh, kw, ph, pw):
+        need = self._lib.lvg_conv2d_fprop_workspace(1, n, groups, cin, cout, h, wd, kh, kw, 1, ph, pw)
+        if need < 0:
+            raise RuntimeError('conv2d: configuration outside the tensor-core kernel envelope')
+        key = x.device
+        buf = self._ws.get(key)
+        if buf is None or buf.numel() < need:
+            buf = torch.empty(max(int(need), 1 << 20), dtype=torch.uint8, device=x.device)
+            self._ws[key] = buf     # stream-ordered reuse: every call repacks before it reads
+        return buf, need
+
+    def fprop(self, x, w, padding, groups):
+        x, w = x.contiguous(), w.contiguous()
+        n, ctot, h, wd = x.shape
+        cout_tot, cin, kh, kw = w.shape
+        ph, pw = padding
+        cout = cout_tot // groups
+        y = torch.empty([n, cout_tot, h + 2 * ph - kh + 1, wd + 2 * pw - kw + 1], dtype=x.dtype, device=x.device)
+        ws, need = self._workspace(x, n, groups, cin, cout, h, wd, kh, kw, ph, pw)
+        with _DeviceGuard(x):
+            rc = _check(self._lib.lvg_conv2d_fprop(_ptr(x), _ptr(w), _ptr(y), 1, n, groups, cin, cout, h, wd, kh, kw, 1, ph, pw,
+                                                   _ptr(ws), ws.numel(), _stream(x)), 'conv2d_fprop')
+        if rc == LVG_UNSUPPORTED:
+            raise RuntimeError('conv2d_fprop: ' + self._lib.lvg_last_error().decode())
+        return y
+
+    def dgrad(self, dy, w, x_shape, padding, groups):
+        dy, w = dy.contiguous(), w.contiguous()
+        n, ctot, h, wd = x_shape
+        cout_tot, cin, kh, kw = w.shape
+        ph, pw = padding
+        cout = cout_tot // groups
+        dx = torch.empty(list(x_shape), dtype=dy.dtype, device=dy.device)
+        ws, need = self._workspace(dy, n, groups, cin, cout, h, wd, kh, kw, ph, pw)
+        with _DeviceGuard(dy):
+            rc = _check(self._lib.lvg_conv2d_dgrad(_ptr(dy), _ptr(w), _ptr(dx), 1, n, groups, cin, cout, h, wd, kh, kw, 1, ph, pw,
+                                                   _ptr(ws), ws.numel(), _stream(dy)), 'conv2d_dgrad')
+        if rc == LVG_UNSUPPORTED:
+            raise RuntimeError('conv2d_dgrad: ' + self._lib.lvg_last_error().decode())
+        return dx
+
+
 _PLUGIN_CLASSES = {
+    'conv2d_plugin': Conv2dPlugin,
     'bias_act_plugin': BiasActPlugin,
     'upfirdn2d_plugin': Upfirdn2dPlugin,
     'filtered_lrelu_plugin': FilteredLReluPlugin,

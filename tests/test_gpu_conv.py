@@ -1,0 +1,95 @@
+"""The tcgen05 implicit-GEMM convolution (conv2d_gradfix.conv2d -> lvg_conv2d_fprop / lvg_conv2d_dgrad)
+against torch's own convolution evaluated in fp32 on the same fp16-rounded operands."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import oracle as orc
+from torch_utils.ops import conv2d_gradfix, conv2d_resample
+from _common import assert_close, golden, cases, t
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+TOL = 2e-3          # fp16 output rounding (4.9e-4) + fp32 accumulation order; relative to max |ref|
+
+CASES = [
+    # (n, groups, cin, cout, h, w, k, pad)
+    (1, 3, 27, 40, 29, 36, 3, 2),       # sres L0-like: cin not a multiple of 16, one m-tile
+    (1, 2, 64, 200, 31, 38, 3, 2),      # two m-tiles, the second partial
+    (1, 4, 155, 3, 20, 40, 1, 0),       # ToRGB 1x1
+    (1, 2, 48, 128, 58, 86, 3, 2),      # two x tiles
+    (3, 1, 32, 64, 16, 16, 3, 1),       # discriminator style: batch shares the weights, pad 1 (odd row start)
+    (2, 2, 16, 16, 9, 7, 3, 0),         # tiny odd image, batch and groups
+    (1, 1, 16, 128, 70, 150, 3, 1),     # several tiles in both directions
+]
+
+
+@pytest.fixture(autouse=True)
+def native_on():
+    conv2d_gradfix.install_native(True)
+    yield
+    conv2d_gradfix.install_native(True)
+
+
+@pytest.mark.parametrize('n,g,cin,cout,h,w,k,pad', CASES)
+def test_conv2d_forward_and_input_gradient(n, g, cin, cout, h, w, k, pad):
+    gen = torch.Generator().manual_seed(n * 1000 + cin)
+    x = torch.randn(n, g * cin, h, w, generator=gen).half().to(DEV).requires_grad_(True)
+    wt = (torch.randn(g * cout, cin, k, k, generator=gen) / np.sqrt(cin * k * k)).half().to(DEV).requires_grad_(True)
+    assert conv2d_gradfix._native.supported(x, wt, (1, 1), (pad, pad), (1, 1), g)
+    y = conv2d_gradfix.conv2d(x, wt, padding=pad, groups=g)
+    ref = F.conv2d(x.detach().float(), wt.detach().float(), padding=pad, groups=g)
+    assert y.dtype == torch.float16 and y.shape == ref.shape
+    assert_close(y, ref, TOL, 'fprop')
+    dy = torch.randn(*y.shape, generator=gen).half().to(DEV)
+    dx, dw = torch.autograd.grad(y, [x, wt], dy)
+    xr, wr = x.detach().float().requires_grad_(True), wt.detach().float().requires_grad_(True)
+    rdx, rdw = torch.autograd.grad(F.conv2d(xr, wr, padding=pad, groups=g), [xr, wr], dy.float())
+    assert_close(dx, rdx, TOL, 'dgrad')
+    assert_close(dw, rdw, 5e-3, 'wgrad')
+
+
+def test_conv2d_against_cpu_oracle():
+    gen = torch.Generator().manual_seed(7)
+    x = torch.randn(1, 2 * 20, 13, 18, generator=gen).half()
+    wt = (torch.randn(2 * 24, 20, 3, 3, generator=gen) / 13).half()
+    y = conv2d_gradfix.conv2d(x.to(DEV), wt.to(DEV), padding=2, groups=2)
+    assert_close(y, orc.conv2d(x.float().numpy(), wt.float().numpy(), padding=2, groups=2), TOL)
+
+
+def test_conv2d_double_backward_matches_torch():
+    # R1-style: gradient of |d y / d x|^2 with respect to the weights and dy
+    gen = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 16, 12, 12, generator=gen).half().to(DEV).requires_grad_(True)
+    wt = (torch.randn(32, 16, 3, 3, generator=gen) / 12).half().to(DEV).requires_grad_(True)
+    y = conv2d_gradfix.conv2d(x, wt, padding=1)
+    gx, = torch.autograd.grad(y.float().square().sum(), [x], create_graph=True)
+    gw, = torch.autograd.grad(gx.float().square().sum(), [wt])
+    xr, wr = x.detach().float().requires_grad_(True), wt.detach().float().requires_grad_(True)
+    yr = F.conv2d(xr, wr, padding=1)
+    gxr, = torch.autograd.grad(yr.square().sum(), [xr], create_graph=True)
+    gwr, = torch.autograd.grad(gxr.square().sum(), [wr])
+    assert_close(gx, gxr, 5e-3, 'first order')
+    assert_close(gw, gwr, 2e-2, 'second order')
+
+
+def test_unsupported_shapes_use_the_library_path():
+    x = torch.randn(1, 8, 16, 16, device=DEV)                       # fp32: outside the envelope
+    w = torch.randn(8, 8, 3, 3, device=DEV)
+    assert not conv2d_gradfix._native.supported(x, w, (1, 1), (1, 1), (1, 1), 1)
+    assert torch.equal(conv2d_gradfix.conv2d(x, w, padding=1), F.conv2d(x, w, padding=1))
+    xh, wh = x.half(), w.half()
+    assert not conv2d_gradfix._native.supported(xh, wh, (2, 2), (1, 1), (1, 1), 1)    # strided
+
+
+_CV = golden('conv')
+
+
+@pytest.mark.parametrize('name', ['plain_3x3', 'fromrgb_1x1', 'grouped_mod'])
+def test_conv2d_resample_fp16_through_native_conv(name):
+    xs, ws, kw, has_f = cases(_CV)[name]
+    x, w = t(_CV[f'{name}/x'], DEV, torch.float16), t(_CV[f'{name}/w'], DEV, torch.float16)
+    y = conv2d_resample.conv2d_resample(x, w, **kw)
+    ref = conv2d_resample.conv2d_resample(x.float().cpu(), w.float().cpu(), **kw)
+    assert_close(y, ref, 3e-3, name)
