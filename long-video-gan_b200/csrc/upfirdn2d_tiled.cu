@@ -40,6 +40,7 @@ struct TiledParams {
     float gain;
     int tow, toh, tiles_x, tiles_y;
     int pb;               // planes per CTA (> 1 only when one tile covers the whole plane)
+    int flat;             // 1: the CTA's input planes are one contiguous, 16-byte aligned block (vector loader)
     int64_t planes;       // n * c
     int p_in, p_mid;      // row pitches (odd)
     int a_size;           // floats reserved for the input tile(s)
@@ -118,38 +119,61 @@ __global__ void __launch_bounds__(kThreads) upfirdn2d_tiled_kernel(TiledParams p
         in_h = toh_e;
     }
 
-    // ---- input tile(s), zero outside the image. One warp per row, lanes along the row (coalesced);
-    // kRows rows are in flight per warp before the first shared-memory store, and all the per-row
-    // index arithmetic is warp-uniform (one division per row, not per element).
-    {
+    // ---- input tile(s), zero outside the image
+    if (p.flat) {
+        // Whole planes, contiguous in memory: zero the tile, then stream the planes with 128-bit loads
+        // (4 vectors in flight per thread) and scatter the elements that fall inside the tile.
+        constexpr int V = VecOf<T>::N;
+        const int tile_floats = npl * in_h * p.p_in;
+        for (int i = threadIdx.x; i < tile_floats; i += kThreads) tin[i] = 0.f;
+        __syncthreads();
+        const T* xp = (const T*)p.x + xoff0;
+        const int plane_elems = p.ih * p.iw;
+        const int nvec = npl * plane_elems / V;
+        const fir::FastDiv by_plane(plane_elems), by_w(p.iw);
+        constexpr int kBatch = 4;
+        for (int base = threadIdx.x; base < nvec; base += kThreads * kBatch) {
+            Pack<T> v[kBatch];
+#pragma unroll
+            for (int j = 0; j < kBatch; j++) {
+                const int vi = base + j * kThreads;
+                if (vi < nvec) v[j] = load_pack(xp + (int64_t)vi * V);
+            }
+#pragma unroll
+            for (int j = 0; j < kBatch; j++) {
+                const int vi = base + j * kThreads;
+                if (vi < nvec) {
+                    const int e = vi * V;
+                    const int pl = by_plane.div(e);
+                    const int rem = e - pl * plane_elems;
+                    const int gy = by_w.div(rem);
+                    const int gx = rem - gy * p.iw;
+                    const int iy = gy - in_y0, ix = gx - in_x0;
+                    if (iy >= 0 && iy < in_h) {
+                        float* dst = tin + (pl * in_h + iy) * p.p_in + ix;
+#pragma unroll
+                        for (int k = 0; k < V; k++)
+                            if (ix + k >= 0 && ix + k < in_w) dst[k] = to_acc(v[j].v[k]);
+                    }
+                }
+            }
+        }
+    } else {
+        // general case: one warp per row, lanes along the row
         const T* xp = (const T*)p.x + xoff0;
         const int rows = npl * in_h;
         const fir::FastDiv by_h(in_h);
-        constexpr int kRows = 8;
         const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-        for (int r0 = warp * kRows; r0 < rows; r0 += (kThreads / 32) * kRows) {
-            const T* src[kRows];
-            bool ok[kRows];
-#pragma unroll
-            for (int j = 0; j < kRows; j++) {
-                const int r = r0 + j;
-                const int pl = npl > 1 ? by_h.div(r) : 0;
-                const int gy = in_y0 + (r - pl * in_h);
-                ok[j] = r < rows && gy >= 0 && gy < p.ih;
-                src[j] = xp + (int64_t)pl * p.xs[1] + (int64_t)gy * p.xs[2];
-            }
+        for (int r = warp; r < rows; r += kThreads / 32) {
+            const int pl = npl > 1 ? by_h.div(r) : 0;
+            const int gy = in_y0 + (r - pl * in_h);
+            const bool rowok = gy >= 0 && gy < p.ih;
+            const T* xrow = xp + (int64_t)pl * p.xs[1] + (int64_t)gy * p.xs[2];
             for (int ix = lane; ix < in_w; ix += 32) {
                 const int gx = in_x0 + ix;
-                const bool colok = gx >= 0 && gx < p.iw;
-                float v[kRows];
-#pragma unroll
-                for (int j = 0; j < kRows; j++) {
-                    v[j] = 0.f;
-                    if (ok[j] && colok) v[j] = to_acc(src[j][(int64_t)gx * p.xs[3]]);
-                }
-#pragma unroll
-                for (int j = 0; j < kRows; j++)
-                    if (r0 + j < rows) tin[(r0 + j) * p.p_in + ix] = v[j];
+                float v = 0.f;
+                if (rowok && gx >= 0 && gx < p.iw) v = to_acc(xrow[(int64_t)gx * p.xs[3]]);
+                tin[r * p.p_in + ix] = v;
             }
         }
     }
@@ -168,20 +192,20 @@ __global__ void __launch_bounds__(kThreads) upfirdn2d_tiled_kernel(TiledParams p
     }
 
     // ---- y pass -> global
-    T* yp = (T*)p.y + yoff0;
+    T* yp = (T*)p.y + yoff0 + (int64_t)oy0 * p.ys[2] + (int64_t)ox0 * p.ys[3];
     const float gain = p.gain;
     const float* src = tmid + dxo;
+    const int64_t ys1 = p.ys[1], ys2 = p.ys[2], ys3 = p.ys[3];
     if constexpr (KY == AX_UP) {
         fir::up_y<SY, FY, kR, kThreads>(src, pmid, tow_e, nqy, s_fy,
             [&](int pl, int a, int col, float acc) {
                 const int o = a - dyo;
-                if (o >= 0 && o < toh_e)
-                    yp[(int64_t)pl * p.ys[1] + (int64_t)(oy0 + o) * p.ys[2] + (int64_t)(ox0 + col) * p.ys[3]] = from_acc<T>(acc * gain);
+                if ((unsigned)o < (unsigned)toh_e) yp[pl * ys1 + col * ys3 + o * ys2] = from_acc<T>(acc * gain);
             }, npl, in_h);
     } else if constexpr (KY == AX_DOWN) {
         fir::down_y<SY, FY, kR, kThreads>(src, pmid, 0, tow_e, toh_e, s_fy,
             [&](int pl, int o, int col, float acc) {
-                yp[(int64_t)pl * p.ys[1] + (int64_t)(oy0 + o) * p.ys[2] + (int64_t)(ox0 + col) * p.ys[3]] = from_acc<T>(acc * gain);
+                yp[pl * ys1 + col * ys3 + o * ys2] = from_acc<T>(acc * gain);
             }, npl, in_h);
     } else {
         const int per = toh_e * tow_e;
@@ -190,16 +214,15 @@ __global__ void __launch_bounds__(kThreads) upfirdn2d_tiled_kernel(TiledParams p
             const int pl = npl > 1 ? by_per.div(idx) : 0;
             const int rem = idx - pl * per;
             const int o = by_w.div(rem), col = rem - o * tow_e;
-            yp[(int64_t)pl * p.ys[1] + (int64_t)(oy0 + o) * p.ys[2] + (int64_t)(ox0 + col) * p.ys[3]] =
-                from_acc<T>(src[(pl * in_h + o) * pmid + col] * gain);
+            yp[pl * ys1 + o * ys2 + col * ys3] = from_acc<T>(src[(pl * in_h + o) * pmid + col] * gain);
         }
     }
 }
 
-// widest tile <= 128 that wastes the fewest lanes of the 32-wide column chunks
+// whole rows up to 256 pixels, else the widest tile <= 128 that wastes the fewest lanes of the 32-wide column chunks
 int pick_tow(int ow)
 {
-    if (ow <= 128) return ow;
+    if (ow <= 256) return ow;
     int best = 64, best_waste = INT32_MAX;
     for (int cand = 128; cand >= 64; cand -= 32) {
         const int tiles = (ow + cand - 1) / cand;
@@ -213,7 +236,7 @@ int pick_tow(int ow)
 template <class T, int KX, int SX, int FX, int KY, int SY, int FY>
 int launch_tiled(TiledParams& p, cudaStream_t s)
 {
-    constexpr int kTargetOutputs = 4096;        // outputs per CTA the tile/plane batching aims for
+    constexpr int kTargetOutputs = 8192;        // outputs per CTA the tile/plane batching aims for
     constexpr size_t kSmemBudget = 56 * 1024;   // keeps 4 CTAs resident per SM
     p.tow = pick_tow(p.ow);
     int toh = kTargetOutputs / (p.tow > 0 ? p.tow : 1);
@@ -248,6 +271,10 @@ int launch_tiled(TiledParams& p, cudaStream_t s)
         p.pb = pb;
         smem = smem_for(p.toh, p.pb);
     }
+    // vector loader: whole contiguous planes, rows a multiple of the 16-byte vector, aligned base
+    constexpr int V = VecOf<T>::N;
+    p.flat = (p.tiles_x == 1 && p.tiles_y == 1 && p.xs[3] == 1 && p.xs[2] == p.iw && p.xs[1] == (int64_t)p.ih * p.iw &&
+              (p.pb == 1 || uniform) && p.iw % V == 0 && p.xs[0] % V == 0 && aligned16(p.x) && (int64_t)p.pb * p.ih * p.iw < (1 << 24)) ? 1 : 0;
     const int64_t blocks = p.pb > 1 ? (p.planes + p.pb - 1) / p.pb : p.planes * p.tiles_x * p.tiles_y;
     if (blocks > INT32_MAX) return LVG_UNSUPPORTED;
     auto k = upfirdn2d_tiled_kernel<T, KX, SX, FX, KY, SY, FY>;
