@@ -30,9 +30,17 @@ struct BiasActParams {
     int64_t n;
     int64_t size_b;
     int64_t step_b;
+    uint64_t magic_step, magic_size;   // ceil(2^64 / d): exact quotients for operands < 2^32 (0 = divide for real)
     int grad;
     float alpha, gain, clamp;
 };
+
+// n / d through a multiply-high when the host could prepare a magic number (n, d < 2^32)
+__device__ __forceinline__ int64_t fast_div(int64_t n, int64_t d, uint64_t magic)
+{
+    if (d == 1) return n;
+    return magic ? (int64_t)__umul64hi((uint64_t)n, magic) : n / d;
+}
 
 // How the bias index of a 16-byte pack is obtained.
 enum BiasMode {
@@ -41,6 +49,13 @@ enum BiasMode {
     BIAS_PACKED = 2,     // step_b == 1 and size_b multiple of the pack width: load a bias pack
     BIAS_PER_ELEM = 3,   // anything else
 };
+
+__device__ __forceinline__ int64_t bias_row(int64_t elem, const BiasActParams& p) { return fast_div(elem, p.step_b, p.magic_step); }
+__device__ __forceinline__ int64_t bias_index(int64_t elem, const BiasActParams& p)
+{
+    const int64_t row = bias_row(elem, p);
+    return row - fast_div(row, p.size_b, p.magic_size) * p.size_b;
+}
 
 template <class S> __device__ __forceinline__ S fexp(S v);
 template <> __device__ __forceinline__ float fexp<float>(float v) { return expf(v); }
@@ -119,26 +134,25 @@ constexpr int kUnroll = 4;
 
 template <class T>
 __device__ __forceinline__ void fetch_bias(typename Acc<T>::type (&bias)[VecOf<T>::N], int64_t& bidx,
-                                           const T* __restrict__ pb, int bmode, int64_t e0,
-                                           int64_t step_b, int64_t size_b)
+                                           const T* __restrict__ pb, int bmode, int64_t e0, const BiasActParams& p)
 {
     typedef typename Acc<T>::type S;
     constexpr int N = VecOf<T>::N;
     bidx = 0;
     if (bmode == BIAS_PER_PACK) {
-        bidx = (e0 / step_b) % size_b;
+        bidx = bias_index(e0, p);
         S bv = pb ? to_acc(pb[bidx]) : (S)0;
 #pragma unroll
         for (int k = 0; k < N; k++) bias[k] = bv;
     } else if (bmode == BIAS_PACKED) {
-        bidx = e0 % size_b;
+        bidx = e0 - fast_div(e0, p.size_b, p.magic_size) * p.size_b;
         Pack<T> vb;
         if (pb) vb = load_pack(pb + bidx);
 #pragma unroll
         for (int k = 0; k < N; k++) bias[k] = pb ? to_acc(vb.v[k]) : (S)0;
     } else if (bmode == BIAS_PER_ELEM) {
 #pragma unroll
-        for (int k = 0; k < N; k++) bias[k] = pb ? to_acc(pb[((e0 + k) / step_b) % size_b]) : (S)0;
+        for (int k = 0; k < N; k++) bias[k] = pb ? to_acc(pb[bias_index(e0 + k, p)]) : (S)0;
     } else {
 #pragma unroll
         for (int k = 0; k < N; k++) bias[k] = (S)0;
@@ -174,7 +188,7 @@ __global__ void __launch_bounds__(kThreads, (G == 2 ? 2 : 4)) bias_act_vec_kerne
     for (int64_t base = (int64_t)blockIdx.x * tile; base < n_pack; base += (int64_t)gridDim.x * tile) {
         Pack<T> vx[kUnroll], vref[kUnroll], vdy[kUnroll];
         const T* __restrict__ pref = kUseX ? pxr : pyr;
-        const int64_t row0 = (FUSE_DB && bmode == BIAS_PER_PACK) ? (base * N) / p.step_b : 0;
+        const int64_t row0 = (FUSE_DB && bmode == BIAS_PER_PACK) ? bias_row(base * N, p) : 0;
         if (FUSE_DB && bmode == BIAS_PER_PACK) {
             if (threadIdx.x < kBins) s_bins[threadIdx.x] = 0.f;
             __syncthreads();
@@ -197,30 +211,37 @@ __global__ void __launch_bounds__(kThreads, (G == 2 ? 2 : 4)) bias_act_vec_kerne
                 const int64_t e0 = pk * N;
                 S bias[N];
                 int64_t bidx;
-                fetch_bias<T>(bias, bidx, pb, bmode, e0, p.step_b, p.size_b);
+                fetch_bias<T>(bias, bidx, pb, bmode, e0, p);
 
-                Pack<T> out;
-                S dbsum = (S)0;
+                S fx[N], fref[N], fdy[N], fo[N];
+                unpack<T>(vx[u], fx);
+                if ((kUseX || kUseY) && pref) unpack<T>(vref[u], fref);
+                if (kUseDy && pdy) unpack<T>(vdy[u], fdy);
 #pragma unroll
                 for (int k = 0; k < N; k++) {
-                    S v = to_acc(vx[u].v[k]);
-                    S xr = (kUseX && pref) ? to_acc(vref[u].v[k]) : (S)0;
-                    S yr = (kUseY && pref) ? to_acc(vref[u].v[k]) : (S)0;
-                    S dyv = (kUseDy && pdy) ? to_acc(vdy[u].v[k]) : (S)1;
+                    S v = fx[k];
+                    S xr = (kUseX && pref) ? fref[k] : (S)0;
+                    S yr = (kUseY && pref) ? fref[k] : (S)0;
+                    S dyv = (kUseDy && pdy) ? fdy[k] : (S)1;
                     if (G == 0) v += bias[k]; else xr += bias[k];
-                    S o = bias_act_elem<S, A>(v, xr, yr, dyv, G, alpha, gain, inv_gain, clamp);
-                    out.v[k] = from_acc<T>(o);
-                    if (FUSE_DB) {
-                        // accumulate what was actually stored, like dx.sum() would see it
-                        S stored = to_acc(out.v[k]);
-                        if (bmode == BIAS_PER_PACK) dbsum += stored;
-                        else if (bmode == BIAS_PACKED) atomicAdd(p.db + bidx + k, (float)stored);
-                        else atomicAdd(p.db + ((e0 + k) / p.step_b) % p.size_b, (float)stored);
+                    fo[k] = bias_act_elem<S, A>(v, xr, yr, dyv, G, alpha, gain, inv_gain, clamp);
+                }
+                const Pack<T> out = pack<T>(fo);
+                S dbsum = (S)0;
+                if (FUSE_DB) {
+                    // accumulate what was actually stored, like dx.sum() would see it
+                    S fs[N];
+                    unpack<T>(out, fs);
+#pragma unroll
+                    for (int k = 0; k < N; k++) {
+                        if (bmode == BIAS_PER_PACK) dbsum += fs[k];
+                        else if (bmode == BIAS_PACKED) atomicAdd(p.db + bidx + k, (float)fs[k]);
+                        else atomicAdd(p.db + bias_index(e0 + k, p), (float)fs[k]);
                     }
                 }
                 store_pack(py + e0, out);
 
-                if (FUSE_DB && bmode == BIAS_PER_PACK) { db_rel = e0 / p.step_b - row0; db_val = (float)dbsum; db_idx = bidx; }
+                if (FUSE_DB && bmode == BIAS_PER_PACK) { db_rel = bias_row(e0, p) - row0; db_val = (float)dbsum; db_idx = bidx; }
             }
             if (FUSE_DB && bmode == BIAS_PER_PACK) {
                 // whole-warp combine (lanes past the end contribute 0): lane 0 holds the smallest pack index,
@@ -261,7 +282,7 @@ __global__ void __launch_bounds__(kThreads) bias_act_scalar_kernel(BiasActParams
     const S inv_gain = gain != (S)0 ? (S)1 / gain : (S)0;
     for (int64_t i = first + (int64_t)blockIdx.x * kThreads + threadIdx.x; i < p.n; i += (int64_t)gridDim.x * kThreads) {
         S v = to_acc(((const T*)p.x)[i]);
-        int64_t bidx = (p.b || FUSE_DB) ? (i / p.step_b) % p.size_b : 0;
+        int64_t bidx = (p.b || FUSE_DB) ? bias_index(i, p) : 0;
         S bias = p.b ? to_acc(((const T*)p.b)[bidx]) : (S)0;
         S xr = p.xref ? to_acc(((const T*)p.xref)[i]) : (S)0;
         S yr = p.yref ? to_acc(((const T*)p.yref)[i]) : (S)0;
@@ -338,6 +359,12 @@ int launch_act(int act, const BiasActParams& p, cudaStream_t s)
     return LVG_ERR_ARG;
 }
 
+uint64_t magic_for(int64_t d, int64_t n)
+{
+    if (d <= 1 || d >= (1ll << 32) || n >= (1ll << 32)) return 0;
+    return (uint64_t)(~0ull / (uint64_t)d) + 1;      // ceil(2^64 / d) for d that is not a power of two; exact enough otherwise too
+}
+
 int check_common(const void* x, const void* y, int dtype, int64_t n, const void* b, int64_t size_b, int64_t step_b, int act)
 {
     LVG_REQUIRE(x && y, "bias_act: x and y must not be NULL");
@@ -362,7 +389,8 @@ extern "C" int lvg_bias_act(const void* x, const void* b, const void* xref, cons
     if (rc) return rc;
     LVG_REQUIRE(grad >= 0 && grad <= 2, "bias_act: grad must be 0, 1 or 2 (got %d)", grad);
     if (n == 0) return LVG_OK;
-    BiasActParams p = {x, b, xref, yref, dy, y, nullptr, n, b ? size_b : 1, b ? step_b : 1, grad, alpha, gain, clamp};
+    BiasActParams p = {x, b, xref, yref, dy, y, nullptr, n, b ? size_b : 1, b ? step_b : 1, 0, 0, grad, alpha, gain, clamp};
+    p.magic_step = magic_for(p.step_b, n); p.magic_size = magic_for(p.size_b, n);
     cudaStream_t s = (cudaStream_t)stream;
     if (dtype == LVG_F32) return launch_act<float, false>(act, p, s);
     if (dtype == LVG_F16) return launch_act<__half, false>(act, p, s);
@@ -381,7 +409,8 @@ extern "C" int lvg_bias_act_grad_db(const void* dy_in, const void* b, const void
     LVG_REQUIRE(dtype == LVG_F32 || dtype == LVG_F16, "bias_act_grad_db: fp32/fp16 only");
     if (n == 0) return LVG_OK;
     // b may be NULL here (bias values are only needed by swish); the index math still applies.
-    BiasActParams p = {dy_in, b, xref, yref, nullptr, dx, db_f32, n, size_b, step_b, 1, alpha, gain, clamp};
+    BiasActParams p = {dy_in, b, xref, yref, nullptr, dx, db_f32, n, size_b, step_b, 0, 0, 1, alpha, gain, clamp};
+    p.magic_step = magic_for(p.step_b, n); p.magic_size = magic_for(p.size_b, n);
     cudaStream_t s = (cudaStream_t)stream;
     if (dtype == LVG_F32) return launch_act<float, true>(act, p, s);
     return launch_act<__half, true>(act, p, s);

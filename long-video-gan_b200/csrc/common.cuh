@@ -94,6 +94,30 @@ template <class T> __device__ __forceinline__ void store_pack(T* p, const Pack<T
     *reinterpret_cast<uint4*>(p) = *reinterpret_cast<const uint4*>(&v);
 }
 
+// whole-pack conversions; fp16 goes through the paired cvt instructions (half2 <-> float2)
+template <class T> __device__ __forceinline__ void unpack(const Pack<T>& p, typename Acc<T>::type (&f)[VecOf<T>::N]) {
+#pragma unroll
+    for (int k = 0; k < VecOf<T>::N; k++) f[k] = to_acc(p.v[k]);
+}
+template <> __device__ __forceinline__ void unpack<__half>(const Pack<__half>& p, float (&f)[8]) {
+    const __half2* h = reinterpret_cast<const __half2*>(&p);
+#pragma unroll
+    for (int k = 0; k < 4; k++) { const float2 t = __half22float2(h[k]); f[2 * k] = t.x; f[2 * k + 1] = t.y; }
+}
+template <class T> __device__ __forceinline__ Pack<T> pack(const typename Acc<T>::type (&f)[VecOf<T>::N]) {
+    Pack<T> p;
+#pragma unroll
+    for (int k = 0; k < VecOf<T>::N; k++) p.v[k] = from_acc<T>(f[k]);
+    return p;
+}
+template <> __device__ __forceinline__ Pack<__half> pack<__half>(const float (&f)[8]) {
+    Pack<__half> p;
+    __half2* h = reinterpret_cast<__half2*>(&p);
+#pragma unroll
+    for (int k = 0; k < 4; k++) h[k] = __floats2half2_rn(f[2 * k], f[2 * k + 1]);
+    return p;
+}
+
 __host__ __device__ __forceinline__ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 // floor division / positive modulo for possibly negative numerators

@@ -99,15 +99,20 @@ def main():
             del x, y
     # the conv boundary as the reference runs it today (cuDNN grouped conv through F.conv2d), for orientation
     for name, nt, cin, cout, h, w in (('L4 539->512 38x52', 64, 539, 512, 38, 52), ('L8 539->512 92x148', 16, 539, 512, 92, 148),
-                                      ('L12 208->128 164x276', 16, 208, 128, 164, 276)):
+                                      ('L12 208->128 164x276', 16, 208, 128, 164, 276), ('L12 208->128 164x276', 4, 208, 128, 164, 276),
+                                      ('L10 389->256 92x148', 16, 389, 256, 92, 148), ('L0 27->512 29x36', 64, 27, 512, 29, 36)):
         if pat not in 'conv2d cudnn':
             continue
+        from torch_utils.ops import conv2d_gradfix
         x = torch.randn(1, nt * cin, h, w, device=DEV, dtype=torch.float16)
         wt = torch.randn(nt * cout, cin, 3, 3, device=DEV, dtype=torch.float16) / 70
-        fn = lambda: torch.nn.functional.conv2d(x, wt, padding=2, groups=nt)
-        ms = timeit(fn)
         flops = 2.0 * nt * cout * cin * 9 * (h + 2) * (w + 2)
-        print(f'conv2d cudnn grouped fp16 {name} NT={nt}: {ms:8.3f} ms {flops / ms / 1e9:8.1f} TFLOP/s', flush=True)
+        conv2d_gradfix.install_native(True)
+        ms = timeit(lambda: conv2d_gradfix.conv2d(x, wt, padding=2, groups=nt))
+        print(f'conv2d tcgen05 grouped fp16 {name} NT={nt}: {ms:8.3f} ms {flops / ms / 1e9:8.1f} TFLOP/s', flush=True)
+        if not (cin == 208 and nt > 4):     # cuDNN takes ~0.2 s on this shape: time it once at small NT only
+            ms = timeit(lambda: torch.nn.functional.conv2d(x, wt, padding=2, groups=nt), iters=3, warmup=1)
+            print(f'conv2d cudnn   grouped fp16 {name} NT={nt}: {ms:8.3f} ms {flops / ms / 1e9:8.1f} TFLOP/s', flush=True)
         del x, wt
     os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
     json.dump(rows, open(os.path.join(ROOT, 'gpurun_out', 'microbench.json'), 'w'), indent=1)
