@@ -43,7 +43,7 @@ WORKLOADS = {
     'sres': ('sres_step.json', 'sres_G', 'sres_D', 16, 8),
 }
 GRAD_ELEMS = {'lres': (83_200_000, 46_400_000), 'sres': (27_200_000, 24_000_000)}   # G, D parameter counts
-HOT_OPS = ('bias_act', 'upfirdn2d', 'filtered_lrelu', 'conv2d_resample')
+HOT_OPS = ('bias_act', 'upfirdn2d', 'filtered_lrelu', 'conv2d_resample', 'conv2d')
 
 
 def load_trace(name):
@@ -69,14 +69,24 @@ def scaled(shape, batch):
 
 class Replay:
     def __init__(self, calls, batch, device, dtype_policy):
-        from torch_utils.ops import bias_act, upfirdn2d, filtered_lrelu, conv2d_resample
-        self.ops = dict(bias_act=bias_act, upfirdn2d=upfirdn2d, filtered_lrelu=filtered_lrelu, conv2d_resample=conv2d_resample)
+        from torch_utils.ops import bias_act, upfirdn2d, filtered_lrelu, conv2d_resample, conv2d_gradfix
+        self.ops = dict(bias_act=bias_act, upfirdn2d=upfirdn2d, filtered_lrelu=filtered_lrelu, conv2d_resample=conv2d_resample,
+                        conv2d=conv2d_gradfix)
         self.device = device
         self.pool = {}
         self.items = []
         gen = torch.Generator().manual_seed(0)
         for c in calls:
             dt = torch.float16 if (c.get('fp16') and dtype_policy == 'mixed') else torch.float32
+            if c['op'] == 'conv2d':
+                # modulated convolution: the batch lives in the groups (x [1, G*Cin, H, W], w [G*Cout, Cin, k, k])
+                xs = [1, c['x'][1] * batch] + list(c['x'][2:])
+                x = self._buf('x', xs, dt)
+                item = dict(c=c, x=x, dtype=dt, groups=c['groups'] * batch)
+                ws = [c['w'][0] * batch] + list(c['w'][1:])
+                item['w'] = (torch.randn(*ws, device=device) / np.sqrt(np.prod(c['w'][1:]))).to(dt)
+                self.items.append(item)
+                continue
             x = self._buf('x', scaled(c['x'], batch), dt)
             item = dict(c=c, x=x, dtype=dt)
             if c['op'] == 'bias_act':
@@ -117,6 +127,8 @@ class Replay:
             return self.ops['filtered_lrelu'].filtered_lrelu(x, fu=it['fu'], fd=it['fd'], b=it['b'], up=c['up'], down=c['down'],
                                                              padding=c['padding'], gain=c['gain'], slope=c['slope'],
                                                              clamp=c['clamp'], flip_filter=c['flip_filter'])
+        if c['op'] == 'conv2d':
+            return self.ops['conv2d'].conv2d(x, it['w'], padding=c['padding'], groups=it['groups'])
         return self.ops['conv2d_resample'].conv2d_resample(x, it['w'], f=it['f'], up=c['up'], down=c['down'], padding=c['padding'],
                                                            groups=c['groups'], flip_weight=c['flip_weight'], flip_filter=c['flip_filter'])
 
@@ -135,6 +147,10 @@ class Replay:
                 leaves.append(b)
             saved_b = it.get('b')
             it['b'] = b
+            saved_w = it.get('w')
+            if saved_w is not None:
+                it['w'] = saved_w.detach().requires_grad_(True)
+                leaves.append(it['w'])
             if timer is not None and it['c']['op'] == 'bias_act':
                 timer.start()
                 y = self._fwd(it, x)
@@ -148,6 +164,8 @@ class Replay:
                 if y.requires_grad:
                     torch.autograd.grad(y, leaves, it['dy'], allow_unused=True)
             it['b'] = saved_b
+            if saved_w is not None:
+                it['w'] = saved_w
 
 
 class KernelTimer:
@@ -237,7 +255,7 @@ def cpu_sample(workload, budget_s=20.0):
     g_calls, d_calls, batch, frames = load_trace(workload)
     gen = torch.Generator().manual_seed(0)
     rng = np.random.default_rng(0)
-    calls = [c for c in g_calls + d_calls if c['op'] != 'conv2d_resample']
+    calls = [c for c in g_calls + d_calls if c['op'] not in ('conv2d_resample', 'conv2d')]
     prepared = []
     for c in calls:
         item = {'c': c, 'x': rng.standard_normal(c['x'], dtype=np.float32)}

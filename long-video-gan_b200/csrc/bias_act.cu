@@ -408,6 +408,13 @@ extern "C" int lvg_bias_act_grad_db(const void* dy_in, const void* b, const void
     LVG_REQUIRE(size_b >= 1 && step_b >= 1, "bias_act_grad_db: needs size_b >= 1 and step_b >= 1");
     LVG_REQUIRE(dtype == LVG_F32 || dtype == LVG_F16, "bias_act_grad_db: fp32/fp16 only");
     if (n == 0) return LVG_OK;
+    // The fused reduction pays off when a 16-byte pack lies within one channel (bias along an outer
+    // dimension). With the bias along the contiguous dimension (fully connected layers) every element
+    // of a pack belongs to a different channel: leave that reduction to a separate pass.
+    if (step_b % (dtype == LVG_F16 ? 8 : 4) != 0) {
+        set_error("bias_act_grad_db: bias runs along the contiguous dimension; use bias_act(grad=1) + a reduction");
+        return LVG_UNSUPPORTED;
+    }
     // b may be NULL here (bias values are only needed by swish); the index math still applies.
     BiasActParams p = {dy_in, b, xref, yref, nullptr, dx, db_f32, n, size_b, step_b, 0, 0, 1, alpha, gain, clamp};
     p.magic_step = magic_for(p.step_b, n); p.magic_size = magic_for(p.size_b, n);

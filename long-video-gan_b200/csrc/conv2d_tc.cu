@@ -49,6 +49,7 @@ struct ConvParams {
     int th, wt;              // output tile: th rows x wt pixels (wt % 8 == 0, th * wt % 16 == 0, <= 256)
     int tiles_x, tiles_y;
     int kc, mt;              // k-chunks, m-tiles
+    int pair_ok;             // x is 4-byte aligned and rows have even length: pixel pairs can be loaded as one word
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -75,6 +76,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
             : "r"(addr), "r"(parity)
             : "memory");
     }
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// 1-D bulk copy global -> shared through the TMA engine; completion is signalled on `bar` (complete_tx)
+__device__ __forceinline__ void bulk_copy_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -175,7 +187,8 @@ __global__ void __launch_bounds__(kThreads, 2) conv_fprop_tc_kernel(ConvParams p
 {
     constexpr int TAPS = KH * KW;
     extern __shared__ __align__(128) unsigned char smem[];
-    __shared__ uint64_t mma_bar;
+    __shared__ uint64_t mma_bar;      // the MMAs of a k-chunk have finished reading shared memory
+    __shared__ uint64_t a_bar;        // the bulk copy of the chunk's weight tiles has landed
     __shared__ uint32_t tmem_base_slot;
 
     const int nch_row = p.wt / 8;                          // 16-byte chunks per tile row
@@ -195,6 +208,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_fprop_tc_kernel(ConvParams p
 
     if (threadIdx.x == 0) {
         mbar_init(&mma_bar, 1);
+        mbar_init(&a_bar, 1);
         fence_barrier_init();
     }
     if (warp == 0) tmem_alloc(&tmem_base_slot, 256);
@@ -212,37 +226,52 @@ __global__ void __launch_bounds__(kThreads, 2) conv_fprop_tc_kernel(ConvParams p
     for (int kci = 0; kci < p.kc; kci++) {
         if (kci > 0) mbar_wait(&mma_bar, (uint32_t)((kci - 1) & 1));   // the MMAs of the previous chunk have consumed the buffers
 
-        // ---- A: TAPS ready-made tile images, straight 16-byte copies
-        {
-            const uint4* src = reinterpret_cast<const uint4*>(wpg + (int64_t)kci * TAPS * kATileBytes);
-            uint4* dst = reinterpret_cast<uint4*>(sA);
-            for (int i = threadIdx.x; i < TAPS * kATileBytes / 16; i += kThreads) dst[i] = __ldg(src + i);
+        // ---- A: TAPS ready-made tile images = one contiguous block: a single TMA bulk copy (no LSU work)
+        if (threadIdx.x == 0) {
+            mbar_expect_tx(&a_bar, TAPS * kATileBytes);
+            bulk_copy_g2s(sA, wpg + (int64_t)kci * TAPS * kATileBytes, TAPS * kATileBytes, &a_bar);
         }
         // ---- B: item = (channel, row, chunk): 8 + KW - 1 pixels in, KW shifted 8-pixel chunks out
         {
             const int rows = p.th + KH - 1;
             const int items = kBK * rows * nch_row;
+            const bool paired = p.pair_ok && (ix0 & 1) == 0;  // rows and tile start are 4-byte aligned: half2 loads
             for (int it = threadIdx.x; it < items; it += kThreads) {
                 const int c = it % nch_row;
                 const int rr = (it / nch_row) % rows;
                 const int ch = it / (nch_row * rows);
                 const int ci = kci * kBK + ch;
                 const int gy = iy0 + rr;
-                __half px[8 + KW - 1];
                 const bool rowok = ci < p.cin && gy >= 0 && gy < p.h;
                 const __half* row = xg + ((int64_t)ci * p.h + gy) * p.w;
+                unsigned char* dst0 = sB + ((size_t)((ch / 8) * nch + rr * nch_row + c)) * 128 + (ch % 8) * 16;
+                constexpr int NPAIR = (8 + KW - 1 + 1) / 2;
+                uint32_t pr[NPAIR];      // pixel pairs (2q, 2q+1)
+                if (paired) {
 #pragma unroll
-                for (int i = 0; i < 8 + KW - 1; i++) {
-                    const int gx = ix0 + c * 8 + i;
-                    px[i] = (rowok && gx >= 0 && gx < p.w) ? row[gx] : __float2half(0.f);
+                    for (int q = 0; q < NPAIR; q++) {
+                        const int gx = ix0 + c * 8 + 2 * q;      // even: the pair is inside or outside the row together
+                        pr[q] = (rowok && gx >= 0 && gx < p.w) ? *reinterpret_cast<const uint32_t*>(row + gx) : 0u;
+                    }
+                } else {
+#pragma unroll
+                    for (int q = 0; q < NPAIR; q++) {
+                        const int gx = ix0 + c * 8 + 2 * q;
+                        const unsigned short lo = (rowok && gx >= 0 && gx < p.w) ? *reinterpret_cast<const unsigned short*>(row + gx) : (unsigned short)0;
+                        const unsigned short hi = (rowok && gx + 1 >= 0 && gx + 1 < p.w) ? *reinterpret_cast<const unsigned short*>(row + gx + 1) : (unsigned short)0;
+                        pr[q] = (uint32_t)lo | ((uint32_t)hi << 16);
+                    }
                 }
 #pragma unroll
                 for (int v = 0; v < KW; v++) {
-                    alignas(16) __half o[8];
-#pragma unroll
-                    for (int i = 0; i < 8; i++) o[i] = px[i + v];
-                    unsigned char* dst = sB + ((size_t)((v * 2 + ch / 8) * nch + rr * nch_row + c)) * 128 + (ch % 8) * 16;
-                    *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(o);
+                    uint4 o;
+                    if (v % 2 == 0) {
+                        o = make_uint4(pr[v / 2], pr[v / 2 + 1], pr[v / 2 + 2], pr[v / 2 + 3]);
+                    } else {        // odd shift: high half of pair j with low half of pair j+1
+                        o = make_uint4(__byte_perm(pr[v / 2], pr[v / 2 + 1], 0x5432), __byte_perm(pr[v / 2 + 1], pr[v / 2 + 2], 0x5432),
+                                       __byte_perm(pr[v / 2 + 2], pr[v / 2 + 3], 0x5432), __byte_perm(pr[v / 2 + 3], pr[v / 2 + 4], 0x5432));
+                    }
+                    *reinterpret_cast<uint4*>(dst0 + (size_t)(v * 2) * nch * 128) = o;
                 }
             }
         }
@@ -251,6 +280,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_fprop_tc_kernel(ConvParams p
         __syncthreads();
 
         if (threadIdx.x == 0) {
+            mbar_wait(&a_bar, (uint32_t)(kci & 1));
             tc_fence_after();
 #pragma unroll
             for (int tap = 0; tap < TAPS; tap++) {
@@ -345,6 +375,7 @@ int run_conv(const __half* x, const __half* w, __half* y, int n, int groups, int
     LVG_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "conv2d: workspace must be 16-byte aligned");
     p.wp = reinterpret_cast<const __half*>(workspace);
     pick_tile(p.ho, p.wo, p.th, p.wt, p.tiles_x, p.tiles_y);
+    p.pair_ok = ((reinterpret_cast<uintptr_t>(x) & 3) == 0 && (wd & 1) == 0) ? 1 : 0;
     LVG_REQUIRE((int64_t)n * groups <= 65535 && p.mt <= 65535, "conv2d: too many groups / channel tiles for one launch");
 
     {

@@ -118,6 +118,15 @@ extern "C" int lvg_upfirdn2d(const void* x, const float* f, void* y, int dtype,
     LVG_REQUIRE(f != nullptr, "upfirdn2d: f must not be NULL");
 
     // a filter spanning one axis only ([k, 1] temporal filters, [1, k]) is a 1-D pass: tiled kernel
+    if (fw == 1 && fh > 1 && upx == 1 && downx == 1 && x_shape[3] == 1 && y_shape[3] == 1) {
+        // [N, C, L, 1] tensors (the temporal embedding pyramid): the filtered axis is the contiguous one.
+        // Same op on the transposed view [N, C, 1, L] with the filter along x, so lanes run along L.
+        const int64_t xsh[4] = {x_shape[0], x_shape[1], 1, x_shape[2]}, xst[4] = {x_stride[0], x_stride[1], x_stride[3], x_stride[2]};
+        const int64_t ysh[4] = {y_shape[0], y_shape[1], 1, y_shape[2]}, yst[4] = {y_stride[0], y_stride[1], y_stride[3], y_stride[2]};
+        rc = upfirdn2d_tiled(x, f, f_stride_y, nullptr, 1, y, dtype, xsh, xst, ysh, yst, fh, 1, upy, 1, downy, 1, pady0, 0,
+                             flip, gain, (cudaStream_t)stream);
+        if (rc != LVG_UNSUPPORTED) return rc;
+    }
     if ((fw == 1) != (fh == 1) && ((fw == 1 && upx == 1 && downx == 1) || (fh == 1 && upy == 1 && downy == 1))) {
         rc = upfirdn2d_tiled(x, fw == 1 ? nullptr : f, f_stride_x, fh == 1 ? nullptr : f, f_stride_y, y, dtype,
                              x_shape, x_stride, y_shape, y_stride, fw, fh, upx, upy, downx, downy, padx0, pady0,

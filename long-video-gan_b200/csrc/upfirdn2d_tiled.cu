@@ -309,6 +309,8 @@ int dispatch(const Axis& ax, const Axis& ay, TiledParams& p, cudaStream_t s)
     LVG_TILED_CASE(AX_ID, 1, 1, AX_DOWN, 2, 4)        // U5  temporal down-sampling
     LVG_TILED_CASE(AX_ID, 1, 1, AX_DOWN, 2, 12)       // U1  temporal Kaiser down-sampling
     LVG_TILED_CASE(AX_ID, 1, 1, AX_UP, 2, 12)         //     adjoint of U1
+    LVG_TILED_CASE(AX_DOWN, 2, 12, AX_ID, 1, 1)       // U1  on [N, C, L, 1] tensors (transposed view: filter along x)
+    LVG_TILED_CASE(AX_UP, 2, 12, AX_ID, 1, 1)         //     and its adjoint
     LVG_TILED_CASE(AX_DOWN, 4, 24, AX_DOWN, 4, 24)    // U6  Kaiser down 4
     LVG_TILED_CASE(AX_DOWN, 2, 12, AX_DOWN, 2, 12)    // U6 / U9 down 2, 12 taps
     LVG_TILED_CASE(AX_UP, 2, 12, AX_UP, 2, 12)        // U6 / U9 up 2, 12 taps

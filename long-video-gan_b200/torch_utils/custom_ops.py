@@ -201,7 +201,8 @@ class BiasActPlugin:
         return y
 
     def bias_act_grad_db(self, dy, b, xref, yref, dim, act, alpha, gain, clamp):
-        """Backward pass with the bias-gradient reduction fused in. Returns (dx, db) with db in dy.dtype."""
+        """Backward pass with the bias-gradient reduction fused in. Returns (dx, db) with db in dy.dtype,
+        or None when the fused kernel does not cover the layout (bias along the contiguous dimension)."""
         if not dy.is_cuda:
             raise RuntimeError('dy must reside on CUDA device')
         code = _dtype_code(dy, 'bias_act_grad_db')
@@ -214,9 +215,11 @@ class BiasActPlugin:
         dx = torch.empty_like(dy)
         db = torch.zeros([size_b], dtype=torch.float32, device=dy.device)
         with _DeviceGuard(dy):
-            _check(self._lib.lvg_bias_act_grad_db(_ptr(dy), _ptr(b), _ptr(xref), _ptr(yref), _ptr(dx), _ptr(db), code,
-                                                  dy.numel(), size_b, step_b, int(act), float(alpha), float(gain),
-                                                  float(clamp), _stream(dy)), 'bias_act_grad_db')
+            rc = _check(self._lib.lvg_bias_act_grad_db(_ptr(dy), _ptr(b), _ptr(xref), _ptr(yref), _ptr(dx), _ptr(db), code,
+                                                       dy.numel(), size_b, step_b, int(act), float(alpha), float(gain),
+                                                       float(clamp), _stream(dy)), 'bias_act_grad_db')
+        if rc == LVG_UNSUPPORTED:
+            return None     # layout not covered by the fused kernel: caller runs bias_act(grad=1) + sum
         return dx, db.to(dy.dtype)
 
 

@@ -143,7 +143,11 @@ class _BiasAct(torch.autograd.Function):
             elif (need_b and not torch.is_grad_enabled() and dy.dtype != torch.float64
                   and hasattr(_plugin, 'bias_act_grad_db')):
                 # plain backward (no create_graph): one kernel produces dx and the bias gradient
-                dx, db = _plugin.bias_act_grad_db(dy, b, x, y, cfg.dim, cfg.spec.cuda_idx, cfg.alpha, cfg.gain, cfg.clamp)
+                fused = _plugin.bias_act_grad_db(dy, b, x, y, cfg.dim, cfg.spec.cuda_idx, cfg.alpha, cfg.gain, cfg.clamp)
+                if fused is not None:
+                    dx, db = fused
+                else:
+                    dx = _BiasActGrad.apply(dy, x, b, y, cfg)
             else:
                 dx = _BiasActGrad.apply(dy, x, b, y, cfg)
         if need_b and db is None:
