@@ -61,11 +61,11 @@ struct Geom {
     static constexpr int TIW = NQXR + KU;                             // input tile incl. filter support
     static constexpr int TIH = NQYR + KU;
     static constexpr int P_IN = fir::odd_pitch(TIW);
-    static constexpr int P_UX = fir::odd_pitch(TUWA);
+    static constexpr int P_UX = fir::even_pitch(TUWA);                 // read column-pair-wise by the y pass: even
     static constexpr int P_UXY = fir::odd_pitch(fir::round_up(TUWA + DOWN * kR, 2));   // slack for the down-x overrun
     static constexpr int TOWR = fir::round_up(TOW, kR);
     static constexpr int TOHR = fir::round_up(TOH, kR);
-    static constexpr int P_DX = fir::odd_pitch(TOWR);
+    static constexpr int P_DX = fir::even_pitch(TOWR);
     static constexpr int UXY_ROWS = TUHA + DOWN * kR;                 // slack rows for the down-y overrun
     static constexpr int A_SIZE = (TIH * P_IN > UXY_ROWS * P_UXY) ? TIH * P_IN : UXY_ROWS * P_UXY;
     static constexpr int B_SIZE = (TIH * P_UX > UXY_ROWS * P_DX) ? TIH * P_UX : UXY_ROWS * P_DX;
@@ -134,37 +134,45 @@ __global__ void __launch_bounds__(kThreads, 2) filtered_lrelu_kernel(FlParams p)
     }
     __syncthreads();
 
-    // ---- stage 2: up-sample along x: A [tih][tiw] -> B [tih][TUWA]
-    fir::up_x<UP, FU, kR, kThreads>(bufA, G::P_IN, bufB, G::P_UX, tih_e, nqx_e, s_fu);
+    // ---- stage 2: up-sample along x: A [tih][tiw] -> B [tih][TUWA]   (packed FMA: two rows per thread)
+    fir::up_x2<UP, FU, kR, kThreads>(bufA, G::P_IN, bufB, G::P_UX, tih_e, nqx_e, s_fu);
     __syncthreads();
 
-    // ---- stage 3: up-sample along y, scale, activation, signs: B -> A [TUHA][TUWA]
+    // ---- stage 3: up-sample along y, scale, activation, signs: B -> A [TUHA][TUWA]   (two columns per thread)
     {
         const float scale = (float)(UP * UP) * p.gain;
         const float slope = p.slope, clamp = p.clamp;
         const int Uax = U0 - dxo, Vay = V0 - dyo;          // global up-sampled coords of aligned sample (0, 0)
         const uint8_t* sgn = (MODE == SIGN_READ) ? p.si + plane * (int64_t)p.s_h * p.s_wb : nullptr;
         const int s_w = p.s_wb * 4;
-        const int cols = nqx_e * UP;
-        fir::up_y<UP, FU, kR, kThreads>(bufB, G::P_UX, cols, nqy_e, s_fu,
-            [&](int, int row, int col, float acc) {
-                float v = acc * scale;
-                if (MODE == SIGN_READ) {
-                    const int qx = Uax + col + p.sx, qy = Vay + row + p.sy;
-                    if ((unsigned)qx < (unsigned)s_w && (unsigned)qy < (unsigned)p.s_h) {
-                        const unsigned s = sgn[(int64_t)qy * p.s_wb + (qx >> 2)] >> ((qx & 3) << 1);
-                        if (s & 1u) v *= slope;
-                        if (s & 2u) v = 0.f;
-                    }
-                } else {
-                    // branch-free: selects only (the sign code is 2 if clamped, else 1 if negative)
-                    const bool neg = v < 0.f;
-                    v = neg ? v * slope : v;
-                    const bool sat = fabsf(v) > clamp;
-                    v = sat ? copysignf(clamp, v) : v;
-                    if (MODE == SIGN_WRITE) s_code[row * G::TUWA + col] = (uint8_t)(sat ? 2 : (neg ? 1 : 0));
+        const int cols = nqx_e * UP;                        // even
+        auto activate = [&](float v, int row, int col, unsigned& code) {
+            v *= scale;
+            if (MODE == SIGN_READ) {
+                const int qx = Uax + col + p.sx, qy = Vay + row + p.sy;
+                if ((unsigned)qx < (unsigned)s_w && (unsigned)qy < (unsigned)p.s_h) {
+                    const unsigned s = sgn[(int64_t)qy * p.s_wb + (qx >> 2)] >> ((qx & 3) << 1);
+                    if (s & 1u) v *= slope;
+                    if (s & 2u) v = 0.f;
                 }
-                bufA[row * G::P_UXY + col] = v;
+            } else {
+                // branch-free: selects only (the sign code is 2 if clamped, else 1 if negative)
+                const bool neg = v < 0.f;
+                v = neg ? v * slope : v;
+                const bool sat = fabsf(v) > clamp;
+                v = sat ? copysignf(clamp, v) : v;
+                code = sat ? 2u : (neg ? 1u : 0u);
+            }
+            return v;
+        };
+        fir::up_y2<UP, FU, kR, kThreads>(bufB, G::P_UX, cols, nqy_e, s_fu,
+            [&](int, int row, int col, float2 acc) {
+                unsigned c0 = 0, c1 = 0;
+                const float v0 = activate(acc.x, row, col, c0);
+                const float v1 = activate(acc.y, row, col + 1, c1);
+                if (MODE == SIGN_WRITE) *reinterpret_cast<uint16_t*>(&s_code[row * G::TUWA + col]) = (uint16_t)(c0 | (c1 << 8));
+                bufA[row * G::P_UXY + col] = v0;
+                bufA[row * G::P_UXY + col + 1] = v1;
             });
     }
     __syncthreads();
@@ -195,16 +203,23 @@ __global__ void __launch_bounds__(kThreads, 2) filtered_lrelu_kernel(FlParams p)
     }
 
     // ---- stage 4: down-sample along x: A [tuh][.] (from column dxo, rows from dyo) -> B [tuh][TOW]
-    fir::down_x<DOWN, FD, kR, kThreads>(bufA + dyo * G::P_UXY, G::P_UXY, dxo, bufB, G::P_DX, tuh_e, tow_e, s_fd);
-    __syncthreads();
-
-    // ---- stage 5: down-sample along y and store
-    {
-        T* yp = (T*)p.y + (int64_t)nn * p.ys[0] + (int64_t)cc * p.ys[1];
-        fir::down_y<DOWN, FD, kR, kThreads>(bufB, G::P_DX, 0, tow_e, toh_e, s_fd,
-            [&](int, int o, int col, float acc) {
-                yp[(int64_t)(oy0 + o) * p.ys[2] + (int64_t)(ox0 + col) * p.ys[3]] = from_acc<T>(acc);
+    // ---- stage 5: down-sample along y and store. 24-tap filters keep the one-output-per-FMA form (registers).
+    T* yp = (T*)p.y + (int64_t)nn * p.ys[0] + (int64_t)cc * p.ys[1] + (int64_t)oy0 * p.ys[2] + (int64_t)ox0 * p.ys[3];
+    const int64_t ys2 = p.ys[2], ys3 = p.ys[3];
+    if constexpr (FD <= 12) {
+        fir::down_x2<DOWN, FD, kR, kThreads>(bufA + dyo * G::P_UXY, G::P_UXY, dxo, bufB, G::P_DX, tuh_e, tow_e, s_fd);
+        __syncthreads();
+        fir::down_y2<DOWN, FD, kR, kThreads>(bufB, G::P_DX, 0, tow_e, toh_e, s_fd,
+            [&](int, int o, int col, float2 acc) {
+                T* dst = yp + o * ys2 + col * ys3;
+                dst[0] = from_acc<T>(acc.x);
+                if (col + 1 < tow_e) dst[ys3] = from_acc<T>(acc.y);
             });
+    } else {
+        fir::down_x<DOWN, FD, kR, kThreads>(bufA + dyo * G::P_UXY, G::P_UXY, dxo, bufB, G::P_DX, tuh_e, tow_e, s_fd);
+        __syncthreads();
+        fir::down_y<DOWN, FD, kR, kThreads>(bufB, G::P_DX, 0, tow_e, toh_e, s_fd,
+            [&](int, int o, int col, float acc) { yp[o * ys2 + col * ys3] = from_acc<T>(acc); });
     }
 }
 
@@ -302,11 +317,11 @@ Cfg pick(int fu_w, int fu_h, int fd_w, int fd_h, int up, int down)
     return CFG_NONE;
 }
 
-// tile height experiment switch: LVG_FL_TOH=32 selects the 64x32 tiles (2 CTAs/SM), default 64x16 (4 CTAs/SM)
+// tile height switch for experiments: 64x32 output tiles by default, LVG_FL_TOH=16 selects 64x16
 bool tall_tiles()
 {
     static int v = -1;
-    if (v < 0) { const char* e = getenv("LVG_FL_TOH"); v = (e && atoi(e) == 32) ? 1 : 0; }
+    if (v < 0) { const char* e = getenv("LVG_FL_TOH"); v = (e && atoi(e) == 16) ? 0 : 1; }
     return v == 1;
 }
 

@@ -200,6 +200,182 @@ __device__ __forceinline__ void down_y(const float* __restrict__ in, int pin, in
     }
 }
 
+// ===========================================================================================
+// Packed variants: every thread produces TWO outputs per FMA instruction with the f32x2 form
+// (SASS FFMA2). A plain 3-register FFMA on sm_100 needs two issue cycles whenever two of its
+// sources share a register-bank parity; the packed form moves 64-bit register pairs and runs at
+// the full FP32 rate, and it halves the instruction count of the inner loops.
+// The two outputs of a pair lie along the axis that is NOT being filtered:
+//   y passes: two adjacent columns  (one 64-bit shared-memory load feeds both; row pitch must be even)
+//   x passes: rows r and r + RW of the same warp item (two conflict-free 32-bit loads)
+// Coefficients are held as (g, g) pairs.
+
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+
+template <int UP, int F, int R, int NTHREADS>
+__device__ __forceinline__ void up_x2(const float* __restrict__ in, int pin, float* __restrict__ out, int pout,
+                                      int rows, int groups, const float* __restrict__ s_taps)
+{
+    static_assert(F % UP == 0, "filter length must be a multiple of the up-sampling factor");
+    constexpr int K = F / UP;
+    constexpr int RW = R;
+    constexpr int GW = kWarp / RW;
+    float2 g[F];
+#pragma unroll
+    for (int i = 0; i < F; i++) g[i] = make_float2(s_taps[i], s_taps[i]);
+    const int warp = threadIdx.x / kWarp, lane = threadIdx.x % kWarp;
+    const int gthreads = (groups + R - 1) / R;
+    const int n_rt = (rows + 2 * RW - 1) / (2 * RW), n_gt = (gthreads + GW - 1) / GW;
+    const FastDiv by_gt(n_gt);
+    for (int wi = warp; wi < n_rt * n_gt; wi += NTHREADS / kWarp) {
+        const int rt = by_gt.div(wi), gt = wi - rt * n_gt;
+        const int ra = rt * 2 * RW + lane % RW;
+        const int tg = gt * GW + lane / RW;
+        if (ra < rows && tg < gthreads) {
+            const bool has_b = ra + RW < rows;
+            const float* sa = in + ra * pin + tg * R;
+            const float* sb = has_b ? sa + RW * pin : sa;
+            float2 v[K + R];
+#pragma unroll
+            for (int i = 0; i < K + R; i++) v[i] = make_float2(sa[i], sb[i]);
+            float* da = out + ra * pout + tg * R * UP;
+            float* db = da + RW * pout;
+#pragma unroll
+            for (int j = 0; j < R; j++) {
+#pragma unroll
+                for (int ph = 0; ph < UP; ph++) {
+                    float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+                    for (int k = 0; k < K; k++)
+                        acc = ffma2(g[(UP - ph) % UP + k * UP], v[j + (ph > 0 ? 1 : 0) + k], acc);
+                    da[j * UP + ph] = acc.x;
+                    if (has_b) db[j * UP + ph] = acc.y;
+                }
+            }
+        }
+    }
+}
+
+// emit(plane, row, col, float2): .x belongs to column col, .y to col + 1 (the caller masks col + 1 >= cols)
+template <int UP, int F, int R, int NTHREADS, class Emit>
+__device__ __forceinline__ void up_y2(const float* __restrict__ in, int pin, int cols, int groups,
+                                      const float* __restrict__ s_taps, Emit emit, int nplanes = 1, int plane_rows = 0)
+{
+    static_assert(F % UP == 0, "filter length must be a multiple of the up-sampling factor");
+    constexpr int K = F / UP;
+    float2 g[F];
+#pragma unroll
+    for (int i = 0; i < F; i++) g[i] = make_float2(s_taps[i], s_taps[i]);
+    const int warp = threadIdx.x / kWarp, lane = threadIdx.x % kWarp;
+    const int gthreads = (groups + R - 1) / R;
+    const int cp = (cols + 1) / 2;                       // column pairs per plane
+    const int vps = nplanes * cp;
+    const int n_cc = (vps + kWarp - 1) / kWarp;
+    const FastDiv by_cp(cp), by_cc(n_cc);
+    const int pin2 = pin / 2;
+    for (int wi = warp; wi < gthreads * n_cc; wi += NTHREADS / kWarp) {
+        const int tg = by_cc.div(wi), cc = wi - tg * n_cc;
+        const int vp = cc * kWarp + lane;
+        if (vp < vps) {
+            const int pl = nplanes > 1 ? by_cp.div(vp) : 0;
+            const int col = 2 * (vp - pl * cp);
+            const float2* src = reinterpret_cast<const float2*>(in + (pl * plane_rows + tg * R) * pin + col);
+            float2 v[K + R];
+#pragma unroll
+            for (int i = 0; i < K + R; i++) v[i] = src[i * pin2];
+#pragma unroll
+            for (int j = 0; j < R; j++) {
+#pragma unroll
+                for (int ph = 0; ph < UP; ph++) {
+                    float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+                    for (int k = 0; k < K; k++)
+                        acc = ffma2(g[(UP - ph) % UP + k * UP], v[j + (ph > 0 ? 1 : 0) + k], acc);
+                    emit(pl, (tg * R + j) * UP + ph, col, acc);
+                }
+            }
+        }
+    }
+}
+
+template <int DOWN, int F, int R, int NTHREADS>
+__device__ __forceinline__ void down_x2(const float* __restrict__ in, int pin, int xoff, float* __restrict__ out, int pout,
+                                        int rows, int outs, const float* __restrict__ s_taps)
+{
+    constexpr int ADV = R * DOWN;
+    constexpr int RW = ADV >= kWarp ? kWarp : ADV;
+    constexpr int GW = kWarp / RW;
+    constexpr int NIN = (R - 1) * DOWN + F;
+    float2 g[F];
+#pragma unroll
+    for (int i = 0; i < F; i++) g[i] = make_float2(s_taps[i], s_taps[i]);
+    const int warp = threadIdx.x / kWarp, lane = threadIdx.x % kWarp;
+    const int gthreads = (outs + R - 1) / R;
+    const int n_rt = (rows + 2 * RW - 1) / (2 * RW), n_gt = (gthreads + GW - 1) / GW;
+    const FastDiv by_gt(n_gt);
+    for (int wi = warp; wi < n_rt * n_gt; wi += NTHREADS / kWarp) {
+        const int rt = by_gt.div(wi), gt = wi - rt * n_gt;
+        const int ra = rt * 2 * RW + lane % RW;
+        const int tg = gt * GW + lane / RW;
+        if (ra < rows && tg < gthreads) {
+            const bool has_b = ra + RW < rows;
+            const float* sa = in + ra * pin + xoff + tg * ADV;
+            const float* sb = has_b ? sa + RW * pin : sa;
+            float2 v[NIN];
+#pragma unroll
+            for (int i = 0; i < NIN; i++) v[i] = make_float2(sa[i], sb[i]);
+            float* da = out + ra * pout + tg * R;
+            float* db = da + RW * pout;
+#pragma unroll
+            for (int j = 0; j < R; j++) {
+                float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int t = 0; t < F; t++) acc = ffma2(g[t], v[j * DOWN + t], acc);
+                da[j] = acc.x;
+                if (has_b) db[j] = acc.y;
+            }
+        }
+    }
+}
+
+template <int DOWN, int F, int R, int NTHREADS, class Emit>
+__device__ __forceinline__ void down_y2(const float* __restrict__ in, int pin, int yoff, int cols, int outs,
+                                        const float* __restrict__ s_taps, Emit emit, int nplanes = 1, int plane_rows = 0)
+{
+    constexpr int NIN = (R - 1) * DOWN + F;
+    float2 g[F];
+#pragma unroll
+    for (int i = 0; i < F; i++) g[i] = make_float2(s_taps[i], s_taps[i]);
+    const int warp = threadIdx.x / kWarp, lane = threadIdx.x % kWarp;
+    const int gthreads = (outs + R - 1) / R;
+    const int cp = (cols + 1) / 2;
+    const int vps = nplanes * cp;
+    const int n_cc = (vps + kWarp - 1) / kWarp;
+    const FastDiv by_cp(cp), by_cc(n_cc);
+    const int pin2 = pin / 2;
+    for (int wi = warp; wi < gthreads * n_cc; wi += NTHREADS / kWarp) {
+        const int tg = by_cc.div(wi), cc = wi - tg * n_cc;
+        const int vp = cc * kWarp + lane;
+        if (vp < vps) {
+            const int pl = nplanes > 1 ? by_cp.div(vp) : 0;
+            const int col = 2 * (vp - pl * cp);
+            const float2* src = reinterpret_cast<const float2*>(in + (pl * plane_rows + yoff + tg * R * DOWN) * pin + col);
+            float2 v[NIN];
+#pragma unroll
+            for (int i = 0; i < NIN; i++) v[i] = src[i * pin2];
+#pragma unroll
+            for (int j = 0; j < R; j++) {
+                float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int t = 0; t < F; t++) acc = ffma2(g[t], v[j * DOWN + t], acc);
+                if (tg * R + j < outs) emit(pl, tg * R + j, col, acc);
+            }
+        }
+    }
+}
+
+__host__ __device__ constexpr int even_pitch(int w) { return (w + 1) & ~1; }
+
 // filter taps global -> shared, oriented for correlation: g[t] = flip ? f[t] : f[F-1-t]
 __device__ __forceinline__ void load_taps(float* s_taps, const float* __restrict__ f, int n, bool flip)
 {
