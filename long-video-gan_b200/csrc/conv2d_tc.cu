@@ -188,13 +188,13 @@ __global__ void __launch_bounds__(kThreads, 2) conv_fprop_tc_kernel(ConvParams p
     constexpr int TAPS = KH * KW;
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t mma_bar;      // the MMAs of a k-chunk have finished reading shared memory
-    __shared__ uint64_t a_bar;        // the bulk copy of the chunk's weight tiles has landed
+    __shared__ uint64_t a_bar[2];     // the bulk copy of a chunk's weight tiles has landed (one per A buffer)
     __shared__ uint32_t tmem_base_slot;
 
     const int nch_row = p.wt / 8;                          // 16-byte chunks per tile row
     const int nch = (p.th + KH - 1) * nch_row;             // chunks per (copy, k-group)
-    unsigned char* sA = smem;                              // [TAPS][4096]
-    unsigned char* sB = smem + TAPS * kATileBytes;         // [KW copies][2 k-groups][nch][128]
+    unsigned char* sA = smem;                              // [2 buffers][TAPS][4096]
+    unsigned char* sB = smem + 2 * TAPS * kATileBytes;     // [KW copies][2 k-groups][nch][128]
     const uint32_t lbo_b = (uint32_t)nch * 128;            // between the two 8-channel groups
     const int N = p.th * p.wt;
 
@@ -208,7 +208,8 @@ __global__ void __launch_bounds__(kThreads, 2) conv_fprop_tc_kernel(ConvParams p
 
     if (threadIdx.x == 0) {
         mbar_init(&mma_bar, 1);
-        mbar_init(&a_bar, 1);
+        mbar_init(&a_bar[0], 1);
+        mbar_init(&a_bar[1], 1);
         fence_barrier_init();
     }
     if (warp == 0) tmem_alloc(&tmem_base_slot, 256);
@@ -223,20 +224,20 @@ __global__ void __launch_bounds__(kThreads, 2) conv_fprop_tc_kernel(ConvParams p
     const __half* xg = p.x + (int64_t)g * p.cin * p.h * p.w;
     const unsigned char* wpg = reinterpret_cast<const unsigned char*>(p.wp) + (((int64_t)(g % p.wgroups) * p.mt + mti) * p.kc) * TAPS * kATileBytes;
 
-    for (int kci = 0; kci < p.kc; kci++) {
-        if (kci > 0) mbar_wait(&mma_bar, (uint32_t)((kci - 1) & 1));   // the MMAs of the previous chunk have consumed the buffers
+    // B staging item = (channel, tile row, 8-pixel chunk): 8 + KW - 1 pixels are fetched as pixel pairs into
+    // registers (prefetch), later written to shared memory as KW shifted 16-byte chunks (commit).
+    constexpr int NPAIR = (8 + KW - 1 + 1) / 2;
+    constexpr int kMaxItems = 4;                           // per thread; host guarantees items <= 4 * kThreads
+    const int rows = p.th + KH - 1;
+    const int items = kBK * rows * nch_row;
+    const bool paired = p.pair_ok && (ix0 & 1) == 0;       // rows and tile start are 4-byte aligned: one load per pair
+    uint32_t pre[kMaxItems][NPAIR];
 
-        // ---- A: TAPS ready-made tile images = one contiguous block: a single TMA bulk copy (no LSU work)
-        if (threadIdx.x == 0) {
-            mbar_expect_tx(&a_bar, TAPS * kATileBytes);
-            bulk_copy_g2s(sA, wpg + (int64_t)kci * TAPS * kATileBytes, TAPS * kATileBytes, &a_bar);
-        }
-        // ---- B: item = (channel, row, chunk): 8 + KW - 1 pixels in, KW shifted 8-pixel chunks out
-        {
-            const int rows = p.th + KH - 1;
-            const int items = kBK * rows * nch_row;
-            const bool paired = p.pair_ok && (ix0 & 1) == 0;  // rows and tile start are 4-byte aligned: half2 loads
-            for (int it = threadIdx.x; it < items; it += kThreads) {
+    auto prefetch = [&](int kci) {
+#pragma unroll
+        for (int s = 0; s < kMaxItems; s++) {
+            const int it = threadIdx.x + s * kThreads;
+            if (it < items) {
                 const int c = it % nch_row;
                 const int rr = (it / nch_row) % rows;
                 const int ch = it / (nch_row * rows);
@@ -244,53 +245,82 @@ __global__ void __launch_bounds__(kThreads, 2) conv_fprop_tc_kernel(ConvParams p
                 const int gy = iy0 + rr;
                 const bool rowok = ci < p.cin && gy >= 0 && gy < p.h;
                 const __half* row = xg + ((int64_t)ci * p.h + gy) * p.w;
-                unsigned char* dst0 = sB + ((size_t)((ch / 8) * nch + rr * nch_row + c)) * 128 + (ch % 8) * 16;
-                constexpr int NPAIR = (8 + KW - 1 + 1) / 2;
-                uint32_t pr[NPAIR];      // pixel pairs (2q, 2q+1)
                 if (paired) {
 #pragma unroll
                     for (int q = 0; q < NPAIR; q++) {
                         const int gx = ix0 + c * 8 + 2 * q;      // even: the pair is inside or outside the row together
-                        pr[q] = (rowok && gx >= 0 && gx < p.w) ? *reinterpret_cast<const uint32_t*>(row + gx) : 0u;
+                        pre[s][q] = (rowok && gx >= 0 && gx < p.w) ? __ldg(reinterpret_cast<const unsigned int*>(row + gx)) : 0u;
                     }
                 } else {
 #pragma unroll
                     for (int q = 0; q < NPAIR; q++) {
                         const int gx = ix0 + c * 8 + 2 * q;
-                        const unsigned short lo = (rowok && gx >= 0 && gx < p.w) ? *reinterpret_cast<const unsigned short*>(row + gx) : (unsigned short)0;
-                        const unsigned short hi = (rowok && gx + 1 >= 0 && gx + 1 < p.w) ? *reinterpret_cast<const unsigned short*>(row + gx + 1) : (unsigned short)0;
-                        pr[q] = (uint32_t)lo | ((uint32_t)hi << 16);
+                        const unsigned short lo = (rowok && gx >= 0 && gx < p.w) ? __ldg(reinterpret_cast<const unsigned short*>(row + gx)) : (unsigned short)0;
+                        const unsigned short hi = (rowok && gx + 1 >= 0 && gx + 1 < p.w) ? __ldg(reinterpret_cast<const unsigned short*>(row + gx + 1)) : (unsigned short)0;
+                        pre[s][q] = (uint32_t)lo | ((uint32_t)hi << 16);
                     }
                 }
+            }
+        }
+    };
+    auto commit = [&]() {
+#pragma unroll
+        for (int s = 0; s < kMaxItems; s++) {
+            const int it = threadIdx.x + s * kThreads;
+            if (it < items) {
+                const int c = it % nch_row;
+                const int rr = (it / nch_row) % rows;
+                const int ch = it / (nch_row * rows);
+                unsigned char* dst0 = sB + ((size_t)((ch / 8) * nch + rr * nch_row + c)) * 128 + (ch % 8) * 16;
 #pragma unroll
                 for (int v = 0; v < KW; v++) {
                     uint4 o;
                     if (v % 2 == 0) {
-                        o = make_uint4(pr[v / 2], pr[v / 2 + 1], pr[v / 2 + 2], pr[v / 2 + 3]);
-                    } else {        // odd shift: high half of pair j with low half of pair j+1
-                        o = make_uint4(__byte_perm(pr[v / 2], pr[v / 2 + 1], 0x5432), __byte_perm(pr[v / 2 + 1], pr[v / 2 + 2], 0x5432),
-                                       __byte_perm(pr[v / 2 + 2], pr[v / 2 + 3], 0x5432), __byte_perm(pr[v / 2 + 3], pr[v / 2 + 4], 0x5432));
+                        o = make_uint4(pre[s][v / 2], pre[s][v / 2 + 1], pre[s][v / 2 + 2], pre[s][v / 2 + 3]);
+                    } else {        // odd shift: high half of pair j with low half of pair j + 1
+                        o = make_uint4(__byte_perm(pre[s][v / 2], pre[s][v / 2 + 1], 0x5432), __byte_perm(pre[s][v / 2 + 1], pre[s][v / 2 + 2], 0x5432),
+                                       __byte_perm(pre[s][v / 2 + 2], pre[s][v / 2 + 3], 0x5432), __byte_perm(pre[s][v / 2 + 3], pre[s][v / 2 + 4 < NPAIR ? v / 2 + 4 : NPAIR - 1], 0x5432));
                     }
                     *reinterpret_cast<uint4*>(dst0 + (size_t)(v * 2) * nch * 128) = o;
                 }
             }
         }
+    };
+
+    // Software pipeline over the k-chunks (A double-buffered through TMA, B through registers):
+    //   top of iteration k : MMAs of chunk k-1 are done -> B buffer free; write the prefetched chunk k to shared memory
+    //   one thread         : wait for A[k % 2], issue the TAPS MMAs of chunk k, commit, start the bulk copy of A[(k+1) % 2]
+    //   everyone           : prefetch chunk k+1 from global memory into registers while the tensor core works on chunk k
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(&a_bar[0], TAPS * kATileBytes);
+        bulk_copy_g2s(sA, wpg, TAPS * kATileBytes, &a_bar[0]);
+    }
+    prefetch(0);
+    for (int kci = 0; kci < p.kc; kci++) {
+        if (kci > 0) mbar_wait(&mma_bar, (uint32_t)((kci - 1) & 1));
+        commit();
         fence_proxy_async();
         tc_fence_before();
         __syncthreads();
 
         if (threadIdx.x == 0) {
-            mbar_wait(&a_bar, (uint32_t)(kci & 1));
+            const int buf = kci & 1;
+            mbar_wait(&a_bar[buf], (uint32_t)((kci >> 1) & 1));
             tc_fence_after();
 #pragma unroll
             for (int tap = 0; tap < TAPS; tap++) {
                 const int ky = tap / KW, kx = tap % KW;
-                const uint64_t adesc = make_desc(smem_u32(sA + tap * kATileBytes), 2048, 128);
+                const uint64_t adesc = make_desc(smem_u32(sA + (size_t)buf * TAPS * kATileBytes + tap * kATileBytes), 2048, 128);
                 const uint64_t bdesc = make_desc(smem_u32(sB + ((size_t)(kx * 2) * nch + ky * nch_row) * 128), lbo_b, 128);
                 umma_f16(tmem_d, adesc, bdesc, idesc, (kci > 0 || tap > 0) ? 1u : 0u);
             }
             umma_commit(&mma_bar);
+            if (kci + 1 < p.kc) {      // A[(k+1) % 2] was last read by the MMAs of chunk k-1, which have completed
+                mbar_expect_tx(&a_bar[buf ^ 1], TAPS * kATileBytes);
+                bulk_copy_g2s(sA + (size_t)(buf ^ 1) * TAPS * kATileBytes, wpg + (int64_t)(kci + 1) * TAPS * kATileBytes, TAPS * kATileBytes, &a_bar[buf ^ 1]);
+            }
         }
+        if (kci + 1 < p.kc) prefetch(kci + 1);
     }
 
     // ---- epilogue: TMEM -> registers -> fp16 -> global (half2 stores along the pixel axis)
@@ -341,7 +371,7 @@ void pick_tile(int ho, int wo, int& th, int& wt, int& tiles_x, int& tiles_y)
 
 size_t smem_bytes(int taps, int kh, int kw, int th, int wt)
 {
-    return (size_t)taps * kATileBytes + (size_t)kw * 2 * (th + kh - 1) * (wt / 8) * 128;
+    return (size_t)2 * taps * kATileBytes + (size_t)kw * 2 * (th + kh - 1) * (wt / 8) * 128;
 }
 
 bool supported(int dtype, int kh, int kw, int stride)
@@ -388,7 +418,8 @@ int run_conv(const __half* x, const __half* w, __half* y, int n, int groups, int
         LVG_LAUNCH_CHECK();
     }
     const size_t smem = smem_bytes(taps, kh, kw, p.th, p.wt);
-    LVG_REQUIRE(smem <= 100 * 1024, "conv2d: tile does not fit shared memory");
+    LVG_REQUIRE(smem <= 110 * 1024, "conv2d: tile does not fit shared memory");
+    LVG_REQUIRE(kBK * (p.th + kh - 1) * (p.wt / 8) <= 4 * kThreads, "conv2d: tile has too many staging items");
     dim3 grid((unsigned)(p.tiles_x * p.tiles_y), (unsigned)p.mt, (unsigned)p.groups);
     if (kh == 3) {
         LVG_CUDA(cudaFuncSetAttribute(conv_fprop_tc_kernel<3, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
