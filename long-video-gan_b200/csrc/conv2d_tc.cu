@@ -238,9 +238,12 @@ __global__ void __launch_bounds__(kThreads, 2) conv_fprop_tc_kernel(ConvParams p
         for (int s = 0; s < kMaxItems; s++) {
             const int it = threadIdx.x + s * kThreads;
             if (it < items) {
-                const int c = it % nch_row;
-                const int rr = (it / nch_row) % rows;
-                const int ch = it / (nch_row * rows);
+                // item order: channel-within-8 fastest, then chunk: 8 consecutive lanes fill one 128-byte
+                // core matrix, so the 16-byte shared-memory stores of a warp cover 512 contiguous bytes
+                const int clo = it % 8;
+                const int c = (it / 8) % nch_row;
+                const int rr = (it / (8 * nch_row)) % rows;
+                const int ch = (it / (8 * nch_row * rows)) * 8 + clo;
                 const int ci = kci * kBK + ch;
                 const int gy = iy0 + rr;
                 const bool rowok = ci < p.cin && gy >= 0 && gy < p.h;
@@ -268,9 +271,12 @@ __global__ void __launch_bounds__(kThreads, 2) conv_fprop_tc_kernel(ConvParams p
         for (int s = 0; s < kMaxItems; s++) {
             const int it = threadIdx.x + s * kThreads;
             if (it < items) {
-                const int c = it % nch_row;
-                const int rr = (it / nch_row) % rows;
-                const int ch = it / (nch_row * rows);
+                // item order: channel-within-8 fastest, then chunk: 8 consecutive lanes fill one 128-byte
+                // core matrix, so the 16-byte shared-memory stores of a warp cover 512 contiguous bytes
+                const int clo = it % 8;
+                const int c = (it / 8) % nch_row;
+                const int rr = (it / (8 * nch_row)) % rows;
+                const int ch = (it / (8 * nch_row * rows)) * 8 + clo;
                 unsigned char* dst0 = sB + ((size_t)((ch / 8) * nch + rr * nch_row + c)) * 128 + (ch % 8) * 16;
 #pragma unroll
                 for (int v = 0; v < KW; v++) {

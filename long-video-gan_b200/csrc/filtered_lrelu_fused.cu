@@ -61,11 +61,11 @@ struct Geom {
     static constexpr int TIW = NQXR + KU;                             // input tile incl. filter support
     static constexpr int TIH = NQYR + KU;
     static constexpr int P_IN = fir::odd_pitch(TIW);
-    static constexpr int P_UX = fir::even_pitch(TUWA);                 // read column-pair-wise by the y pass: even
+    static constexpr int P_UX = fir::odd_pitch(TUWA);
     static constexpr int P_UXY = fir::odd_pitch(fir::round_up(TUWA + DOWN * kR, 2));   // slack for the down-x overrun
     static constexpr int TOWR = fir::round_up(TOW, kR);
     static constexpr int TOHR = fir::round_up(TOH, kR);
-    static constexpr int P_DX = fir::even_pitch(TOWR);
+    static constexpr int P_DX = fir::odd_pitch(TOWR);
     static constexpr int UXY_ROWS = TUHA + DOWN * kR;                 // slack rows for the down-y overrun
     static constexpr int A_SIZE = (TIH * P_IN > UXY_ROWS * P_UXY) ? TIH * P_IN : UXY_ROWS * P_UXY;
     static constexpr int B_SIZE = (TIH * P_UX > UXY_ROWS * P_DX) ? TIH * P_UX : UXY_ROWS * P_DX;
@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(kThreads, 2) filtered_lrelu_kernel(FlParams p)
         const int Uax = U0 - dxo, Vay = V0 - dyo;          // global up-sampled coords of aligned sample (0, 0)
         const uint8_t* sgn = (MODE == SIGN_READ) ? p.si + plane * (int64_t)p.s_h * p.s_wb : nullptr;
         const int s_w = p.s_wb * 4;
-        const int cols = nqx_e * UP;                        // even
+        const int cols = nqx_e * UP;
         auto activate = [&](float v, int row, int col, unsigned& code) {
             v *= scale;
             if (MODE == SIGN_READ) {
@@ -166,13 +166,11 @@ __global__ void __launch_bounds__(kThreads, 2) filtered_lrelu_kernel(FlParams p)
             return v;
         };
         fir::up_y2<UP, FU, kR, kThreads>(bufB, G::P_UX, cols, nqy_e, s_fu,
-            [&](int, int row, int col, float2 acc) {
-                unsigned c0 = 0, c1 = 0;
-                const float v0 = activate(acc.x, row, col, c0);
-                const float v1 = activate(acc.y, row, col + 1, c1);
-                if (MODE == SIGN_WRITE) *reinterpret_cast<uint16_t*>(&s_code[row * G::TUWA + col]) = (uint16_t)(c0 | (c1 << 8));
-                bufA[row * G::P_UXY + col] = v0;
-                bufA[row * G::P_UXY + col + 1] = v1;
+            [&](int, int row, int col, float acc) {
+                unsigned code = 0;
+                const float v = activate(acc, row, col, code);
+                if (MODE == SIGN_WRITE) s_code[row * G::TUWA + col] = (uint8_t)code;
+                bufA[row * G::P_UXY + col] = v;
             });
     }
     __syncthreads();
@@ -210,11 +208,7 @@ __global__ void __launch_bounds__(kThreads, 2) filtered_lrelu_kernel(FlParams p)
         fir::down_x2<DOWN, FD, kR, kThreads>(bufA + dyo * G::P_UXY, G::P_UXY, dxo, bufB, G::P_DX, tuh_e, tow_e, s_fd);
         __syncthreads();
         fir::down_y2<DOWN, FD, kR, kThreads>(bufB, G::P_DX, 0, tow_e, toh_e, s_fd,
-            [&](int, int o, int col, float2 acc) {
-                T* dst = yp + o * ys2 + col * ys3;
-                dst[0] = from_acc<T>(acc.x);
-                if (col + 1 < tow_e) dst[ys3] = from_acc<T>(acc.y);
-            });
+            [&](int, int o, int col, float acc) { yp[o * ys2 + col * ys3] = from_acc<T>(acc); });
     } else {
         fir::down_x<DOWN, FD, kR, kThreads>(bufA + dyo * G::P_UXY, G::P_UXY, dxo, bufB, G::P_DX, tuh_e, tow_e, s_fd);
         __syncthreads();

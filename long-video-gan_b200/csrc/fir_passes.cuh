@@ -206,7 +206,7 @@ __device__ __forceinline__ void down_y(const float* __restrict__ in, int pin, in
 // sources share a register-bank parity; the packed form moves 64-bit register pairs and runs at
 // the full FP32 rate, and it halves the instruction count of the inner loops.
 // The two outputs of a pair lie along the axis that is NOT being filtered:
-//   y passes: two adjacent columns  (one 64-bit shared-memory load feeds both; row pitch must be even)
+//   y passes: columns L and L + 32 of a 64-column span (lane L; all accesses stay stride-1 32-bit)
 //   x passes: rows r and r + RW of the same warp item (two conflict-free 32-bit loads)
 // Coefficients are held as (g, g) pairs.
 
@@ -256,7 +256,9 @@ __device__ __forceinline__ void up_x2(const float* __restrict__ in, int pin, flo
     }
 }
 
-// emit(plane, row, col, float2): .x belongs to column col, .y to col + 1 (the caller masks col + 1 >= cols)
+// Packed y pass: a warp item covers TWO 32-column chunks; lane L owns columns L and L + 32 of the
+// item's 64-column span, so every shared-memory access stays a stride-1 32-bit access (no pitch
+// or alignment constraints) while the FMAs are issued in pairs. Same interface as up_y.
 template <int UP, int F, int R, int NTHREADS, class Emit>
 __device__ __forceinline__ void up_y2(const float* __restrict__ in, int pin, int cols, int groups,
                                       const float* __restrict__ s_taps, Emit emit, int nplanes = 1, int plane_rows = 0)
@@ -268,21 +270,21 @@ __device__ __forceinline__ void up_y2(const float* __restrict__ in, int pin, int
     for (int i = 0; i < F; i++) g[i] = make_float2(s_taps[i], s_taps[i]);
     const int warp = threadIdx.x / kWarp, lane = threadIdx.x % kWarp;
     const int gthreads = (groups + R - 1) / R;
-    const int cp = (cols + 1) / 2;                       // column pairs per plane
-    const int vps = nplanes * cp;
-    const int n_cc = (vps + kWarp - 1) / kWarp;
-    const FastDiv by_cp(cp), by_cc(n_cc);
-    const int pin2 = pin / 2;
+    const int vcols = nplanes * cols;
+    const int n_cc = (vcols + 2 * kWarp - 1) / (2 * kWarp);
+    const FastDiv by_cols(cols), by_cc(n_cc);
     for (int wi = warp; wi < gthreads * n_cc; wi += NTHREADS / kWarp) {
         const int tg = by_cc.div(wi), cc = wi - tg * n_cc;
-        const int vp = cc * kWarp + lane;
-        if (vp < vps) {
-            const int pl = nplanes > 1 ? by_cp.div(vp) : 0;
-            const int col = 2 * (vp - pl * cp);
-            const float2* src = reinterpret_cast<const float2*>(in + (pl * plane_rows + tg * R) * pin + col);
+        const int va = cc * 2 * kWarp + lane, vb = va + kWarp;
+        if (va < vcols) {
+            const bool has_b = vb < vcols;
+            const int pla = nplanes > 1 ? by_cols.div(va) : 0, cola = va - pla * cols;
+            const int plb = has_b ? (nplanes > 1 ? by_cols.div(vb) : 0) : pla, colb = has_b ? vb - plb * cols : cola;
+            const float* sa = in + (pla * plane_rows + tg * R) * pin + cola;
+            const float* sb = in + (plb * plane_rows + tg * R) * pin + colb;
             float2 v[K + R];
 #pragma unroll
-            for (int i = 0; i < K + R; i++) v[i] = src[i * pin2];
+            for (int i = 0; i < K + R; i++) v[i] = make_float2(sa[i * pin], sb[i * pin]);
 #pragma unroll
             for (int j = 0; j < R; j++) {
 #pragma unroll
@@ -291,7 +293,8 @@ __device__ __forceinline__ void up_y2(const float* __restrict__ in, int pin, int
 #pragma unroll
                     for (int k = 0; k < K; k++)
                         acc = ffma2(g[(UP - ph) % UP + k * UP], v[j + (ph > 0 ? 1 : 0) + k], acc);
-                    emit(pl, (tg * R + j) * UP + ph, col, acc);
+                    emit(pla, (tg * R + j) * UP + ph, cola, acc.x);
+                    if (has_b) emit(plb, (tg * R + j) * UP + ph, colb, acc.y);
                 }
             }
         }
@@ -348,27 +351,30 @@ __device__ __forceinline__ void down_y2(const float* __restrict__ in, int pin, i
     for (int i = 0; i < F; i++) g[i] = make_float2(s_taps[i], s_taps[i]);
     const int warp = threadIdx.x / kWarp, lane = threadIdx.x % kWarp;
     const int gthreads = (outs + R - 1) / R;
-    const int cp = (cols + 1) / 2;
-    const int vps = nplanes * cp;
-    const int n_cc = (vps + kWarp - 1) / kWarp;
-    const FastDiv by_cp(cp), by_cc(n_cc);
-    const int pin2 = pin / 2;
+    const int vcols = nplanes * cols;
+    const int n_cc = (vcols + 2 * kWarp - 1) / (2 * kWarp);
+    const FastDiv by_cols(cols), by_cc(n_cc);
     for (int wi = warp; wi < gthreads * n_cc; wi += NTHREADS / kWarp) {
         const int tg = by_cc.div(wi), cc = wi - tg * n_cc;
-        const int vp = cc * kWarp + lane;
-        if (vp < vps) {
-            const int pl = nplanes > 1 ? by_cp.div(vp) : 0;
-            const int col = 2 * (vp - pl * cp);
-            const float2* src = reinterpret_cast<const float2*>(in + (pl * plane_rows + yoff + tg * R * DOWN) * pin + col);
+        const int va = cc * 2 * kWarp + lane, vb = va + kWarp;
+        if (va < vcols) {
+            const bool has_b = vb < vcols;
+            const int pla = nplanes > 1 ? by_cols.div(va) : 0, cola = va - pla * cols;
+            const int plb = has_b ? (nplanes > 1 ? by_cols.div(vb) : 0) : pla, colb = has_b ? vb - plb * cols : cola;
+            const float* sa = in + (pla * plane_rows + yoff + tg * R * DOWN) * pin + cola;
+            const float* sb = in + (plb * plane_rows + yoff + tg * R * DOWN) * pin + colb;
             float2 v[NIN];
 #pragma unroll
-            for (int i = 0; i < NIN; i++) v[i] = src[i * pin2];
+            for (int i = 0; i < NIN; i++) v[i] = make_float2(sa[i * pin], sb[i * pin]);
 #pragma unroll
             for (int j = 0; j < R; j++) {
                 float2 acc = make_float2(0.f, 0.f);
 #pragma unroll
                 for (int t = 0; t < F; t++) acc = ffma2(g[t], v[j * DOWN + t], acc);
-                if (tg * R + j < outs) emit(pl, tg * R + j, col, acc);
+                if (tg * R + j < outs) {
+                    emit(pla, tg * R + j, cola, acc.x);
+                    if (has_b) emit(plb, tg * R + j, colb, acc.y);
+                }
             }
         }
     }

@@ -181,10 +181,8 @@ __global__ void __launch_bounds__(kThreads) upfirdn2d_tiled_kernel(TiledParams p
 
     // ---- x pass
     // Packed (two outputs per FMA) passes; 24-tap down-sampling keeps the scalar form (register budget).
-    // The x pass stores its result shifted by (dxo & 1) so that the columns the y pass consumes start at
-    // an even offset (the y pass loads column pairs as 64-bit words).
     int pmid = p.p_in;
-    const int xshift = dxo & 1;
+    const int xshift = 0;
     if constexpr (KX == AX_UP) {
         fir::up_x2<SX, FX, kR, kThreads>(tin, p.p_in, tmid + xshift, p.p_mid, npl * in_h, nqx, s_fx);
         pmid = p.p_mid;
@@ -199,22 +197,18 @@ __global__ void __launch_bounds__(kThreads) upfirdn2d_tiled_kernel(TiledParams p
     // ---- y pass -> global
     T* yp = (T*)p.y + yoff0 + (int64_t)oy0 * p.ys[2] + (int64_t)ox0 * p.ys[3];
     const float gain = p.gain;
-    const float* src = tmid + dxo + xshift;            // even offset, even pitch: 8-byte aligned column pairs
+    const float* src = tmid + dxo + xshift;
     const int64_t ys1 = p.ys[1], ys2 = p.ys[2], ys3 = p.ys[3];
-    auto store2 = [&](T* dst, int col, float2 acc) {
-        dst[0] = from_acc<T>(acc.x * gain);
-        if (col + 1 < tow_e) dst[ys3] = from_acc<T>(acc.y * gain);
-    };
     if constexpr (KY == AX_UP) {
         fir::up_y2<SY, FY, kR, kThreads>(src, pmid, tow_e, nqy, s_fy,
-            [&](int pl, int a, int col, float2 acc) {
+            [&](int pl, int a, int col, float acc) {
                 const int o = a - dyo;
-                if ((unsigned)o < (unsigned)toh_e) store2(yp + pl * ys1 + col * ys3 + o * ys2, col, acc);
+                if ((unsigned)o < (unsigned)toh_e) yp[pl * ys1 + col * ys3 + o * ys2] = from_acc<T>(acc * gain);
             }, npl, in_h);
     } else if constexpr (KY == AX_DOWN) {
         if constexpr (FY <= 12) {
             fir::down_y2<SY, FY, kR, kThreads>(src, pmid, 0, tow_e, toh_e, s_fy,
-                [&](int pl, int o, int col, float2 acc) { store2(yp + pl * ys1 + col * ys3 + o * ys2, col, acc); }, npl, in_h);
+                [&](int pl, int o, int col, float acc) { yp[pl * ys1 + col * ys3 + o * ys2] = from_acc<T>(acc * gain); }, npl, in_h);
         } else {
             fir::down_y<SY, FY, kR, kThreads>(src, pmid, 0, tow_e, toh_e, s_fy,
                 [&](int pl, int o, int col, float acc) { yp[pl * ys1 + col * ys3 + o * ys2] = from_acc<T>(acc * gain); }, npl, in_h);
@@ -257,8 +251,8 @@ int launch_tiled(TiledParams& p, cudaStream_t s)
     p.pb = 1;
     auto smem_for = [&](int toh_, int pb_) {
         const int in_w = in_extent<KX, SX, FX>(p.tow), in_h = in_extent<KY, SY, FY>(toh_);
-        p.p_in = (KX == AX_ID) ? fir::even_pitch(in_w) : fir::odd_pitch(in_w);
-        p.p_mid = fir::even_pitch(mid_extent<KX, SX, FX>(p.tow) + (KX == AX_UP ? SX : 0) + 2);
+        p.p_in = fir::odd_pitch(in_w);
+        p.p_mid = fir::odd_pitch(mid_extent<KX, SX, FX>(p.tow) + (KX == AX_UP ? SX : 0));
         p.a_size = pb_ * in_h * p.p_in;
         const int mid = (KX == AX_ID) ? 0 : pb_ * in_h * p.p_mid;
         return (size_t)(p.a_size + mid + FX + FY) * sizeof(float);
