@@ -226,58 +226,66 @@ __global__ void __launch_bounds__(kThreads, 2) conv_fprop_tc_kernel(ConvParams p
 
     // B staging item = (channel, tile row, 8-pixel chunk): 8 + KW - 1 pixels are fetched as pixel pairs into
     // registers (prefetch), later written to shared memory as KW shifted 16-byte chunks (commit).
+    // Item order: channel-within-8 fastest, then chunk, so 8 consecutive lanes fill one 128-byte core matrix and
+    // a warp's 16-byte stores cover 512 contiguous bytes. The decomposition of an item does not depend on the
+    // k-chunk, so it is done ONCE here (global offset, shared-memory offset, validity mask of the pixel pairs).
     constexpr int NPAIR = (8 + KW - 1 + 1) / 2;
     constexpr int kMaxItems = 4;                           // per thread; host guarantees items <= 4 * kThreads
     const int rows = p.th + KH - 1;
     const int items = kBK * rows * nch_row;
     const bool paired = p.pair_ok && (ix0 & 1) == 0;       // rows and tile start are 4-byte aligned: one load per pair
+    int it_goff[kMaxItems];      // element offset of the item's first pixel inside one k-chunk of x (may point before the row)
+    int it_soff[kMaxItems];      // byte offset of the item's 16-byte slot inside copy 0 of the B buffer
+    int it_ch[kMaxItems];        // channel within the chunk (for the cin bound)
+    unsigned it_mask[kMaxItems]; // bit 2q / 2q+1: pixel 2q / 2q+1 of the item is inside the image
+#pragma unroll
+    for (int s = 0; s < kMaxItems; s++) {
+        const int it = threadIdx.x + s * kThreads;
+        const int clo = it % 8;
+        const int c = (it / 8) % nch_row;
+        const int rr = (it / (8 * nch_row)) % rows;
+        const int ch = (it / (8 * nch_row * rows)) * 8 + clo;
+        const int gy = iy0 + rr;
+        const int gx0 = ix0 + c * 8;
+        unsigned mask = 0;
+        if (it < items && gy >= 0 && gy < p.h) {
+#pragma unroll
+            for (int i = 0; i < 2 * NPAIR; i++)
+                if (gx0 + i >= 0 && gx0 + i < p.w) mask |= 1u << i;
+        }
+        it_mask[s] = mask;
+        it_ch[s] = ch;
+        it_goff[s] = (ch * p.h + gy) * p.w + gx0;
+        it_soff[s] = ((ch / 8) * nch + rr * nch_row + c) * 128 + (ch % 8) * 16;
+    }
     uint32_t pre[kMaxItems][NPAIR];
 
     auto prefetch = [&](int kci) {
+        const __half* xc = xg + (int64_t)kci * kBK * p.h * p.w;
+        const int ch_left = p.cin - kci * kBK;             // channels of this chunk that exist
 #pragma unroll
         for (int s = 0; s < kMaxItems; s++) {
-            const int it = threadIdx.x + s * kThreads;
-            if (it < items) {
-                // item order: channel-within-8 fastest, then chunk: 8 consecutive lanes fill one 128-byte
-                // core matrix, so the 16-byte shared-memory stores of a warp cover 512 contiguous bytes
-                const int clo = it % 8;
-                const int c = (it / 8) % nch_row;
-                const int rr = (it / (8 * nch_row)) % rows;
-                const int ch = (it / (8 * nch_row * rows)) * 8 + clo;
-                const int ci = kci * kBK + ch;
-                const int gy = iy0 + rr;
-                const bool rowok = ci < p.cin && gy >= 0 && gy < p.h;
-                const __half* row = xg + ((int64_t)ci * p.h + gy) * p.w;
+            const unsigned mask = it_ch[s] < ch_left ? it_mask[s] : 0u;
+            const __half* src = xc + it_goff[s];
+#pragma unroll
+            for (int q = 0; q < NPAIR; q++) {
+                const unsigned m2 = (mask >> (2 * q)) & 3u;
+                uint32_t v = 0;
                 if (paired) {
-#pragma unroll
-                    for (int q = 0; q < NPAIR; q++) {
-                        const int gx = ix0 + c * 8 + 2 * q;      // even: the pair is inside or outside the row together
-                        pre[s][q] = (rowok && gx >= 0 && gx < p.w) ? __ldg(reinterpret_cast<const unsigned int*>(row + gx)) : 0u;
-                    }
+                    if (m2 == 3u) v = __ldg(reinterpret_cast<const unsigned int*>(src + 2 * q));
                 } else {
-#pragma unroll
-                    for (int q = 0; q < NPAIR; q++) {
-                        const int gx = ix0 + c * 8 + 2 * q;
-                        const unsigned short lo = (rowok && gx >= 0 && gx < p.w) ? __ldg(reinterpret_cast<const unsigned short*>(row + gx)) : (unsigned short)0;
-                        const unsigned short hi = (rowok && gx + 1 >= 0 && gx + 1 < p.w) ? __ldg(reinterpret_cast<const unsigned short*>(row + gx + 1)) : (unsigned short)0;
-                        pre[s][q] = (uint32_t)lo | ((uint32_t)hi << 16);
-                    }
+                    if (m2 & 1u) v = __ldg(reinterpret_cast<const unsigned short*>(src + 2 * q));
+                    if (m2 & 2u) v |= (uint32_t)__ldg(reinterpret_cast<const unsigned short*>(src + 2 * q + 1)) << 16;
                 }
+                pre[s][q] = v;
             }
         }
     };
     auto commit = [&]() {
 #pragma unroll
         for (int s = 0; s < kMaxItems; s++) {
-            const int it = threadIdx.x + s * kThreads;
-            if (it < items) {
-                // item order: channel-within-8 fastest, then chunk: 8 consecutive lanes fill one 128-byte
-                // core matrix, so the 16-byte shared-memory stores of a warp cover 512 contiguous bytes
-                const int clo = it % 8;
-                const int c = (it / 8) % nch_row;
-                const int rr = (it / (8 * nch_row)) % rows;
-                const int ch = (it / (8 * nch_row * rows)) * 8 + clo;
-                unsigned char* dst0 = sB + ((size_t)((ch / 8) * nch + rr * nch_row + c)) * 128 + (ch % 8) * 16;
+            if (threadIdx.x + s * kThreads < items) {
+                unsigned char* dst0 = sB + it_soff[s];
 #pragma unroll
                 for (int v = 0; v < KW; v++) {
                     uint4 o;

@@ -45,3 +45,9 @@ k12 = torch.randn(12, device=DEV) / 3
 x = torch.randn(16, 128, 166, 278, device=DEV, dtype=torch.float16)
 bb = torch.randn(128, device=DEV, dtype=torch.float16)
 run('flrelu_u2d2', lambda: filtered_lrelu.filtered_lrelu(x, k12, k12, bb, up=2, down=2, padding=[9, 8, 9, 8], clamp=256))
+
+from torch_utils.ops import conv2d_gradfix  # noqa: E402
+conv2d_gradfix.install_native(True)
+xc = torch.randn(1, 16 * 539, 92, 148, device=DEV, dtype=torch.float16)
+wc = torch.randn(16 * 512, 539, 3, 3, device=DEV, dtype=torch.float16) / 70
+run('conv_l8', lambda: conv2d_gradfix.conv2d(xc, wc, padding=2, groups=16))
