@@ -94,7 +94,12 @@ __global__ void __launch_bounds__(kThreads, 2) filtered_lrelu_kernel(FlParams p)
     const int cc = (int)(plane % p.c);
     const int nn = (int)(plane / p.c);
 
-    fir::load_taps(s_fu, p.fu, FU, p.flip != 0);
+    // The factor up^2 * gain that precedes the leaky ReLU is positive, so it is folded into the up-sampling
+    // taps (its square root into each of the two passes) instead of costing a multiply per up-sampled sample.
+    {
+        const float tap_scale = sqrtf((float)(UP * UP) * p.gain);
+        for (int i = threadIdx.x; i < FU; i += kThreads) s_fu[i] = (p.flip ? p.fu[i] : p.fu[FU - 1 - i]) * tap_scale;
+    }
     fir::load_taps(s_fd, p.fd, FD, p.flip != 0);
 
     // geometry of this tile: U0 = first consumed up-sampled sample; the phase-aligned origin is
@@ -108,28 +113,45 @@ __global__ void __launch_bounds__(kThreads, 2) filtered_lrelu_kernel(FlParams p)
     const int tiw_e = fir::round_up(nqx_e, kR) + G::KU, tih_e = fir::round_up(nqy_e, kR) + G::KU;
 
     // ---- stage 1: input tile (+ bias inside the image, zero outside) -> A
-    // All global loads of a thread are issued before the first shared-memory store, so a CTA has
-    // its whole input tile in flight at once instead of one row per warp round trip.
+    // One warp per tile row, lanes along the row; the loop nest has compile-time trip counts and is fully
+    // unrolled, so all of a thread's global loads are in flight before the first shared-memory store, and the
+    // per-element work is a predicated load, a convert, the bias add and the store (row / column validity and
+    // the row pointer are computed once per row / per lane-column).
     {
         const T* xp = (const T*)p.x + (int64_t)nn * p.xs[0] + (int64_t)cc * p.xs[1];
         const float bias = to_acc(((const T*)p.b)[cc]);
-        constexpr int kTile = G::TIH * G::TIW;
-        constexpr int kLoads = (kTile + kThreads - 1) / kThreads;
-        float v[kLoads];
+        constexpr int kWarps = kThreads / 32;
+        constexpr int kRowIters = (G::TIH + kWarps - 1) / kWarps;
+        constexpr int kColIters = (G::TIW + 31) / 32;
+        const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+        bool colok[kColIters];
+        int64_t coloff[kColIters];
 #pragma unroll
-        for (int j = 0; j < kLoads; j++) {
-            const int idx = threadIdx.x + j * kThreads;
-            const int iy = idx / G::TIW, ix = idx - iy * G::TIW;
-            const int gy = m0y + iy, gx = m0x + ix;
-            v[j] = 0.f;
-            if (iy < tih_e && ix < tiw_e && gy >= 0 && gy < p.ih && gx >= 0 && gx < p.iw)
-                v[j] = to_acc(xp[(int64_t)gy * p.xs[2] + (int64_t)gx * p.xs[3]]) + bias;
+        for (int cj = 0; cj < kColIters; cj++) {
+            const int ix = lane + 32 * cj, gx = m0x + ix;
+            colok[cj] = ix < tiw_e && gx >= 0 && gx < p.iw;
+            coloff[cj] = (int64_t)gx * p.xs[3];
+        }
+        float v[kRowIters][kColIters];
+#pragma unroll
+        for (int ri = 0; ri < kRowIters; ri++) {
+            const int iy = warp + kWarps * ri, gy = m0y + iy;
+            const bool rowok = iy < tih_e && gy >= 0 && gy < p.ih;
+            const T* xrow = xp + (int64_t)gy * p.xs[2];
+#pragma unroll
+            for (int cj = 0; cj < kColIters; cj++) {
+                v[ri][cj] = 0.f;
+                if (rowok && colok[cj]) v[ri][cj] = to_acc(xrow[coloff[cj]]) + bias;
+            }
         }
 #pragma unroll
-        for (int j = 0; j < kLoads; j++) {
-            const int idx = threadIdx.x + j * kThreads;
-            const int iy = idx / G::TIW, ix = idx - iy * G::TIW;
-            if (idx < kTile) bufA[iy * G::P_IN + ix] = v[j];
+        for (int ri = 0; ri < kRowIters; ri++) {
+            const int iy = warp + kWarps * ri;
+#pragma unroll
+            for (int cj = 0; cj < kColIters; cj++) {
+                const int ix = lane + 32 * cj;
+                if (iy < G::TIH && ix < G::TIW) bufA[iy * G::P_IN + ix] = v[ri][cj];
+            }
         }
     }
     __syncthreads();
@@ -140,14 +162,13 @@ __global__ void __launch_bounds__(kThreads, 2) filtered_lrelu_kernel(FlParams p)
 
     // ---- stage 3: up-sample along y, scale, activation, signs: B -> A [TUHA][TUWA]   (two columns per thread)
     {
-        const float scale = (float)(UP * UP) * p.gain;
         const float slope = p.slope, clamp = p.clamp;
+        const bool shrink = slope <= 1.f;                  // lrelu(v) = max(v, v*slope) for slope <= 1, min(...) otherwise
         const int Uax = U0 - dxo, Vay = V0 - dyo;          // global up-sampled coords of aligned sample (0, 0)
         const uint8_t* sgn = (MODE == SIGN_READ) ? p.si + plane * (int64_t)p.s_h * p.s_wb : nullptr;
         const int s_w = p.s_wb * 4;
         const int cols = nqx_e * UP;
         auto activate = [&](float v, int row, int col, unsigned& code) {
-            v *= scale;
             if (MODE == SIGN_READ) {
                 const int qx = Uax + col + p.sx, qy = Vay + row + p.sy;
                 if ((unsigned)qx < (unsigned)s_w && (unsigned)qy < (unsigned)p.s_h) {
@@ -155,13 +176,17 @@ __global__ void __launch_bounds__(kThreads, 2) filtered_lrelu_kernel(FlParams p)
                     if (s & 1u) v *= slope;
                     if (s & 2u) v = 0.f;
                 }
-            } else {
+            } else if (MODE == SIGN_WRITE) {
                 // branch-free: selects only (the sign code is 2 if clamped, else 1 if negative)
                 const bool neg = v < 0.f;
                 v = neg ? v * slope : v;
                 const bool sat = fabsf(v) > clamp;
-                v = sat ? copysignf(clamp, v) : v;
+                v = fminf(fmaxf(v, -clamp), clamp);
                 code = sat ? 2u : (neg ? 1u : 0u);
+            } else {
+                const float vs = v * slope;
+                v = shrink ? fmaxf(v, vs) : fminf(v, vs);
+                v = fminf(fmaxf(v, -clamp), clamp);
             }
             return v;
         };
