@@ -178,21 +178,34 @@ __global__ void __launch_bounds__(kThreads, (G == 2 ? 2 : 4)) bias_act_vec_kerne
     const T* __restrict__ pdy = kUseDy ? (const T*)p.dy : nullptr;
     T* __restrict__ py = (T*)p.y;
 
-    // fused bias gradient: per tile, rows (= runs of step_b elements sharing one bias index) are
-    // binned in shared memory relative to the tile's first row, then flushed with one global
-    // atomic per touched bin -- a tile of 1024 packs rarely spans more than a couple of rows
-    constexpr int kBins = 32;
-    __shared__ float s_bins[FUSE_DB ? kBins : 1];
-
+    // Fused bias gradient (FUSE_DB): every CTA walks a CONTIGUOUS range of tiles, so a warp stays inside one
+    // channel ("row" = run of step_b elements sharing a bias index) for many packs. Each lane keeps a running sum
+    // for the warp's current row; only when the row changes (or at the end) the warp reduces by shuffle and issues
+    // ONE global atomic. No shared memory, no block barriers in the streaming loop.
     const int64_t tile = (int64_t)kThreads * kUnroll;
-    for (int64_t base = (int64_t)blockIdx.x * tile; base < n_pack; base += (int64_t)gridDim.x * tile) {
+    const int64_t n_tiles = (n_pack + tile - 1) / tile;
+    int64_t t_begin = blockIdx.x, t_end = n_tiles, t_step = gridDim.x;
+    if (FUSE_DB) {
+        const int64_t per = (n_tiles + gridDim.x - 1) / gridDim.x;
+        t_begin = (int64_t)blockIdx.x * per;
+        t_end = t_begin + per < n_tiles ? t_begin + per : n_tiles;
+        t_step = 1;
+    }
+    float run_sum = 0.f;           // this lane's share of the warp's current row
+    int64_t run_row = -1, run_idx = 0;
+    const unsigned full = 0xffffffffu;
+    auto warp_flush = [&]() {
+        float s = run_sum;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(full, s, o);
+        if ((threadIdx.x & 31) == 0 && run_row >= 0) atomicAdd(p.db + run_idx, s);
+        run_sum = 0.f;
+    };
+
+    for (int64_t t = t_begin; t < t_end; t += t_step) {
+        const int64_t base = t * tile;
         Pack<T> vx[kUnroll], vref[kUnroll], vdy[kUnroll];
         const T* __restrict__ pref = kUseX ? pxr : pyr;
-        const int64_t row0 = (FUSE_DB && bmode == BIAS_PER_PACK) ? bias_row(base * N, p) : 0;
-        if (FUSE_DB && bmode == BIAS_PER_PACK) {
-            if (threadIdx.x < kBins) s_bins[threadIdx.x] = 0.f;
-            __syncthreads();
-        }
 #pragma unroll
         for (int u = 0; u < kUnroll; u++) {
             const int64_t pk = base + (int64_t)u * kThreads + threadIdx.x;
@@ -205,7 +218,7 @@ __global__ void __launch_bounds__(kThreads, (G == 2 ? 2 : 4)) bias_act_vec_kerne
 #pragma unroll
         for (int u = 0; u < kUnroll; u++) {
             const int64_t pk = base + (int64_t)u * kThreads + threadIdx.x;
-            int64_t db_rel = -1, db_idx = 0;      // fused bias gradient of this pack (row relative to the tile, value, bias index)
+            int64_t db_row = -1, db_idx = 0;      // fused bias gradient of this pack: row, bias index, value
             float db_val = 0.f;
             if (pk < n_pack) {
                 const int64_t e0 = pk * N;
@@ -227,49 +240,42 @@ __global__ void __launch_bounds__(kThreads, (G == 2 ? 2 : 4)) bias_act_vec_kerne
                     fo[k] = bias_act_elem<S, A>(v, xr, yr, dyv, G, alpha, gain, inv_gain, clamp);
                 }
                 const Pack<T> out = pack<T>(fo);
-                S dbsum = (S)0;
+                store_pack(py + e0, out);
                 if (FUSE_DB) {
                     // accumulate what was actually stored, like dx.sum() would see it
                     S fs[N];
                     unpack<T>(out, fs);
+                    if (bmode == BIAS_PER_PACK) {
+                        S s = (S)0;
 #pragma unroll
-                    for (int k = 0; k < N; k++) {
-                        if (bmode == BIAS_PER_PACK) dbsum += fs[k];
-                        else if (bmode == BIAS_PACKED) atomicAdd(p.db + bidx + k, (float)fs[k]);
-                        else atomicAdd(p.db + bias_index(e0 + k, p), (float)fs[k]);
+                        for (int k = 0; k < N; k++) s += fs[k];
+                        db_row = bias_row(e0, p); db_idx = bidx; db_val = (float)s;
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < N; k++) atomicAdd(p.db + bias_index(e0 + k, p), (float)fs[k]);
                     }
                 }
-                store_pack(py + e0, out);
-
-                if (FUSE_DB && bmode == BIAS_PER_PACK) { db_rel = bias_row(e0, p) - row0; db_val = (float)dbsum; db_idx = bidx; }
             }
             if (FUSE_DB && bmode == BIAS_PER_PACK) {
-                // whole-warp combine (lanes past the end contribute 0): lane 0 holds the smallest pack index,
-                // so if it is past the end every lane is
-                const unsigned full = 0xffffffffu;
-                const int64_t rel0 = __shfl_sync(full, db_rel, 0);
-                const bool uniform = __all_sync(full, db_rel < 0 || db_rel == rel0);
+                // lane 0 holds the smallest pack index: if it is past the end, every lane is
+                const int64_t row0 = __shfl_sync(full, db_row, 0);
+                const int64_t idx0 = __shfl_sync(full, db_idx, 0);
+                const bool uniform = __all_sync(full, db_row < 0 || db_row == row0);
                 if (uniform) {
-                    float ssum = db_val;
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) ssum += __shfl_xor_sync(full, ssum, o);
-                    if ((threadIdx.x & 31) == 0 && rel0 >= 0) {
-                        if (rel0 < kBins) atomicAdd(&s_bins[rel0], ssum); else atomicAdd(p.db + db_idx, ssum);
+                    if (row0 >= 0) {
+                        if (row0 != run_row) {          // warp-uniform branch
+                            warp_flush();
+                            run_row = row0; run_idx = idx0;
+                        }
+                        run_sum += db_val;              // lanes past the end add 0
                     }
-                } else if (db_rel >= 0) {
-                    if (db_rel < kBins) atomicAdd(&s_bins[db_rel], db_val); else atomicAdd(p.db + db_idx, db_val);
+                } else if (db_row >= 0) {
+                    atomicAdd(p.db + db_idx, db_val);   // a row boundary runs through this warp's 32 packs
                 }
             }
         }
-        if (FUSE_DB && bmode == BIAS_PER_PACK) {
-            __syncthreads();
-            if (threadIdx.x < kBins) {
-                const float v = s_bins[threadIdx.x];
-                if (v != 0.f) atomicAdd(p.db + (row0 + threadIdx.x) % p.size_b, v);
-            }
-            __syncthreads();
-        }
     }
+    if (FUSE_DB && bmode == BIAS_PER_PACK) warp_flush();
 }
 
 // Scalar kernel: fp64, unaligned buffers, and the < one-pack tail of the vector kernel.
