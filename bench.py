@@ -398,7 +398,8 @@ def main():
     # warm-up: at least W (>= 3) steps AND at least 2 s, so that a cold box (first CUDA process after boot: page
     # cache, allocator growth, clock ramp) does not leak into the timed region
     warm_steps, t_warm = 0, time.perf_counter()
-    while warm_steps < max(3, args.warmup) or time.perf_counter() - t_warm < 2.0:
+    # (with several ranks the count must be identical everywhere -- the step contains collectives -- so it is fixed)
+    while (warm_steps < max(3, args.warmup) + (8 if world > 1 else 0)) or (world == 1 and time.perf_counter() - t_warm < 2.0):
         step()
         torch.cuda.synchronize()
         warm_steps += 1

@@ -229,11 +229,13 @@ __global__ void __launch_bounds__(kThreads, (TOH <= 24 ? 3 : 2)) filtered_lrelu_
     // ---- stage 5: down-sample along y and store. 24-tap filters keep the one-output-per-FMA form (registers).
     T* yp = (T*)p.y + (int64_t)nn * p.ys[0] + (int64_t)cc * p.ys[1] + (int64_t)oy0 * p.ys[2] + (int64_t)ox0 * p.ys[3];
     const int64_t ys2 = p.ys[2], ys3 = p.ys[3];
+    const int ys2_32 = (int)p.ys[2];          // a plane spans < 2^31 elements (checked on the host)
     if constexpr (FD <= 12) {
         fir::down_x2<DOWN, FD, kR, kThreads>(bufA + dyo * G::P_UXY, G::P_UXY, dxo, bufB, G::P_DX, tuh_e, tow_e, s_fd);
         __syncthreads();
         fir::down_y2<DOWN, FD, kR, kThreads>(bufB, G::P_DX, 0, tow_e, toh_e, s_fd,
-            [&](int, int o, int col, float acc) { yp[o * ys2 + col * ys3] = from_acc<T>(acc); });
+            fir::make_emitter([&](int, int col) { return yp + col * ys3; },
+                              [&](T* base, int o, float acc) { base[o * ys2_32] = from_acc<T>(acc); }));
     } else {
         fir::down_x<DOWN, FD, kR, kThreads>(bufA + dyo * G::P_UXY, G::P_UXY, dxo, bufB, G::P_DX, tuh_e, tow_e, s_fd);
         __syncthreads();
@@ -390,6 +392,7 @@ extern "C" int lvg_filtered_lrelu(const void* x, const float* fu, const float* f
         LVG_REQUIRE(y_shape[i] >= 1 && y_shape[i] <= INT32_MAX, "filtered_lrelu: output must be at least 1x1");
     }
     LVG_REQUIRE(x_shape[0] == y_shape[0] && x_shape[1] == y_shape[1], "filtered_lrelu: x and y disagree on batch/channels");
+    LVG_REQUIRE(y_shape[2] * (y_stride[2] < 0 ? -y_stride[2] : y_stride[2]) < (1ll << 31), "filtered_lrelu: output plane too large");
     LVG_REQUIRE(!(write_signs && si), "filtered_lrelu: cannot read and write signs in one call");
     LVG_REQUIRE(!write_signs || so, "filtered_lrelu: write_signs needs an output sign buffer");
     LVG_REQUIRE(!(write_signs || si) || (s_h >= 1 && s_wbytes >= 1), "filtered_lrelu: bad sign tensor shape");

@@ -37,6 +37,24 @@ struct FastDiv {
 };
 
 
+
+// A y pass hands every result to an "emitter". Plain callables get emit(plane, row, col, value). Emitters made with
+// make_emitter(begin, put) first get begin(plane, col) -> context ONCE per thread item (e.g. the column's base pointer)
+// and then put(context, row, value) per result, which keeps 64-bit address arithmetic out of the per-result path.
+template <class Begin, class Put> struct ItemEmitter { Begin begin; Put put; };
+template <class Begin, class Put> __device__ __forceinline__ ItemEmitter<Begin, Put> make_emitter(Begin b, Put p) { return ItemEmitter<Begin, Put>{b, p}; }
+
+template <class E> struct EmitCtx {
+    int pl, col;
+    __device__ __forceinline__ EmitCtx(E&, int pl_, int col_) : pl(pl_), col(col_) {}
+    __device__ __forceinline__ void put(E& e, int row, float v) const { e(pl, row, col, v); }
+};
+template <class Begin, class Put> struct EmitCtx<ItemEmitter<Begin, Put>> {
+    decltype(((Begin*)nullptr)->operator()(0, 0)) ctx;
+    __device__ __forceinline__ EmitCtx(ItemEmitter<Begin, Put>& e, int pl, int col) : ctx(e.begin(pl, col)) {}
+    __device__ __forceinline__ void put(ItemEmitter<Begin, Put>& e, int row, float v) const { e.put(ctx, row, v); }
+};
+
 // ---------------------------------------------------------------------------
 // up-sampling along x.  in: [rows][pin], out: [rows][pout] (phase-aligned axis)
 // groups = number of input-aligned groups to produce per row (each UP outputs).
@@ -109,6 +127,7 @@ __device__ __forceinline__ void up_y(const float* __restrict__ in, int pin, int 
             float v[K + R];
 #pragma unroll
             for (int i = 0; i < K + R; i++) v[i] = src[i * pin];
+            const EmitCtx<Emit> ec(emit, pl, col);
 #pragma unroll
             for (int j = 0; j < R; j++) {
 #pragma unroll
@@ -117,7 +136,7 @@ __device__ __forceinline__ void up_y(const float* __restrict__ in, int pin, int 
 #pragma unroll
                     for (int k = 0; k < K; k++)
                         acc = fmaf(g[(UP - ph) % UP + k * UP], v[j + (ph > 0 ? 1 : 0) + k], acc);
-                    emit(pl, (tg * R + j) * UP + ph, col, acc);
+                    ec.put(emit, (tg * R + j) * UP + ph, acc);
                 }
             }
         }
@@ -194,7 +213,7 @@ __device__ __forceinline__ void down_y(const float* __restrict__ in, int pin, in
                 float acc = 0.f;
 #pragma unroll
                 for (int t = 0; t < F; t++) acc = fmaf(g[t], v[j * DOWN + t], acc);
-                if (tg * R + j < outs) emit(pl, tg * R + j, col, acc);
+                if (tg * R + j < outs) EmitCtx<Emit>(emit, pl, col).put(emit, tg * R + j, acc);
             }
         }
     }
@@ -285,6 +304,7 @@ __device__ __forceinline__ void up_y2(const float* __restrict__ in, int pin, int
             float2 v[K + R];
 #pragma unroll
             for (int i = 0; i < K + R; i++) v[i] = make_float2(sa[i * pin], sb[i * pin]);
+            const EmitCtx<Emit> ea(emit, pla, cola), eb(emit, plb, colb);
 #pragma unroll
             for (int j = 0; j < R; j++) {
 #pragma unroll
@@ -293,8 +313,8 @@ __device__ __forceinline__ void up_y2(const float* __restrict__ in, int pin, int
 #pragma unroll
                     for (int k = 0; k < K; k++)
                         acc = ffma2(g[(UP - ph) % UP + k * UP], v[j + (ph > 0 ? 1 : 0) + k], acc);
-                    emit(pla, (tg * R + j) * UP + ph, cola, acc.x);
-                    if (has_b) emit(plb, (tg * R + j) * UP + ph, colb, acc.y);
+                    ea.put(emit, (tg * R + j) * UP + ph, acc.x);
+                    if (has_b) eb.put(emit, (tg * R + j) * UP + ph, acc.y);
                 }
             }
         }
@@ -366,14 +386,15 @@ __device__ __forceinline__ void down_y2(const float* __restrict__ in, int pin, i
             float2 v[NIN];
 #pragma unroll
             for (int i = 0; i < NIN; i++) v[i] = make_float2(sa[i * pin], sb[i * pin]);
+            const EmitCtx<Emit> ea(emit, pla, cola), eb(emit, plb, colb);
 #pragma unroll
             for (int j = 0; j < R; j++) {
                 float2 acc = make_float2(0.f, 0.f);
 #pragma unroll
                 for (int t = 0; t < F; t++) acc = ffma2(g[t], v[j * DOWN + t], acc);
                 if (tg * R + j < outs) {
-                    emit(pla, tg * R + j, cola, acc.x);
-                    if (has_b) emit(plb, tg * R + j, colb, acc.y);
+                    ea.put(emit, tg * R + j, acc.x);
+                    if (has_b) eb.put(emit, tg * R + j, acc.y);
                 }
             }
         }

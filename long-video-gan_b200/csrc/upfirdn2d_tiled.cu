@@ -232,24 +232,27 @@ __global__ void __launch_bounds__(kThreads) upfirdn2d_tiled_kernel(TiledParams p
         __syncthreads();
     }
 
-    // ---- y pass -> global
+    // ---- y pass -> global. The store address of a thread item is formed once (64-bit), results then only
+    // add a 32-bit row offset (the host guarantees that a plane spans < 2^31 elements).
     T* yp = (T*)p.y + yoff0 + (int64_t)oy0 * p.ys[2] + (int64_t)ox0 * p.ys[3];
     const float gain = p.gain;
     const float* src = tmid + dxo + xshift;
-    const int64_t ys1 = p.ys[1], ys2 = p.ys[2], ys3 = p.ys[3];
+    const int64_t ys1 = p.ys[1], ys3 = p.ys[3];
+    const int ys2 = (int)p.ys[2];
+    auto col_base = [&](int pl, int col) { return yp + pl * ys1 + col * ys3; };
     if constexpr (KY == AX_UP) {
         fir::up_y2<SY, FY, kR, kThreads>(src, pmid, tow_e, nqy, s_fy,
-            [&](int pl, int a, int col, float acc) {
+            fir::make_emitter(col_base, [&](T* base, int a, float acc) {
                 const int o = a - dyo;
-                if ((unsigned)o < (unsigned)toh_e) yp[pl * ys1 + col * ys3 + o * ys2] = from_acc<T>(acc * gain);
-            }, npl, in_h);
+                if ((unsigned)o < (unsigned)toh_e) base[o * ys2] = from_acc<T>(acc * gain);
+            }), npl, in_h);
     } else if constexpr (KY == AX_DOWN) {
         if constexpr (FY <= 12) {
             fir::down_y2<SY, FY, kR, kThreads>(src, pmid, 0, tow_e, toh_e, s_fy,
-                [&](int pl, int o, int col, float acc) { yp[pl * ys1 + col * ys3 + o * ys2] = from_acc<T>(acc * gain); }, npl, in_h);
+                fir::make_emitter(col_base, [&](T* base, int o, float acc) { base[o * ys2] = from_acc<T>(acc * gain); }), npl, in_h);
         } else {
             fir::down_y<SY, FY, kR, kThreads>(src, pmid, 0, tow_e, toh_e, s_fy,
-                [&](int pl, int o, int col, float acc) { yp[pl * ys1 + col * ys3 + o * ys2] = from_acc<T>(acc * gain); }, npl, in_h);
+                fir::make_emitter(col_base, [&](T* base, int o, float acc) { base[o * ys2] = from_acc<T>(acc * gain); }), npl, in_h);
         }
     } else {
         const int per = toh_e * tow_e;
@@ -258,7 +261,7 @@ __global__ void __launch_bounds__(kThreads) upfirdn2d_tiled_kernel(TiledParams p
             const int pl = npl > 1 ? by_per.div(idx) : 0;
             const int rem = idx - pl * per;
             const int o = by_w.div(rem), col = rem - o * tow_e;
-            yp[pl * ys1 + o * ys2 + col * ys3] = from_acc<T>(src[(pl * in_h + o) * pmid + col] * gain);
+            yp[pl * ys1 + o * (int64_t)ys2 + col * ys3] = from_acc<T>(src[(pl * in_h + o) * pmid + col] * gain);
         }
     }
     if (p.n_work > gridDim.x) __syncthreads();     // the next work item rewrites the tiles
@@ -386,6 +389,7 @@ int upfirdn2d_tiled(const void* x, const float* fx, int64_t fsx, const float* fy
                     int flip, float gain, cudaStream_t s)
 {
     if (dtype != LVG_F32 && dtype != LVG_F16) return LVG_UNSUPPORTED;
+    if (ysh[2] * (yst[2] < 0 ? -yst[2] : yst[2]) >= (1ll << 31)) return LVG_UNSUPPORTED;     // 32-bit row offsets inside a plane
     const Axis ax = classify(fx != nullptr, upx, downx, fw), ay = classify(fy != nullptr, upy, downy, fh);
     if (ax.kind < 0 || ay.kind < 0) return LVG_UNSUPPORTED;
     TiledParams p;
