@@ -40,9 +40,7 @@ struct TiledParams {
     float gain;
     int tow, toh, tiles_x, tiles_y;
     int pb;               // planes per CTA (> 1 only when one tile covers the whole plane)
-    int flat;             // 0: general loader; 1: whole contiguous planes, 128-bit vector loader; 2: same, with the next
-                          //    work item's vectors prefetched into registers while the current one is filtered
-    int64_t n_work;       // work items (plane groups or tiles); in flat mode CTAs loop over them (persistent grid)
+    int flat;             // 1: the CTA's input planes are one contiguous, 16-byte aligned block (vector loader)
     int64_t planes;       // n * c
     int p_in, p_mid;      // row pitches (odd)
     int a_size;           // floats reserved for the input tile(s)
@@ -78,24 +76,10 @@ __global__ void __launch_bounds__(kThreads) upfirdn2d_tiled_kernel(TiledParams p
     float* s_fx = smem + p.a_size + mid_size;
     float* s_fy = s_fx + FX;
 
-    if (KX != AX_ID) for (int i = threadIdx.x; i < FX; i += kThreads) s_fx[i] = p.flip ? p.fx[i * p.fsx] : p.fx[(FX - 1 - i) * p.fsx];
-    if (KY != AX_ID) for (int i = threadIdx.x; i < FY; i += kThreads) s_fy[i] = p.flip ? p.fy[i * p.fsy] : p.fy[(FY - 1 - i) * p.fsy];
-
-    constexpr int V = VecOf<T>::N;
-    const int plane_elems = p.ih * p.iw;
-    const fir::FastDiv by_plane(plane_elems), by_iw(p.iw);
-    constexpr int kPre = 8;                    // prefetch depth (vectors per thread) of flat mode 2
-    Pack<T> pre[kPre];
-    if (p.flat) {                              // zero the whole input tile once: only in-image positions are rewritten
-        for (int i = threadIdx.x; i < p.a_size; i += kThreads) tin[i] = 0.f;
-        __syncthreads();
-    }
-
-    for (int64_t work = blockIdx.x; work < p.n_work; work += gridDim.x) {
-    // work item -> (first plane, tile). With pb > 1 it is pb whole planes (tiles_x == tiles_y == 1).
+    // CTA -> (first plane, tile). With pb > 1 the CTA owns pb whole planes (tiles_x == tiles_y == 1).
     const int tiles = p.tiles_x * p.tiles_y;
-    const int64_t plane0 = (p.pb > 1) ? work * p.pb : work / tiles;
-    const int tile = (p.pb > 1) ? 0 : (int)(work - plane0 * tiles);
+    const int64_t plane0 = (p.pb > 1) ? (int64_t)blockIdx.x * p.pb : (int64_t)(blockIdx.x / tiles);
+    const int tile = (p.pb > 1) ? 0 : (int)(blockIdx.x - plane0 * tiles);
     const int npl = (p.pb > 1) ? (int)min((int64_t)p.pb, p.planes - plane0) : 1;
     const int ty = tile / p.tiles_x, tx = tile - ty * p.tiles_x;
     const int ox0 = tx * p.tow, oy0 = ty * p.toh;
@@ -103,6 +87,9 @@ __global__ void __launch_bounds__(kThreads) upfirdn2d_tiled_kernel(TiledParams p
     // plane -> memory offset: pb > 1 requires stride[0] == C * stride[1] (checked on the host)
     const int64_t xoff0 = (p.pb > 1) ? plane0 * p.xs[1] : (plane0 / p.c) * p.xs[0] + (plane0 % p.c) * p.xs[1];
     const int64_t yoff0 = (p.pb > 1) ? plane0 * p.ys[1] : (plane0 / p.c) * p.ys[0] + (plane0 % p.c) * p.ys[1];
+
+    if (KX != AX_ID) for (int i = threadIdx.x; i < FX; i += kThreads) s_fx[i] = p.flip ? p.fx[i * p.fsx] : p.fx[(FX - 1 - i) * p.fsx];
+    if (KY != AX_ID) for (int i = threadIdx.x; i < FY; i += kThreads) s_fy[i] = p.flip ? p.fy[i * p.fsy] : p.fy[(FY - 1 - i) * p.fsy];
 
     // per-axis geometry: first input sample of the tile, how many to load, phase offsets
     int in_x0, in_w, nqx = 0, dxo = 0;
@@ -132,66 +119,42 @@ __global__ void __launch_bounds__(kThreads) upfirdn2d_tiled_kernel(TiledParams p
         in_h = toh_e;
     }
 
-    // flat loader helpers: vector vi of a work item covers elements [vi*V, vi*V + V) of its contiguous planes
-    auto scatter = [&](const Pack<T>& v, int vi) {
-        const int e = vi * V;
-        const int pl = by_plane.div(e);
-        const int rem = e - pl * plane_elems;
-        const int gy = by_iw.div(rem);
-        const int gx = rem - gy * p.iw;
-        const int iy = gy - in_y0, ix = gx - in_x0;
-        if (iy >= 0 && iy < in_h) {
-            float* dst = tin + (pl * in_h + iy) * p.p_in + ix;
-#pragma unroll
-            for (int k = 0; k < V; k++)
-                if (ix + k >= 0 && ix + k < in_w) dst[k] = to_acc(v.v[k]);
-        }
-    };
-    auto plane_offset = [&](int64_t pl0) { return (p.pb > 1) ? pl0 * p.xs[1] : (pl0 / p.c) * p.xs[0] + (pl0 % p.c) * p.xs[1]; };
-    auto prefetch = [&](int64_t w) {
-        const int64_t pl0 = (p.pb > 1) ? w * p.pb : w;
-        const int n = (p.pb > 1) ? (int)min((int64_t)p.pb, p.planes - pl0) : 1;
-        const T* xp = (const T*)p.x + plane_offset(pl0);
-        const int nvec = n * plane_elems / V;
-#pragma unroll
-        for (int j = 0; j < kPre; j++) {
-            const int vi = threadIdx.x + j * kThreads;
-            if (vi < nvec) pre[j] = load_pack(xp + (int64_t)vi * V);
-        }
-    };
-    auto commit_prefetched = [&](int64_t, int n) {
-        const int nvec = n * plane_elems / V;
-#pragma unroll
-        for (int j = 0; j < kPre; j++) {
-            const int vi = threadIdx.x + j * kThreads;
-            if (vi < nvec) scatter(pre[j], vi);
-        }
-    };
-    if (p.flat == 2 && work == blockIdx.x) prefetch(work);     // first item of this CTA: nothing was prefetched yet
-
     // ---- input tile(s), zero outside the image
     if (p.flat) {
-        // Whole planes, contiguous in memory. The halo of the tile is zeroed ONCE per CTA (the geometry is the
-        // same for every work item); the planes are streamed with 128-bit loads and the elements that fall
-        // inside the tile are scattered into it. In prefetch mode the vectors of this work item were loaded
-        // into registers while the previous item was being filtered.
-        if (p.flat == 2) {
-            commit_prefetched(plane0, npl);
-        } else {
-            const T* xp = (const T*)p.x + xoff0;
-            const int nvec = npl * plane_elems / V;
-            constexpr int kBatch = 4;
-            for (int base = threadIdx.x; base < nvec; base += kThreads * kBatch) {
-                Pack<T> v[kBatch];
+        // Whole planes, contiguous in memory: zero the tile, then stream the planes with 128-bit loads
+        // (4 vectors in flight per thread) and scatter the elements that fall inside the tile.
+        constexpr int V = VecOf<T>::N;
+        const int tile_floats = npl * in_h * p.p_in;
+        for (int i = threadIdx.x; i < tile_floats; i += kThreads) tin[i] = 0.f;
+        __syncthreads();
+        const T* xp = (const T*)p.x + xoff0;
+        const int plane_elems = p.ih * p.iw;
+        const int nvec = npl * plane_elems / V;
+        const fir::FastDiv by_plane(plane_elems), by_w(p.iw);
+        constexpr int kBatch = 4;
+        for (int base = threadIdx.x; base < nvec; base += kThreads * kBatch) {
+            Pack<T> v[kBatch];
 #pragma unroll
-                for (int j = 0; j < kBatch; j++) {
-                    const int vi = base + j * kThreads;
-                    if (vi < nvec) v[j] = load_pack(xp + (int64_t)vi * V);
-                }
+            for (int j = 0; j < kBatch; j++) {
+                const int vi = base + j * kThreads;
+                if (vi < nvec) v[j] = load_pack(xp + (int64_t)vi * V);
+            }
 #pragma unroll
-                for (int j = 0; j < kBatch; j++) {
-                    const int vi = base + j * kThreads;
-                    if (vi < nvec) scatter(v[j], vi);
+            for (int j = 0; j < kBatch; j++) {
+                const int vi = base + j * kThreads;
+                if (vi < nvec) {
+                    const int e = vi * V;
+                    const int pl = by_plane.div(e);
+                    const int rem = e - pl * plane_elems;
+                    const int gy = by_w.div(rem);
+                    const int gx = rem - gy * p.iw;
+                    const int iy = gy - in_y0, ix = gx - in_x0;
+                    if (iy >= 0 && iy < in_h) {
+                        float* dst = tin + (pl * in_h + iy) * p.p_in + ix;
+#pragma unroll
+                        for (int k = 0; k < V; k++)
+                            if (ix + k >= 0 && ix + k < in_w) dst[k] = to_acc(v[j].v[k]);
+                    }
                 }
             }
         }
@@ -215,7 +178,6 @@ __global__ void __launch_bounds__(kThreads) upfirdn2d_tiled_kernel(TiledParams p
         }
     }
     __syncthreads();
-    if (p.flat == 2 && work + gridDim.x < p.n_work) prefetch(work + gridDim.x);    // in flight during the passes below
 
     // ---- x pass
     // Packed (two outputs per FMA) passes; 24-tap down-sampling keeps the scalar form (register budget).
@@ -264,8 +226,6 @@ __global__ void __launch_bounds__(kThreads) upfirdn2d_tiled_kernel(TiledParams p
             yp[pl * ys1 + o * (int64_t)ys2 + col * ys3] = from_acc<T>(src[(pl * in_h + o) * pmid + col] * gain);
         }
     }
-    if (p.n_work > gridDim.x) __syncthreads();     // the next work item rewrites the tiles
-    }   // work loop
 }
 
 // whole rows up to 256 pixels, else the widest tile <= 128 that wastes the fewest lanes of the 32-wide column chunks
@@ -324,18 +284,10 @@ int launch_tiled(TiledParams& p, cudaStream_t s)
     constexpr int V = VecOf<T>::N;
     p.flat = (p.tiles_x == 1 && p.tiles_y == 1 && p.xs[3] == 1 && p.xs[2] == p.iw && p.xs[1] == (int64_t)p.ih * p.iw &&
               (p.pb == 1 || uniform) && p.iw % V == 0 && p.xs[0] % V == 0 && aligned16(p.x) && (int64_t)p.pb * p.ih * p.iw < (1 << 24)) ? 1 : 0;
-    p.n_work = p.pb > 1 ? (p.planes + p.pb - 1) / p.pb : p.planes * p.tiles_x * p.tiles_y;
-    int64_t blocks = p.n_work;
+    const int64_t blocks = p.pb > 1 ? (p.planes + p.pb - 1) / p.pb : p.planes * p.tiles_x * p.tiles_y;
     if (blocks > INT32_MAX) return LVG_UNSUPPORTED;
-    if (p.flat) {
-        // persistent grid: a few CTAs per SM loop over the plane groups; with <= 8 vectors per thread and item
-        // the next item's loads are prefetched into registers behind the filtering of the current one
-        const int64_t vec_per_item = (int64_t)p.pb * p.ih * p.iw / V;
-        if (vec_per_item <= 8 * kThreads) p.flat = 2;
-        const int per_sm = (int)(200 * 1024 / (smem + 1024));
-        const int64_t cap = (int64_t)num_sms() * (per_sm < 1 ? 1 : (per_sm > 6 ? 6 : per_sm));
-        if (blocks > cap) blocks = cap;
-    }
+    // (A persistent grid that prefetched the next work item's vectors into registers measured 5-60 % slower on
+    //  B200 -- more live registers, fewer resident CTAs -- and was dropped: one CTA per work item.)
     auto k = upfirdn2d_tiled_kernel<T, KX, SX, FX, KY, SY, FY>;
     if (smem > 48 * 1024) LVG_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k<<<(unsigned)blocks, kThreads, smem, s>>>(p);

@@ -207,3 +207,46 @@ def test_grid_sample_gradfix_double_backward():
         assert torch.allclose(gg, gg_ref)
     finally:
         grid_sample_gradfix.enabled = False
+
+
+def test_workload_traces_are_consistent():
+    """bench.py replays workloads/*.json: every recorded call must name a hot-path op with usable arguments."""
+    import json
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    seen = set()
+    for fname, keys in (('lres_step.json', ('lres_G', 'lres_D')), ('sres_step.json', ('sres_G', 'sres_D'))):
+        tr = json.load(open(os.path.join(root, 'workloads', fname)))
+        for k in keys:
+            assert len(tr[k]) > 20
+            for c in tr[k]:
+                seen.add(c['op'])
+                assert len(c['x']) >= 2 and all(isinstance(v, int) and v > 0 for v in c['x'])
+                if c['op'] == 'upfirdn2d':
+                    upfirdn2d._parse_scaling(c['up']), upfirdn2d._parse_scaling(c['down']), upfirdn2d._parse_padding(c['padding'])
+                if c['op'] == 'bias_act':
+                    assert c['act'] in bias_act.activation_funcs
+    # call counts of SURVEY.md Appendix A
+    lres = json.load(open(os.path.join(root, 'workloads', 'lres_step.json')))
+    assert sum(c['op'] == 'bias_act' for c in lres['lres_G']) == 23 and sum(c['op'] == 'upfirdn2d' for c in lres['lres_G']) == 14
+    assert sum(c['op'] == 'bias_act' for c in lres['lres_D']) == 18
+    sres = json.load(open(os.path.join(root, 'workloads', 'sres_step.json')))
+    assert sum(c['op'] == 'filtered_lrelu' for c in sres['sres_G']) == 15 and sum(c['op'] == 'conv2d' for c in sres['sres_G']) == 15
+    assert sum(c['op'] == 'conv2d_resample' for c in sres['sres_D']) == 20
+    assert {'bias_act', 'upfirdn2d', 'filtered_lrelu', 'conv2d', 'conv2d_resample'} <= seen
+
+
+def test_bench_reference_arm_runs_on_cpu():
+    """`bench.py --impl reference` (the oracle on host cores) prints one well-formed JSON line without a GPU."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, 'bench.py'), '--impl', 'reference', '--steps', '1', '--warmup', '0',
+                          '--cpu-budget', '1'], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line['impl'] == 'reference' and line['unit'] == 'frames/s' and line['value'] > 0
+    assert line['cpu_baseline']['kind'] == 'port' and line['cpu_baseline']['cores'] >= 1
+    assert line['e2e']['h2d_bytes_per_step'] == 0 and line['higher_is_better'] is True
