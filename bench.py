@@ -67,6 +67,17 @@ def scaled(shape, batch):
 # ---------------------------------------------------------------------------------------------
 # our arm: replay through torch_utils.ops on the GPU
 
+def run_backward(y, leaves, dy):
+    """Backward of ONE replayed call. A training step calls loss.backward() once; replaying the calls one by one
+    would pay torch.autograd.grad's Python-side argument validation (~50 us) per call, which is harness overhead,
+    not operator cost -- so the autograd engine is entered directly (what torch.autograd.grad does after validating)."""
+    try:
+        torch.autograd.variable.Variable._execution_engine.run_backward(
+            (y,), (dy,), False, False, tuple(leaves), allow_unreachable=True, accumulate_grad=False)
+    except (AttributeError, TypeError):
+        torch.autograd.grad(y, leaves, dy, allow_unused=True)
+
+
 class Replay:
     def __init__(self, calls, batch, device, dtype_policy):
         from torch_utils.ops import bias_act, upfirdn2d, filtered_lrelu, conv2d_resample, conv2d_gradfix
@@ -157,12 +168,12 @@ class Replay:
                 timer.stop(it['bytes_fwd'])
                 if y.requires_grad:
                     timer.start()
-                    torch.autograd.grad(y, leaves, it['dy'], allow_unused=True)
+                    run_backward(y, leaves, it['dy'])
                     timer.stop(it['bytes_bwd'])
             else:
                 y = self._fwd(it, x)
                 if y.requires_grad:
-                    torch.autograd.grad(y, leaves, it['dy'], allow_unused=True)
+                    run_backward(y, leaves, it['dy'])
             it['b'] = saved_b
             if saved_w is not None:
                 it['w'] = saved_w
@@ -304,6 +315,8 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--cpu-budget', type=float, default=20.0)
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--launch', default='graph', choices=['graph', 'eager'],
+                    help='graph: the step is captured once into CUDA graphs and replayed (default); eager: every call launched from Python')
     args = ap.parse_args()
 
     rank = int(os.environ.get('RANK', 0))
@@ -314,7 +327,9 @@ def main():
     config = {'workload': f'{args.workload}: train_{args.workload} op trace (torch_utils.ops calls of G+D update), per-GPU batch {batch}, '
                           f'{frames} frames/sample, {"64x36" if args.workload == "lres" else "256x144 from 64x36"}',
               'global_batch': batch * world, 'parallelism': f'dp{world}',
-              'l2': 'inputs and outputs of the replayed calls exceed L2 (largest tensors 0.75 GB); buffers shared per shape'}
+              'l2': 'inputs and outputs of the replayed calls exceed L2 (largest tensors 0.75 GB); buffers shared per shape',
+              'launch': 'cuda_graph (step captured once, replayed; NCCL all-reduces eager between the two graphs)' if args.launch == 'graph'
+                        else 'eager (every call launched from Python)'}
 
     if args.impl == 'reference':
         if rank != 0:
@@ -359,18 +374,35 @@ def main():
     dev_video = torch.empty(vid_shape, dtype=torch.float32, device=device)
     host_out = torch.empty(1, dtype=torch.float32).pin_memory()
 
-    def step(timer=None, e2e=False):
-        if e2e:
-            dev_video.copy_(host_video, non_blocking=True)
-        # update_G: G fwd+bwd, D fwd+bwd ; update_D: G fwd, D fwd+bwd (fake), D fwd+bwd (real)
+    def part_a(timer=None):                 # update_G: G fwd+bwd, D fwd+bwd
         G.forward_backward(timer)
         D.forward_backward(timer)
-        if world > 1:
-            dist.all_reduce(flat_g)
-            postprocess_(flat_g, 1.0 / world)
+
+    def part_b(timer=None):                 # update_D: G fwd, D fwd+bwd (fake), D fwd+bwd (real)
         G.forward_only()
         D.forward_backward(timer)
         D.forward_backward(timer)
+
+    graphs = {}
+
+    def step(timer=None, e2e=False, eager=False, prefill=False):
+        if e2e:
+            dev_video.copy_(host_video, non_blocking=True)
+        if prefill:                          # see the roofline pass below
+            torch.cuda._sleep(prefill)
+        if graphs and not eager:
+            graphs['a'].replay()
+        else:
+            part_a(timer)
+        if world > 1:
+            dist.all_reduce(flat_g)
+            postprocess_(flat_g, 1.0 / world)
+        if prefill:
+            torch.cuda._sleep(prefill)
+        if graphs and not eager:
+            graphs['b'].replay()
+        else:
+            part_b(timer)
         if world > 1:
             dist.all_reduce(flat_d)
             postprocess_(flat_d, 1.0 / world)
@@ -382,12 +414,12 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(nsteps, e2e, timer=None):
+    def timed(nsteps, e2e, timer=None, eager=False):
         barrier()
         t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0.record()
         for _ in range(nsteps):
-            step(timer, e2e)
+            step(timer, e2e, eager)
         t1.record()
         barrier()
         ms = torch.tensor([t0.elapsed_time(t1)], device=device)
@@ -403,15 +435,46 @@ def main():
         step()
         torch.cuda.synchronize()
         warm_steps += 1
-    step(KernelTimer())                      # untimed: same code path as the timed region (event pairs included)
+    launches_per_step = None
+    if args.launch == 'graph':
+        # Capture the two halves of the step (the gradient all-reduces stay outside: eager NCCL calls between the replays).
+        # Launch counting happens while capturing: exactly one step's kernels.
+        pool = None
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        launches0 = custom_ops.launch_count()
+        with torch.cuda.stream(side):
+            for name, fn in (('a', part_a), ('b', part_b)):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, pool=pool, stream=side, capture_error_mode='thread_local'):
+                    fn()
+                pool = g.pool()
+                graphs[name] = g
+        torch.cuda.current_stream().wait_stream(side)
+        launches_per_step = custom_ops.launch_count() - launches0
+        for _ in range(3):
+            step()
+        torch.cuda.synchronize()
+    else:
+        step(KernelTimer())                  # untimed: same code path as the timed region (event pairs included)
     launches0 = custom_ops.launch_count()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     timer = KernelTimer()
-    ms_total = timed(args.steps, e2e=False, timer=timer)
-    launches = custom_ops.launch_count() - launches0
+    ms_total = timed(args.steps, e2e=False, timer=None if graphs else timer)
+    launches = launches_per_step * args.steps if graphs else custom_ops.launch_count() - launches0
     step(e2e=True)                           # untimed warm-up of the host-copy flavour
     ms_e2e = timed(args.steps, e2e=True)
+    ms_e2e_eager = timed(args.steps, e2e=True, eager=True) if graphs else ms_e2e
     clocks = sampler.finish() if sampler is not None else None
+    if graphs:
+        # Per-kernel timing for the roofline: graph nodes cannot carry timing events, so one extra EAGER step is timed
+        # with an event pair around every bias_act call. The stream is pre-filled with a ~30 ms spin kernel before
+        # each half so that the host runs ahead and the pairs bracket kernel execution, not Python launch latency.
+        spin = int(0.03 * 1.9e9)
+        step(KernelTimer(), eager=True, prefill=spin)
+        torch.cuda.synchronize()
+        step(timer, eager=True, prefill=spin)
+        torch.cuda.synchronize()
 
     frames_per_step = batch * frames * world
     value = frames_per_step * args.steps / (ms_total / 1000.0)
@@ -419,16 +482,24 @@ def main():
     k_ms, k_bytes, k_n = timer.summary()
     peak, peak_src = measured_peak()
     achieved = k_bytes / (k_ms / 1000.0) / 1e9 if k_ms > 0 else 0.0
+    if graphs:
+        k_share = k_ms / (ms_total / args.steps) if ms_total else None
+        k_how = ('CUDA events around every bias_act call of one extra eager step (stream pre-filled by a spin kernel so that the '
+                 'pairs bracket execution, not launch latency); the timed region itself replays CUDA graphs')
+    else:
+        k_share = k_ms / ms_total if ms_total else None
+        k_how = 'CUDA events around every bias_act call inside the timed region'
 
     if rank == 0:
         out = {'metric': metric, 'value': value, 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps, 'warmup': warm_steps + 1,
                'ms_per_step': ms_total / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
                'dtype': 'f32' if policy == 'fp32' else 'f16/f32 mixed (fp16 layers as the reference config)', 'data': 'synthetic',
                'config': config, 'gpu_launches': int(launches),
-               'e2e': {'value': e2e_value, 'unit': 'frames/s', 'h2d_bytes_per_step': host_video.numel() * 4, 'd2h_bytes_per_step': 4},
+               'e2e': {'value': e2e_value, 'unit': 'frames/s', 'h2d_bytes_per_step': host_video.numel() * 4, 'd2h_bytes_per_step': 4,
+                       'eager_value': frames_per_step * args.steps / (ms_e2e_eager / 1000.0)},
                'roofline': {'bound': 'hbm', 'kernel': 'bias_act (vector kernel, forward + fused dx/db backward)', 'achieved': achieved,
                             'peak': peak, 'peak_source': peak_src, 'unit': 'GB/s', 'frac': achieved / peak if peak else None,
-                            'launches_timed': k_n, 'share_of_step': k_ms / ms_total if ms_total else None, 'traffic': None},
+                            'launches_timed': k_n, 'share_of_step': k_share, 'traffic': None, 'timing': k_how},
                'clocks': clocks}
         if not args.no_cpu:
             fps, desc, threads = cpu_sample(args.workload, budget_s=args.cpu_budget)

@@ -30,9 +30,9 @@ constexpr int kWarp = 32;
 
 // n / d for small non-negative n without the integer-division sequence
 struct FastDiv {
-    unsigned magic;   // ceil(2^32 / d); exact for n * d < 2^32
+    unsigned magic;   // ceil(2^32 / d) = floor((2^32 - 1) / d) + 1 for d > 1 (32-bit division only); exact for n * d < 2^32
     int d;
-    __host__ __device__ explicit FastDiv(int d_ = 1) : magic(d_ > 1 ? (unsigned)((0x100000000ull + (unsigned)d_ - 1) / (unsigned)d_) : 0u), d(d_) {}
+    __host__ __device__ explicit FastDiv(int d_ = 1) : magic(d_ > 1 ? 0xFFFFFFFFu / (unsigned)d_ + 1u : 0u), d(d_) {}
     __device__ __forceinline__ int div(int n) const { return d > 1 ? (int)__umulhi((unsigned)n, magic) : n; }
 };
 

@@ -22,6 +22,10 @@ namespace lvg {
 
 int upfirdn2d_check(const void* x, const void* y, int dtype, const int64_t* xsh, const int64_t* ysh,
                     int fw, int fh, int upx, int upy, int downx, int downy);
+int upfirdn2d_stream(const void* x, const float* fx, int64_t fsx, const float* fy, int64_t fsy, void* y, int dtype,
+                     const int64_t* xsh, const int64_t* xst, const int64_t* ysh, const int64_t* yst,
+                     int fw, int fh, int upx, int upy, int downx, int downy, int padx0, int pady0,
+                     int flip, float gain, cudaStream_t s);
 
 namespace {
 
@@ -40,7 +44,9 @@ struct TiledParams {
     float gain;
     int tow, toh, tiles_x, tiles_y;
     int pb;               // planes per CTA (> 1 only when one tile covers the whole plane)
-    int flat;             // 1: the CTA's input planes are one contiguous, 16-byte aligned block (vector loader)
+    int flat;             // 1: the CTA's input planes are one contiguous, 16-byte aligned block (vector loader);
+                          // 2: additionally every input element lies inside the tile (no bounds checks)
+    fir::FastDiv by_plane_elems, by_iw;   // host-made dividers of the vector loader
     int64_t planes;       // n * c
     int p_in, p_mid;      // row pitches (odd)
     int a_size;           // floats reserved for the input tile(s)
@@ -64,6 +70,126 @@ __host__ __device__ constexpr int mid_extent(int n)
     return KIND == AX_UP ? fir::round_up((n + S - 1 + S - 1) / S, kR) * S : fir::round_up(n, kR);
 }
 
+
+// ---- y passes that store straight to global memory.
+// Same item decomposition as fir::up_y2 / fir::down_y2 (lane L owns columns L and L + 32 of a 64-column span,
+// R groups / outputs along y per item), but the store addresses are formed ONCE per item as two 64-bit column
+// pointers; every result then costs one pointer bump and one store, and items that lie completely inside the
+// tile (all but the first / last along y) take a path without row checks. `ys*` are element strides of y; the
+// host guarantees that one CTA's outputs span < 2^31 elements.
+template <class T> __device__ __forceinline__ T* opaque(T* p)
+{
+    asm volatile("" : "+l"(p));      // keeps the compiler from re-deriving the pointer from its 64-bit offset form per store
+    __builtin_assume(__isGlobal(p));
+    return p;
+}
+
+template <class T, int UP, int F, int R, int NTHREADS>
+__device__ __forceinline__ void up_y2_store(const float* __restrict__ in, int pin, int cols, int groups, const float* __restrict__ s_taps,
+                                            T* yp, int ys1, int ys2, int ys3, int dyo, int toh_e, int nplanes, int plane_rows)
+{
+    constexpr int K = F / UP;
+    float2 g[F];
+#pragma unroll
+    for (int i = 0; i < F; i++) g[i] = make_float2(s_taps[i], s_taps[i]);
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    const int gthreads = (groups + R - 1) / R;
+    const int vcols = nplanes * cols;
+    const int n_cc = (vcols + 63) / 64;
+    const fir::FastDiv by_cols(cols), by_cc(n_cc);
+    for (int wi = warp; wi < gthreads * n_cc; wi += NTHREADS / 32) {
+        const int tg = by_cc.div(wi), cc = wi - tg * n_cc;
+        const int va = cc * 64 + lane, vb = va + 32;
+        if (va < vcols) {
+            const bool has_b = vb < vcols;
+            const int pla = nplanes > 1 ? by_cols.div(va) : 0, cola = va - pla * cols;
+            const int plb = has_b ? (nplanes > 1 ? by_cols.div(vb) : 0) : pla, colb = has_b ? vb - plb * cols : cola;
+            const float* sa = in + (pla * plane_rows + tg * R) * pin + cola;
+            const float* sb = in + (plb * plane_rows + tg * R) * pin + colb;
+            float2 v[K + R];
+#pragma unroll
+            for (int i = 0; i < K + R; i++) v[i] = make_float2(sa[i * pin], sb[i * pin]);
+            const int o0 = tg * R * UP - dyo;                       // output row of the item's first result (may be < 0)
+            T* pa = opaque(yp + (pla * ys1 + cola * ys3 + o0 * ys2));
+            T* pb = opaque(yp + (plb * ys1 + colb * ys3 + o0 * ys2));
+            const bool full = o0 >= 0 && o0 + R * UP <= toh_e;      // warp-uniform
+            if (full) {
+#pragma unroll
+                for (int j = 0; j < R; j++) {
+#pragma unroll
+                    for (int ph = 0; ph < UP; ph++) {
+                        float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+                        for (int k = 0; k < K; k++) acc = fir::ffma2(g[(UP - ph) % UP + k * UP], v[j + (ph > 0 ? 1 : 0) + k], acc);
+                        *pa = from_acc<T>(acc.x);
+                        if (has_b) *pb = from_acc<T>(acc.y);
+                        pa += ys2; pb += ys2;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < R; j++) {
+#pragma unroll
+                    for (int ph = 0; ph < UP; ph++) {
+                        float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+                        for (int k = 0; k < K; k++) acc = fir::ffma2(g[(UP - ph) % UP + k * UP], v[j + (ph > 0 ? 1 : 0) + k], acc);
+                        if ((unsigned)(o0 + j * UP + ph) < (unsigned)toh_e) {
+                            *pa = from_acc<T>(acc.x);
+                            if (has_b) *pb = from_acc<T>(acc.y);
+                        }
+                        pa += ys2; pb += ys2;
+                    }
+                }
+            }
+        }
+    }
+}
+
+template <class T, int DOWN, int F, int R, int NTHREADS>
+__device__ __forceinline__ void down_y2_store(const float* __restrict__ in, int pin, int cols, int outs, const float* __restrict__ s_taps,
+                                              T* yp, int ys1, int ys2, int ys3, int nplanes, int plane_rows)
+{
+    constexpr int NIN = (R - 1) * DOWN + F;
+    float2 g[F];
+#pragma unroll
+    for (int i = 0; i < F; i++) g[i] = make_float2(s_taps[i], s_taps[i]);
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    const int gthreads = (outs + R - 1) / R;
+    const int vcols = nplanes * cols;
+    const int n_cc = (vcols + 63) / 64;
+    const fir::FastDiv by_cols(cols), by_cc(n_cc);
+    for (int wi = warp; wi < gthreads * n_cc; wi += NTHREADS / 32) {
+        const int tg = by_cc.div(wi), cc = wi - tg * n_cc;
+        const int va = cc * 64 + lane, vb = va + 32;
+        if (va < vcols) {
+            const bool has_b = vb < vcols;
+            const int pla = nplanes > 1 ? by_cols.div(va) : 0, cola = va - pla * cols;
+            const int plb = has_b ? (nplanes > 1 ? by_cols.div(vb) : 0) : pla, colb = has_b ? vb - plb * cols : cola;
+            const float* sa = in + (pla * plane_rows + tg * R * DOWN) * pin + cola;
+            const float* sb = in + (plb * plane_rows + tg * R * DOWN) * pin + colb;
+            float2 v[NIN];
+#pragma unroll
+            for (int i = 0; i < NIN; i++) v[i] = make_float2(sa[i * pin], sb[i * pin]);
+            const int o0 = tg * R;
+            T* pa = opaque(yp + (pla * ys1 + cola * ys3 + o0 * ys2));
+            T* pb = opaque(yp + (plb * ys1 + colb * ys3 + o0 * ys2));
+            const bool full = o0 + R <= outs;                       // warp-uniform
+#pragma unroll
+            for (int j = 0; j < R; j++) {
+                float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int t = 0; t < F; t++) acc = fir::ffma2(g[t], v[j * DOWN + t], acc);
+                if (full || o0 + j < outs) {
+                    *pa = from_acc<T>(acc.x);
+                    if (has_b) *pb = from_acc<T>(acc.y);
+                }
+                pa += ys2; pb += ys2;
+            }
+        }
+    }
+}
+
 template <class T, int KX, int SX, int FX, int KY, int SY, int FY>
 __global__ void __launch_bounds__(kThreads) upfirdn2d_tiled_kernel(TiledParams p)
 {
@@ -77,19 +203,22 @@ __global__ void __launch_bounds__(kThreads) upfirdn2d_tiled_kernel(TiledParams p
     float* s_fy = s_fx + FX;
 
     // CTA -> (first plane, tile). With pb > 1 the CTA owns pb whole planes (tiles_x == tiles_y == 1).
-    const int tiles = p.tiles_x * p.tiles_y;
-    const int64_t plane0 = (p.pb > 1) ? (int64_t)blockIdx.x * p.pb : (int64_t)(blockIdx.x / tiles);
-    const int tile = (p.pb > 1) ? 0 : (int)(blockIdx.x - plane0 * tiles);
-    const int npl = (p.pb > 1) ? (int)min((int64_t)p.pb, p.planes - plane0) : 1;
-    const int ty = tile / p.tiles_x, tx = tile - ty * p.tiles_x;
+    // (all 32-bit: the host bounds the grid by 2^31 - 1, so plane indices fit)
+    const unsigned tiles = (unsigned)(p.tiles_x * p.tiles_y);
+    const unsigned plane0 = (p.pb > 1) ? blockIdx.x * (unsigned)p.pb : (tiles > 1 ? blockIdx.x / tiles : blockIdx.x);
+    const int tile = (p.pb > 1 || tiles == 1) ? 0 : (int)(blockIdx.x - plane0 * tiles);
+    const int npl = (p.pb > 1) ? (int)min((int64_t)p.pb, p.planes - (int64_t)plane0) : 1;
+    const int ty = (p.tiles_x > 1) ? tile / p.tiles_x : tile, tx = tile - ty * p.tiles_x;
     const int ox0 = tx * p.tow, oy0 = ty * p.toh;
     const int tow_e = min(p.tow, p.ow - ox0), toh_e = min(p.toh, p.oh - oy0);
     // plane -> memory offset: pb > 1 requires stride[0] == C * stride[1] (checked on the host)
-    const int64_t xoff0 = (p.pb > 1) ? plane0 * p.xs[1] : (plane0 / p.c) * p.xs[0] + (plane0 % p.c) * p.xs[1];
-    const int64_t yoff0 = (p.pb > 1) ? plane0 * p.ys[1] : (plane0 / p.c) * p.ys[0] + (plane0 % p.c) * p.ys[1];
+    const unsigned pn = plane0 / (unsigned)p.c, pc = plane0 - pn * (unsigned)p.c;
+    const int64_t xoff0 = (p.pb > 1) ? (int64_t)plane0 * p.xs[1] : (int64_t)pn * p.xs[0] + (int64_t)pc * p.xs[1];
+    const int64_t yoff0 = (p.pb > 1) ? (int64_t)plane0 * p.ys[1] : (int64_t)pn * p.ys[0] + (int64_t)pc * p.ys[1];
 
+    // taps oriented for correlation; the gain is folded into the taps of the y pass (or applied on store when there is none)
     if (KX != AX_ID) for (int i = threadIdx.x; i < FX; i += kThreads) s_fx[i] = p.flip ? p.fx[i * p.fsx] : p.fx[(FX - 1 - i) * p.fsx];
-    if (KY != AX_ID) for (int i = threadIdx.x; i < FY; i += kThreads) s_fy[i] = p.flip ? p.fy[i * p.fsy] : p.fy[(FY - 1 - i) * p.fsy];
+    if (KY != AX_ID) for (int i = threadIdx.x; i < FY; i += kThreads) s_fy[i] = p.gain * (p.flip ? p.fy[i * p.fsy] : p.fy[(FY - 1 - i) * p.fsy]);
 
     // per-axis geometry: first input sample of the tile, how many to load, phase offsets
     int in_x0, in_w, nqx = 0, dxo = 0;
@@ -130,7 +259,8 @@ __global__ void __launch_bounds__(kThreads) upfirdn2d_tiled_kernel(TiledParams p
         const T* xp = (const T*)p.x + xoff0;
         const int plane_elems = p.ih * p.iw;
         const int nvec = npl * plane_elems / V;
-        const fir::FastDiv by_plane(plane_elems), by_w(p.iw);
+        const fir::FastDiv by_plane = p.by_plane_elems, by_w = p.by_iw;
+        const bool inside = p.flat == 2;
         constexpr int kBatch = 4;
         for (int base = threadIdx.x; base < nvec; base += kThreads * kBatch) {
             Pack<T> v[kBatch];
@@ -149,8 +279,11 @@ __global__ void __launch_bounds__(kThreads) upfirdn2d_tiled_kernel(TiledParams p
                     const int gy = by_w.div(rem);
                     const int gx = rem - gy * p.iw;
                     const int iy = gy - in_y0, ix = gx - in_x0;
-                    if (iy >= 0 && iy < in_h) {
-                        float* dst = tin + (pl * in_h + iy) * p.p_in + ix;
+                    float* dst = tin + (pl * in_h + iy) * p.p_in + ix;
+                    if (inside) {
+#pragma unroll
+                        for (int k = 0; k < V; k++) dst[k] = to_acc(v[j].v[k]);
+                    } else if (iy >= 0 && iy < in_h) {
 #pragma unroll
                         for (int k = 0; k < V; k++)
                             if (ix + k >= 0 && ix + k < in_w) dst[k] = to_acc(v[j].v[k]);
@@ -196,25 +329,22 @@ __global__ void __launch_bounds__(kThreads) upfirdn2d_tiled_kernel(TiledParams p
 
     // ---- y pass -> global. The store address of a thread item is formed once (64-bit), results then only
     // add a 32-bit row offset (the host guarantees that a plane spans < 2^31 elements).
+    // yp is CTA-uniform; every result adds an unsigned 32-bit element offset (the host guarantees that the
+    // outputs of one CTA span < 2^31 elements), so no per-result 64-bit address arithmetic is left.
     T* yp = (T*)p.y + yoff0 + (int64_t)oy0 * p.ys[2] + (int64_t)ox0 * p.ys[3];
     const float gain = p.gain;
     const float* src = tmid + dxo + xshift;
-    const int64_t ys1 = p.ys[1], ys3 = p.ys[3];
-    const int ys2 = (int)p.ys[2];
-    auto col_base = [&](int pl, int col) { return yp + pl * ys1 + col * ys3; };
+    const int ys1 = (int)p.ys[1], ys2 = (int)p.ys[2], ys3 = (int)p.ys[3];
     if constexpr (KY == AX_UP) {
-        fir::up_y2<SY, FY, kR, kThreads>(src, pmid, tow_e, nqy, s_fy,
-            fir::make_emitter(col_base, [&](T* base, int a, float acc) {
-                const int o = a - dyo;
-                if ((unsigned)o < (unsigned)toh_e) base[o * ys2] = from_acc<T>(acc * gain);
-            }), npl, in_h);
+        up_y2_store<T, SY, FY, kR, kThreads>(src, pmid, tow_e, nqy, s_fy, yp, ys1, ys2, ys3, dyo, toh_e, npl, in_h);
     } else if constexpr (KY == AX_DOWN) {
         if constexpr (FY <= 12) {
-            fir::down_y2<SY, FY, kR, kThreads>(src, pmid, 0, tow_e, toh_e, s_fy,
-                fir::make_emitter(col_base, [&](T* base, int o, float acc) { base[o * ys2] = from_acc<T>(acc * gain); }), npl, in_h);
+            down_y2_store<T, SY, FY, kR, kThreads>(src, pmid, tow_e, toh_e, s_fy, yp, ys1, ys2, ys3, npl, in_h);
         } else {
+            const unsigned uys1 = (unsigned)ys1, uys2 = (unsigned)ys2, uys3 = (unsigned)ys3;
             fir::down_y<SY, FY, kR, kThreads>(src, pmid, 0, tow_e, toh_e, s_fy,
-                fir::make_emitter(col_base, [&](T* base, int o, float acc) { base[o * ys2] = from_acc<T>(acc * gain); }), npl, in_h);
+                fir::make_emitter([&](int pl, int col) { return (unsigned)pl * uys1 + (unsigned)col * uys3; },
+                                  [&](unsigned off, int o, float acc) { yp[off + (unsigned)o * uys2] = from_acc<T>(acc); }), npl, in_h);
         }
     } else {
         const int per = toh_e * tow_e;
@@ -223,7 +353,7 @@ __global__ void __launch_bounds__(kThreads) upfirdn2d_tiled_kernel(TiledParams p
             const int pl = npl > 1 ? by_per.div(idx) : 0;
             const int rem = idx - pl * per;
             const int o = by_w.div(rem), col = rem - o * tow_e;
-            yp[pl * ys1 + o * (int64_t)ys2 + col * ys3] = from_acc<T>(src[(pl * in_h + o) * pmid + col] * gain);
+            yp[(unsigned)(pl * ys1 + o * ys2 + col * ys3)] = from_acc<T>(src[(pl * in_h + o) * pmid + col] * gain);
         }
     }
 }
@@ -245,7 +375,11 @@ int pick_tow(int ow)
 template <class T, int KX, int SX, int FX, int KY, int SY, int FY>
 int launch_tiled(TiledParams& p, cudaStream_t s)
 {
-    constexpr int kTargetOutputs = 8192;        // outputs per CTA the tile/plane batching aims for
+    static const int kTargetOutputs = [] {      // outputs per CTA the tile/plane batching aims for
+        const char* e = getenv("LVG_UPFIRDN_TARGET");
+        const int v = e ? atoi(e) : 0;
+        return v >= 1024 ? v : 16384;
+    }();
     constexpr size_t kSmemBudget = 56 * 1024;   // keeps 4 CTAs resident per SM
     p.tow = pick_tow(p.ow);
     int toh = kTargetOutputs / (p.tow > 0 ? p.tow : 1);
@@ -260,7 +394,9 @@ int launch_tiled(TiledParams& p, cudaStream_t s)
         const int mid = (KX == AX_ID) ? 0 : pb_ * in_h * p.p_mid;
         return (size_t)(p.a_size + mid + FX + FY) * sizeof(float);
     };
-    size_t smem = smem_for(toh, 1);
+    // the whole plane fits: one tile per plane (vector loader, no halo re-reads, plane batching below)
+    if (p.tow == p.ow && smem_for(p.oh, 1) <= kSmemBudget) toh = p.oh;
+    size_t smem = smem_for(toh, 1);       // (smem_for also records the pitches / tile sizes in p: call it last for the choice made)
     while (smem > kSmemBudget && toh > 4) {
         toh = fir::round_up(toh / 2, 4);
         smem = smem_for(toh, 1);
@@ -284,6 +420,25 @@ int launch_tiled(TiledParams& p, cudaStream_t s)
     constexpr int V = VecOf<T>::N;
     p.flat = (p.tiles_x == 1 && p.tiles_y == 1 && p.xs[3] == 1 && p.xs[2] == p.iw && p.xs[1] == (int64_t)p.ih * p.iw &&
               (p.pb == 1 || uniform) && p.iw % V == 0 && p.xs[0] % V == 0 && aligned16(p.x) && (int64_t)p.pb * p.ih * p.iw < (1 << 24)) ? 1 : 0;
+    if (p.flat) {
+        p.by_plane_elems = fir::FastDiv(p.ih * p.iw);
+        p.by_iw = fir::FastDiv(p.iw);
+        // does the (single) tile contain every input sample? then the scatter needs no bounds checks
+        const int in_x0 = KX == AX_UP ? floordiv(-p.padx0, SX) : -p.padx0;
+        const int in_y0 = KY == AX_UP ? floordiv(-p.pady0, SY) : -p.pady0;
+        const int in_w = KX == AX_UP ? fir::round_up((p.ow + (-p.padx0 - in_x0 * SX) + SX - 1) / SX, kR) + FX / SX
+                       : KX == AX_DOWN ? (p.ow - 1) * SX + FX : p.ow;
+        const int in_h = KY == AX_UP ? fir::round_up((p.oh + (-p.pady0 - in_y0 * SY) + SY - 1) / SY, kR) + FY / SY
+                       : KY == AX_DOWN ? (p.oh - 1) * SY + FY : p.oh;
+        if (in_x0 <= 0 && in_y0 <= 0 && p.iw - in_x0 <= in_w && p.ih - in_y0 <= in_h) p.flat = 2;
+    }
+    // 32-bit output offsets inside one CTA's share of y
+    {
+        auto mag = [](int64_t v) { return v < 0 ? -v : v; };
+        for (int i = 0; i < 4; i++) if (p.ys[i] < 0) return LVG_UNSUPPORTED;
+        const int64_t span = (int64_t)(p.pb - 1) * mag(p.ys[1]) + (int64_t)(p.toh - 1) * mag(p.ys[2]) + (int64_t)(p.tow - 1) * mag(p.ys[3]);
+        if (span >= (1ll << 31) || p.ys[1] >= (1ll << 32) || p.ys[2] >= (1ll << 32) || p.ys[3] >= (1ll << 32)) return LVG_UNSUPPORTED;
+    }
     const int64_t blocks = p.pb > 1 ? (p.planes + p.pb - 1) / p.pb : p.planes * p.tiles_x * p.tiles_y;
     if (blocks > INT32_MAX) return LVG_UNSUPPORTED;
     // (A persistent grid that prefetched the next work item's vectors into registers measured 5-60 % slower on
@@ -341,7 +496,11 @@ int upfirdn2d_tiled(const void* x, const float* fx, int64_t fsx, const float* fy
                     int flip, float gain, cudaStream_t s)
 {
     if (dtype != LVG_F32 && dtype != LVG_F16) return LVG_UNSUPPORTED;
-    if (ysh[2] * (yst[2] < 0 ? -yst[2] : yst[2]) >= (1ll << 31)) return LVG_UNSUPPORTED;     // 32-bit row offsets inside a plane
+    // the 2x / 4-tap signatures of the low-res networks stream through registers (upfirdn2d_stream.cu)
+    {
+        const int rc = upfirdn2d_stream(x, fx, fsx, fy, fsy, y, dtype, xsh, xst, ysh, yst, fw, fh, upx, upy, downx, downy, padx0, pady0, flip, gain, s);
+        if (rc != LVG_UNSUPPORTED) return rc;
+    }
     const Axis ax = classify(fx != nullptr, upx, downx, fw), ay = classify(fy != nullptr, upy, downy, fh);
     if (ax.kind < 0 || ay.kind < 0) return LVG_UNSUPPORTED;
     TiledParams p;

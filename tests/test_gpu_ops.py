@@ -178,6 +178,48 @@ def test_upfirdn2d_separable_vs_oracle(shape, taps, kw, dtype):
     assert_close(ycl, ref, tol(dtype, 1e-5), 'channels_last')
 
 
+STREAM_SHAPES = [
+    # (x shape, kwargs): signatures of the register-streaming kernel (upfirdn2d_stream.cu) -- strips per row 1..32,
+    # plane counts that leave part of a warp idle, planes tall enough to be split into row segments
+    ((1, 3, 18, 32), dict(up=2, padding=[2, 1, 2, 1], gain=4)),
+    ((2, 5, 5, 8), dict(up=2, padding=[2, 1, 2, 1], gain=4)),
+    ((1, 7, 9, 16), dict(up=2, padding=[2, 1, 2, 1], gain=4, flip_filter=True)),
+    ((1, 2, 200, 128), dict(up=2, padding=[2, 1, 2, 1], gain=4)),
+    ((1, 3, 64, 64), dict(down=2, padding=[1, 1, 1, 1])),
+    ((3, 11, 8, 8), dict(down=2, padding=[1, 1, 1, 1], flip_filter=True)),
+    ((1, 1, 36, 64), dict(down=2, padding=[1, 1, 1, 1], gain=0.5)),
+    ((1, 2, 300, 256), dict(down=2, padding=[1, 1, 1, 1])),
+    ((1, 5, 32, 16), dict(down=2, padding=[1, 1, 1, 1])),
+]
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.float16])
+@pytest.mark.parametrize('shape,kw', STREAM_SHAPES)
+def test_upfirdn2d_streamed_signatures_vs_oracle(shape, kw, dtype):
+    gen = torch.Generator().manual_seed(shape[1] * 31 + shape[2])
+    x = torch.randn(*shape, generator=gen).to(dtype)
+    f = torch.rand(4, generator=gen) + 0.1          # asymmetric: catches orientation / phase mix-ups
+    xd = x.to(DEV).requires_grad_(True)
+    y = upfirdn2d.upfirdn2d(xd, f.to(DEV), **kw)
+    ref = orc.upfirdn2d(x.float().numpy(), f.numpy(), **kw)
+    assert_close(y, ref, tol(dtype, 1e-5), 'forward')
+    # backward = the adjoint signature (UP2 <-> DOWN2), also streamed
+    dy = torch.randn(y.shape, generator=gen).to(dtype)
+    dx, = torch.autograd.grad(y, [xd], dy.to(DEV))
+    ref_dx = orc.upfirdn2d_adjoint(dy.float().numpy(), f.numpy(), x.shape, **kw)
+    assert_close(dx, ref_dx, tol(dtype, 1e-5), 'adjoint')
+    # one-axis variants (temporal resampling of [N, C, T, H*W] tensors)
+    kw1 = dict(kw)
+    kw1['padding'] = [0, 0] + list(kw['padding'][2:])
+    for key in ('up', 'down'):
+        if key in kw1:
+            kw1[key] = [1, kw1[key]]
+    if 'gain' in kw1 and 'up' in kw1:
+        kw1['gain'] = 2
+    y1 = upfirdn2d.upfirdn2d(x.to(DEV), f[:, None].to(DEV), **kw1)
+    assert_close(y1, orc.upfirdn2d(x.float().numpy(), f[:, None].numpy(), **kw1), tol(dtype, 1e-5), 'y axis only')
+
+
 @pytest.mark.parametrize('dtype', [torch.float32, torch.float16])
 def test_upfirdn2d_temporal_axis_vs_oracle(dtype):
     # filters along H only on [N, C, T, H*W] tensors (U1, U2, U5)
