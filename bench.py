@@ -490,6 +490,17 @@ def main():
         k_share = k_ms / ms_total if ms_total else None
         k_how = 'CUDA events around every bias_act call inside the timed region'
 
+    traffic, traffic_note = None, None
+    try:        # DRAM bytes of the dominant kernel from the committed ncu --set full capture (bench.py never runs under ncu)
+        tr = json.load(open(os.path.join(ROOT, 'profiles', 'r01_traffic.json')))
+        f, b = tr['bias_act_fwd'], tr['bias_act_bwd_fused_db']
+        traffic = (f['dram_read'] + f['dram_write'] + b['dram_read'] + b['dram_write']) / 2.0
+        traffic_note = (f"mean DRAM bytes per launch (one forward + one fused backward launch) at {tr['shape']}; algorithmic "
+                        f"{(f['algorithmic'] + b['algorithmic']) / 2.0:.0f} B; {tr['source']}")
+    except Exception:
+        pass
+    if rank == 0 and args.workload != 'lres':
+        traffic, traffic_note = None, None
     if rank == 0:
         out = {'metric': metric, 'value': value, 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps, 'warmup': warm_steps + 1,
                'ms_per_step': ms_total / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
@@ -499,7 +510,7 @@ def main():
                        'eager_value': frames_per_step * args.steps / (ms_e2e_eager / 1000.0)},
                'roofline': {'bound': 'hbm', 'kernel': 'bias_act (vector kernel, forward + fused dx/db backward)', 'achieved': achieved,
                             'peak': peak, 'peak_source': peak_src, 'unit': 'GB/s', 'frac': achieved / peak if peak else None,
-                            'launches_timed': k_n, 'share_of_step': k_share, 'traffic': None, 'timing': k_how},
+                            'launches_timed': k_n, 'share_of_step': k_share, 'traffic': traffic, 'traffic_note': traffic_note, 'timing': k_how},
                'clocks': clocks}
         if not args.no_cpu:
             fps, desc, threads = cpu_sample(args.workload, budget_s=args.cpu_budget)

@@ -69,6 +69,15 @@ def main():
             y = bias_act.bias_act(xg, bg, act='lrelu', clamp=256)
             dy = torch.randn_like(y)
             run(f'bias_act bwd dx+db {tag} {shape}', lambda: torch.autograd.grad(y, [xg, bg], dy, retain_graph=True), 3 * n * sz)
+            if len(shape) == 5:
+                from torch_utils import custom_ops
+                plug = custom_ops.get_plugin('bias_act_plugin')
+                yd = y.detach()
+                run(f'bias_act bwd dx only (grad=1 kernel) {tag} {shape}',
+                    lambda: plug.bias_act(dy, b, None, yd, None, 1, 1, 3, 0.2, 2 ** 0.5, 256.0), 3 * n * sz)
+                out = torch.empty_like(x)
+                run(f'bias_act ref 2R1W torch.add {tag} {shape}', lambda: torch.add(x, dy, out=out), 3 * n * sz)
+                run(f'bias_act ref 1R1W torch.copy {tag} {shape}', lambda: out.copy_(x), 2 * n * sz)
             del x, xg, y, dy
         f4 = upfirdn2d.setup_filter([1, 3, 3, 1], separable=True).to(DEV)
         lin = (torch.tensor([1., 3., 3., 1.], device=DEV) / 8)[:, None]
