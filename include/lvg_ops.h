@@ -187,6 +187,15 @@ int lvg_conv2d_dgrad(const void* dy, const void* w, void* dx, int dtype,
                      int n, int groups, int cin, int cout, int h, int wd,
                      int kh, int kw, int stride, int pad_h, int pad_w,
                      void* workspace, int64_t workspace_bytes, void* stream);
+/*
+ * Gradient of the same convolution with respect to its weights: dw [G*Cout][Cin][kh][kw] (fp16, summed
+ * over the N samples) from x [N][G*Cin][H][W] and dy [N][G*Cout][Ho][Wo]. Replaces the weight-gradient
+ * leg of conv2d_gradfix (conv2d_gradfix.py:119-141 -> aten::convolution_backward / cuDNN). The argument
+ * list describes the FORWARD convolution. No workspace. Returns -1 outside fp16 / stride 1 / 3x3, 1x1.
+ */
+int lvg_conv2d_wgrad(const void* x, const void* dy, void* dw, int dtype,
+                     int n, int groups, int cin, int cout, int h, int wd,
+                     int kh, int kw, int stride, int pad_h, int pad_w, void* stream);
 
 /*
  * Post-processing of an all-reduced flat gradient buffer, in place and in one pass:

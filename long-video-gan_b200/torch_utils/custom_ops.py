@@ -56,6 +56,7 @@ _SIGNATURES = {
     'lvg_conv2d_fprop': (_c_int, [_c_void_p] * 3 + [_c_int] * 12 + [_c_void_p, _c_i64, _c_void_p]),
     'lvg_conv2d_fprop_workspace': (_c_i64, [_c_int] * 12),
     'lvg_conv2d_dgrad': (_c_int, [_c_void_p] * 3 + [_c_int] * 12 + [_c_void_p, _c_i64, _c_void_p]),
+    'lvg_conv2d_wgrad': (_c_int, [_c_void_p] * 3 + [_c_int] * 12 + [_c_void_p]),
 }
 
 LVG_UNSUPPORTED = -1
@@ -484,6 +485,21 @@ class Conv2dPlugin:
         if rc == LVG_UNSUPPORTED:
             raise RuntimeError('conv2d_dgrad: ' + self._lib.lvg_last_error().decode())
         return dx
+
+    def wgrad(self, x, dy, w_shape, padding, groups):
+        """dw [G*Cout, Cin, kh, kw] (fp16, summed over the batch) from x and dy."""
+        x, dy = x.contiguous(), dy.contiguous()
+        n, ctot, h, wd = x.shape
+        cout_tot, cin, kh, kw = w_shape
+        ph, pw = padding
+        cout = cout_tot // groups
+        dw = torch.empty(list(w_shape), dtype=x.dtype, device=x.device)
+        with _DeviceGuard(x):
+            rc = _check(self._lib.lvg_conv2d_wgrad(_ptr(x), _ptr(dy), _ptr(dw), 1, n, groups, cin, cout, h, wd, kh, kw, 1, ph, pw,
+                                                   _stream(x)), 'conv2d_wgrad')
+        if rc == LVG_UNSUPPORTED:
+            raise RuntimeError('conv2d_wgrad: ' + self._lib.lvg_last_error().decode())
+        return dw
 
 
 _PLUGIN_CLASSES = {

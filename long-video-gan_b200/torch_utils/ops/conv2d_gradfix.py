@@ -9,6 +9,7 @@ grouped "modulated" 3x3 / 1x1 convolutions in fp16) are routed to it through
 ``_native`` below; everything else goes to ``torch.nn.functional``.
 """
 import contextlib
+import os
 
 import torch
 
@@ -113,12 +114,19 @@ class _Conv2dDgrad(torch.autograd.Function):
 
 
 class _Conv2dWgrad(torch.autograd.Function):
-    """dw: the reduction over pixels is not on the tensor-core kernel yet -- ATen / cuDNN weight gradient."""
+    """dw = sum over samples and pixels of dy (x) shifted x: lvg_conv2d_wgrad (tcgen05, pixels as the GEMM K axis).
+    LVG_NATIVE_WGRAD = 1: always the native kernel (what the GPU tests set); 0: always ATen / cuDNN; unset ("auto"):
+    native where it measured faster than cuDNN on B200 -- few input channels per group (<= 64: 3.4x on the 27-channel
+    first layer) -- and ATen for the wide layers, where the round-1 kernel reaches 300-440 TFLOP/s against cuDNN's
+    360-740 (profiles/r01_microbench.txt)."""
 
     @staticmethod
     def forward(ctx, dy, x, w_shape, padding, groups):
         ctx.save_for_backward(dy, x)
         ctx.cfg = (w_shape, padding, groups)
+        mode = os.environ.get('LVG_NATIVE_WGRAD', 'auto')
+        if _native is not None and hasattr(_native, 'wgrad') and (mode == '1' or (mode != '0' and w_shape[1] <= 64)):
+            return _native.wgrad(x, dy, tuple(w_shape), padding, groups)
         w_stub = torch.empty(w_shape, dtype=x.dtype, device=x.device)
         return torch.ops.aten.convolution_backward(dy, x, w_stub, None, [1, 1], list(padding), [1, 1], False, [0, 0], groups,
                                                    [False, True, False])[1]

@@ -26,8 +26,9 @@ CASES = [
 
 
 @pytest.fixture(autouse=True)
-def native_on():
+def native_on(monkeypatch):
     conv2d_gradfix.install_native(True)
+    monkeypatch.setenv('LVG_NATIVE_WGRAD', '1')      # every weight gradient below runs on lvg_conv2d_wgrad
     yield
     conv2d_gradfix.install_native(True)
 
@@ -48,6 +49,19 @@ def test_conv2d_forward_and_input_gradient(n, g, cin, cout, h, w, k, pad):
     rdx, rdw = torch.autograd.grad(F.conv2d(xr, wr, padding=pad, groups=g), [xr, wr], dy.float())
     assert_close(dx, rdx, TOL, 'dgrad')
     assert_close(dw, rdw, 5e-3, 'wgrad')
+
+
+def test_wgrad_modes_agree(monkeypatch):
+    # the native weight gradient against the ATen one on a ragged shape: odd width (no pixel pairs), partial last stage,
+    # Cin not a multiple of 16, two n-tiles (Cin > 160), batch accumulation
+    gen = torch.Generator().manual_seed(5)
+    for (n, g, cin, cout, h, w, k, pad) in ((2, 1, 170, 130, 11, 71, 3, 1), (1, 2, 20, 24, 9, 131, 3, 2), (2, 3, 40, 8, 5, 6, 1, 0)):
+        x = torch.randn(n, g * cin, h, w, generator=gen).half().to(DEV)
+        dy = torch.randn(n, g * cout, h + 2 * pad - k + 1, w + 2 * pad - k + 1, generator=gen).half().to(DEV)
+        dw = conv2d_gradfix._native.wgrad(x, dy, (g * cout, cin, k, k), (pad, pad), g)
+        wr = torch.zeros(g * cout, cin, k, k, device=DEV, requires_grad=True)
+        ref, = torch.autograd.grad(F.conv2d(x.float(), wr, padding=pad, groups=g), [wr], dy.float())
+        assert_close(dw, ref, 5e-3, f'wgrad {(n, g, cin, cout, h, w, k, pad)}')
 
 
 def test_conv2d_against_cpu_oracle():

@@ -122,7 +122,17 @@ def main():
         if not (cin == 208 and nt > 4):     # cuDNN takes ~0.2 s on this shape: time it once at small NT only
             ms = timeit(lambda: torch.nn.functional.conv2d(x, wt, padding=2, groups=nt), iters=3, warmup=1)
             print(f'conv2d cudnn   grouped fp16 {name} NT={nt}: {ms:8.3f} ms {flops / ms / 1e9:8.1f} TFLOP/s', flush=True)
-        del x, wt
+        # weight gradient: tcgen05 kernel vs aten::convolution_backward (cuDNN)
+        plug = conv2d_gradfix._native
+        y = conv2d_gradfix.conv2d(x, wt, padding=2, groups=nt)
+        dy = torch.randn_like(y)
+        ms = timeit(lambda: plug.wgrad(x, dy, tuple(wt.shape), (2, 2), nt))
+        print(f'conv2d wgrad tcgen05 fp16 {name} NT={nt}: {ms:8.3f} ms {flops / ms / 1e9:8.1f} TFLOP/s', flush=True)
+        if not (cin == 208 and nt > 4):
+            ms = timeit(lambda: torch.ops.aten.convolution_backward(dy, x, wt, None, [1, 1], [2, 2], [1, 1], False, [0, 0], nt,
+                                                                    [False, True, False]), iters=3, warmup=1)
+            print(f'conv2d wgrad cudnn   fp16 {name} NT={nt}: {ms:8.3f} ms {flops / ms / 1e9:8.1f} TFLOP/s', flush=True)
+        del x, wt, y, dy
     os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
     json.dump(rows, open(os.path.join(ROOT, 'gpurun_out', 'microbench.json'), 'w'), indent=1)
 

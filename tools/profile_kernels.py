@@ -51,3 +51,6 @@ conv2d_gradfix.install_native(True)
 xc = torch.randn(1, 16 * 539, 92, 148, device=DEV, dtype=torch.float16)
 wc = torch.randn(16 * 512, 539, 3, 3, device=DEV, dtype=torch.float16) / 70
 run('conv_l8', lambda: conv2d_gradfix.conv2d(xc, wc, padding=2, groups=16))
+yc = conv2d_gradfix.conv2d(xc, wc, padding=2, groups=16)
+dyc = torch.randn_like(yc)
+run('conv_wgrad_l8', lambda: conv2d_gradfix._native.wgrad(xc, dyc, tuple(wc.shape), (2, 2), 16))
