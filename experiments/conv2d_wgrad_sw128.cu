@@ -1,0 +1,351 @@
+// Weight gradient of the grouped 2-D convolution as an implicit GEMM on tcgen05 tensor cores.
+//
+//   dW[g][co][ci][ky][kx] = sum_n sum_{oy,ox} dy[n][g][co][oy][ox] * x[n][g][ci][oy + ky - pad][ox + kx - pad]
+//
+// (the third leg of conv2d_gradfix: torch_utils/ops/conv2d_gradfix.py:119-141 hands it to
+// aten::convolution_backward / cuDNN). For the per-sample-weight ("modulated") convolutions of the
+// super-res generator every sample is its own group, so dW is as large as all the weights of the
+// batch (318 MB for 64 groups of 512 x 539 x 3 x 3) and cuDNN's grouped wgrad is far off the tensor-core rate.
+//
+// GEMM view per (group g, 128-channel tile of co, NT-channel tile of ci, filter row ky):
+//   D_kx[co][ci] += A[co][pix] * B_kx[ci][pix]     M = 128 (co), N = NT (ci), K = output pixels
+// for the KW taps kx of that filter row at once: KW accumulators of NT fp32 columns each live in TMEM
+// (3 x 144 = 432 of the 512 columns for Cin = 539). The K dimension runs over the output pixels in
+// stages of 64 pixels of one output row (4 UMMA k-steps of 16).
+//
+// Operand staging, both K-major with the 128-byte swizzle: one stage of 64 pixels is exactly one 128-byte
+// swizzle row per channel, 8 channels form a 1024-byte atom whose 16-byte chunks are XOR-ed with the row index
+// (canonical SWIZZLE_128B layout of the UMMA shared-memory descriptor; a k-step of 16 pixels advances the
+// descriptor's start address by 32 bytes):
+//   A  dy rows:   [128 co][128 B]
+//   B  x rows, one copy per tap kx, shifted by kx pixels (a one-pixel shift cannot be expressed in a
+//      descriptor, so the shift happens in registers between the load and the store):  [kx][NT ci][128 B]
+// A warp moves whole rows: its 32 lanes load the 32 pixel pairs of one row with one coalesced 128-byte
+// request and store them with one conflict-free 128-byte shared-memory write (the swizzle only permutes
+// the 16-byte chunks inside the row). An earlier version with the no-swizzle layout had to give every lane
+// its own 16-byte piece of a row (4-byte loads 8 rows x 4 chunks per request): 5x the sector requests,
+// L1-request-bound at ~25 % tensor-pipe utilisation.
+// Loads run one stage ahead of their use in a second register set; a dedicated warp issues 4 x KW MMAs per
+// stage as soon as the stage's buffer is complete (full/empty mbarrier pairs, no block-wide barrier in the
+// loop). One CTA per SM (142-156 KB of shared memory, 512 TMEM columns). Epilogue: TMEM -> registers ->
+// fp16 -> a [co][ci][kx] tile in shared memory -> global, so that a warp's stores cover runs of KW values
+// per (co, ci) instead of 2-byte stores 18 bytes apart per lane.
+
+#include "common.cuh"
+#include "tcgen05.cuh"
+
+namespace lvg {
+namespace {
+
+using namespace tc;
+
+constexpr int kProducers = 256;               // warps 0-7 stage the operands (and run the epilogue)
+constexpr int kThreads = kProducers + 32;    // warp 8 issues the MMAs
+constexpr int kBM = 128;
+constexpr int kStagePx = 64;                 // pixels per stage = 4 k-steps
+constexpr int kAStage = 4 * kBM * 16 * 2;    // 16 KB
+constexpr int kRowsA = kBM / 8;               // A rows per producer warp
+constexpr int kRowsB = 20;                    // B rows per producer warp: NT <= 160
+
+struct WgradParams {
+    const __half* x;
+    const __half* dy;
+    __half* dw;
+    int n, groups, cin, cout;
+    int h, w, ho, wo;
+    int kh, kw, pad_h, pad_w;
+    int nt;                 // ci per n-tile (multiple of 16, <= 160 for KW = 3, <= 256 for KW = 1)
+    int x_pair_ok, dy_pair_ok;
+};
+
+// 8 consecutive fp16 starting `v` pixels into the fetched pairs (v = 0..3)
+// shared-memory matrix descriptor, K-major, SWIZZLE_128B: 8-row atoms of 1024 bytes (stride byte offset), leading offset unused
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3fff);
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+// pixel pair of the copy shifted by V pixels: elements (2 l + V, 2 l + V + 1) of the window whose pairs l, l + 1, ... are in q
+template <int V, int NPB>
+__device__ __forceinline__ uint32_t shifted(const uint32_t (&q)[NPB])
+{
+    if constexpr (V % 2 == 0) return q[V / 2];
+    else return __byte_perm(q[V / 2], q[V / 2 + 1], 0x5432);
+}
+
+// pixel pair (e, e + 1) of a row; elements outside [lo, hi) read as zero
+__device__ __forceinline__ uint32_t load_pair(const __half* row, int e, int lo, int hi, bool paired)
+{
+    const bool v0 = e >= lo && e < hi, v1 = e + 1 >= lo && e + 1 < hi;
+    uint32_t v = 0;
+    if (paired && v0 && v1) return __ldg(reinterpret_cast<const unsigned int*>(row + e));
+    if (v0) v = __ldg(reinterpret_cast<const unsigned short*>(row + e));
+    if (v1) v |= (uint32_t)__ldg(reinterpret_cast<const unsigned short*>(row + e + 1)) << 16;
+    return v;
+}
+
+template <int KH, int KW, int SH>
+__global__ void __launch_bounds__(kThreads, 1) conv_wgrad_tc_kernel(WgradParams p)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ uint64_t full_bar[2];      // stage buffer written (all producer threads arrive)
+    __shared__ uint64_t empty_bar[2];     // the MMAs reading the buffer have completed (tcgen05.commit arrives)
+    __shared__ uint32_t tmem_base_slot;
+    // swizzle atoms must sit on 1024-byte boundaries of the shared-memory address space
+    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+
+    const int NT = p.nt;
+    const int b_copy = NT * 128;                 // bytes of one shifted copy: NT rows x 64 pixels
+    const int stage_bytes = kAStage + KW * b_copy;
+    const int nti = blockIdx.x / KH, ky = blockIdx.x - nti * KH;
+    const int mti = blockIdx.y, g = blockIdx.z;
+    const int ci0 = nti * NT, co0 = mti * kBM;
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+
+    if (threadIdx.x == 0) {
+        mbar_init(&full_bar[0], kProducers);
+        mbar_init(&full_bar[1], kProducers);
+        mbar_init(&empty_bar[0], 1);
+        mbar_init(&empty_bar[1], 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) tmem_alloc(&tmem_base_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_d = tmem_base_slot;
+    // instruction descriptor: D = f32, A = B = f16, both K-major, N >> 3, M >> 4
+    const uint32_t idesc = (1u << 4) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+
+    const int xstages = (p.wo + kStagePx - 1) / kStagePx;
+    const int n_stages = p.n * p.ho * xstages;
+    constexpr int sh = SH;               // = pad_w & 1: the fetched window starts at an even pixel, ox0 - pad_w - sh
+    constexpr int NPB = (SH + KW) / 2 + 1;         // pixel pairs a lane needs per x row: own pair + neighbours for shifts up to SH + KW - 1
+    const bool x_paired = p.x_pair_ok != 0, dy_paired = p.dy_pair_ok != 0;
+
+    // Producer warp w moves rows w, w + 8, ...; lane l moves pixel pair l of the stage's 64 pixels.
+    // Row r of an operand tile: byte (r / 8) * 1024 + (r % 8) * 128 + ((chunk ^ (r % 8)) * 16) + 4 * (l % 4), chunk = l / 4.
+    const int nb_rows = NT / 8;                                       // B rows per warp (NT % 8 == 0)
+    const int a_valid = min(kRowsA, max(0, (p.cout - co0 - warp + 7) / 8));    // rows of this warp with a real co
+    const int b_valid = min(nb_rows, max(0, (p.cin - ci0 - warp + 7) / 8));    // ... with a real ci
+    const int row_lo = (warp % 8) * 128 + (((lane / 4) ^ (warp % 8)) * 16) + (lane % 4) * 4;     // + 1024 per row step (r += 8)
+    const int a_rstride = 8 * p.ho * p.wo, b_rstride = 8 * p.h * p.w;
+
+    // Two register sets: the loads of stage s + 1 are in flight while stage s is written to shared memory.
+    struct Regs { uint32_t pa[kRowsA], pb[kRowsB][NPB]; };
+    Regs R0, R1;
+    int pf_inst = 0, pf_oy = 0, pf_xs = 0;       // the next stage to fetch
+
+    auto prefetch = [&](Regs& R) {
+        const int ox0 = pf_xs * kStagePx;
+        const int left = p.wo - ox0;
+        // A: dy, pixel pair `lane` of the rows; pixels [0, left) exist
+        const __half* rowa = p.dy + ((int64_t)(pf_inst * p.groups + g) * p.cout + co0 + warp) * p.ho * p.wo + (int64_t)pf_oy * p.wo + ox0;
+        const bool a_in = 2 * lane < left;
+#pragma unroll
+        for (int j = 0; j < kRowsA; j++) {
+            uint32_t v = 0;
+            if (j < a_valid) {
+                const __half* row = rowa + j * a_rstride;
+                if (dy_paired) { if (a_in) v = __ldg(reinterpret_cast<const unsigned int*>(row) + lane); }
+                else v = load_pair(row, 2 * lane, 0, left, false);
+            }
+            R.pa[j] = v;
+        }
+        // B: x, window element e sits at image column ix0 + e; element pairs lane, lane + 1, (lane + 2)
+        const int iy = pf_oy + ky - p.pad_h;
+        const bool rowok = iy >= 0 && iy < p.h;
+        const int ix0 = ox0 - p.pad_w - sh;
+        const __half* rowb = p.x + ((int64_t)(pf_inst * p.groups + g) * p.cin + ci0 + warp) * p.h * p.w + (int64_t)iy * p.w + ix0;
+        const int lo = rowok ? -ix0 : 1 << 20;                        // valid elements: [lo, hi)
+        int hi = p.w - ix0;
+        if (left < kStagePx) {                                        // ragged last stage of a row: zero what meets no valid
+            const int need = (sh + KW - 1 + left + 1) & ~1;           // output pixel (keeps stray NaNs out of the sums)
+            if (need < hi) hi = need;
+        }
+        bool in[NPB];
+#pragma unroll
+        for (int q = 0; q < NPB; q++) in[q] = 2 * (lane + q) >= lo && 2 * (lane + q) < hi;
+#pragma unroll
+        for (int j = 0; j < kRowsB; j++) {
+            if (j < nb_rows) {
+                const __half* row = rowb + j * b_rstride;
+#pragma unroll
+                for (int q = 0; q < NPB; q++) {
+                    uint32_t v = 0;
+                    if (j < b_valid) {
+                        if (x_paired) { if (in[q]) v = __ldg(reinterpret_cast<const unsigned int*>(row) + lane + q); }
+                        else v = load_pair(row, 2 * (lane + q), lo, hi, false);
+                    }
+                    R.pb[j][q] = v;
+                }
+            }
+        }
+        // advance to the following stage
+        if (++pf_xs == xstages) { pf_xs = 0; if (++pf_oy == p.ho) { pf_oy = 0; ++pf_inst; } }
+    };
+    auto commit = [&](unsigned char* buf, const Regs& R) {
+        unsigned char* da = buf + row_lo;
+#pragma unroll
+        for (int j = 0; j < kRowsA; j++) *reinterpret_cast<uint32_t*>(da + j * 1024) = R.pa[j];
+        unsigned char* db = buf + kAStage + row_lo;
+#pragma unroll
+        for (int j = 0; j < kRowsB; j++) {
+            if (j < nb_rows) {
+                *reinterpret_cast<uint32_t*>(db + j * 1024) = shifted<SH, NPB>(R.pb[j]);
+                if constexpr (KW > 1) *reinterpret_cast<uint32_t*>(db + b_copy + j * 1024) = shifted<SH + 1, NPB>(R.pb[j]);
+                if constexpr (KW > 2) *reinterpret_cast<uint32_t*>(db + 2 * b_copy + j * 1024) = shifted<SH + 2, NPB>(R.pb[j]);
+            }
+        }
+    };
+
+    // Warp-specialised pipeline over the stages, two buffers, no block-wide barrier inside the loop:
+    //   producers (warps 0-7): wait empty[b] (MMAs of stage s - 2 done) -> registers of stage s to buffer b ->
+    //                          fence -> arrive full[b] -> start the loads of stage s + 2
+    //   MMA warp (warp 8)    : wait full[b] -> 4 x KW MMAs of stage s -> tcgen05.commit -> empty[b]
+    if (warp < kProducers / 32) {
+        auto stage = [&](int s, Regs& R) {
+            const int b = s & 1;
+            unsigned char* buf = smem + (size_t)b * stage_bytes;
+            if (s >= 2) mbar_wait(&empty_bar[b], (uint32_t)(((s >> 1) - 1) & 1));
+            commit(buf, R);
+            fence_proxy_async();
+            mbar_arrive(&full_bar[b]);
+            if (s + 2 < n_stages) prefetch(R);
+        };
+        prefetch(R0);
+        if (n_stages > 1) prefetch(R1);
+        for (int s = 0; s < n_stages; s += 2) {
+            stage(s, R0);
+            if (s + 1 < n_stages) stage(s + 1, R1);
+        }
+    } else if (lane == 0) {
+        // descriptors advance by plain adds on the 16-byte-unit start-address field (shared memory < 256 KB)
+        const uint64_t adesc0 = make_desc_sw128(smem_u32(smem));
+        const uint64_t bdesc0 = make_desc_sw128(smem_u32(smem + kAStage));
+        const uint32_t stage16 = (uint32_t)stage_bytes >> 4, bc16 = (uint32_t)b_copy >> 4;
+        int xs = 0;
+        for (int s = 0; s < n_stages; s++) {
+            const int b = s & 1;
+            const int left = p.wo - xs * kStagePx;
+            const int ksteps = ((left < kStagePx ? left : kStagePx) + 15) / 16;
+            if (++xs == xstages) xs = 0;
+            mbar_wait(&full_bar[b], (uint32_t)((s >> 1) & 1));
+            tc_fence_after();
+            const uint64_t ad = adesc0 + (uint64_t)(b * stage16), bd = bdesc0 + (uint64_t)(b * stage16);
+            for (int k = 0; k < ksteps; k++) {           // 16 pixels = 32 bytes along the swizzle row
+#pragma unroll
+                for (int kx = 0; kx < KW; kx++)
+                    umma_f16(tmem_d + (uint32_t)(kx * NT), ad + (uint64_t)(k * 2), bd + (uint64_t)(kx * bc16 + k * 2), idesc,
+                             (s > 0 || k > 0) ? 1u : 0u);
+            }
+            umma_commit(&empty_bar[b]);
+        }
+    }
+    if (warp == kProducers / 32) __syncwarp();        // lanes 1-31 of the MMA warp sleep here instead of polling a barrier
+
+    // ---- epilogue: all MMAs done when the last commit has arrived
+    {
+        const int last = n_stages - 1;
+        mbar_wait(&empty_bar[last & 1], (uint32_t)((last >> 1) & 1));
+        if (n_stages >= 2) mbar_wait(&empty_bar[(last - 1) & 1], (uint32_t)(((last - 1) >> 1) & 1));
+    }
+    tc_fence_after();
+    __syncthreads();                                   // stage buffers are free: reuse them as the output tile
+    __half* tile = reinterpret_cast<__half*>(smem);
+    const int row_pitch = NT * KW + 2;                 // halves; (pitch / 2) odd -> the per-row 2-byte stores spread over the banks
+    {
+        const int q = warp % 4;
+        const int r = q * 32 + lane;                   // co row = TMEM lane
+        const int ncols = warp < kProducers / 32 ? KW * NT : 0;
+        for (int n0 = (warp / 4) * 32; n0 < ncols; n0 += 64) {
+            uint32_t acc[32];
+            tmem_ld32(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)n0, acc);
+#pragma unroll
+            for (int j = 0; j < 32; j++) {
+                const int col = n0 + j;
+                if (col < ncols) {
+                    const int kx = col / NT, ci = col - kx * NT;
+                    tile[r * row_pitch + ci * KW + kx] = __float2half_rn(__uint_as_float(acc[j]));
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    {
+        // global: dw[((g * cout + co) * cin + ci) * KH * KW + ky * KW + kx]; lanes run over j = ci * KW + kx
+        const int ci_n = min(NT, p.cin - ci0);
+        const int per_row = ci_n * KW;
+        for (int r = warp; r < kBM; r += kThreads / 32) {
+            const int co = co0 + r;
+            if (co >= p.cout) break;
+            __half* dst = p.dw + (((int64_t)g * p.cout + co) * p.cin + ci0) * (KH * KW) + ky * KW;
+            const __half* src = tile + r * row_pitch;
+            for (int j = lane; j < per_row; j += 32) {
+                const int ci = j / KW, kx = j - ci * KW;
+                dst[ci * (KH * KW) + kx] = src[j];
+            }
+        }
+    }
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_d, 512);
+}
+
+bool wgrad_supported(int dtype, int kh, int kw, int stride)
+{
+    return dtype == LVG_F16 && stride == 1 && ((kh == 3 && kw == 3) || (kh == 1 && kw == 1));
+}
+
+}  // namespace
+}  // namespace lvg
+
+using namespace lvg;
+
+extern "C" int lvg_conv2d_wgrad(const void* x, const void* dy, void* dw, int dtype, int n, int groups, int cin, int cout,
+                                int h, int wd, int kh, int kw, int stride, int pad_h, int pad_w, void* stream)
+{
+    LVG_REQUIRE(x && dy && dw, "conv2d_wgrad: x, dy, dw must not be NULL");
+    if (!wgrad_supported(dtype, kh, kw, stride) || n < 1 || pad_h < 0 || pad_w < 0) {
+        set_error("conv2d_wgrad: outside the tensor-core kernel's envelope (fp16, stride 1, 3x3 or 1x1)");
+        return LVG_UNSUPPORTED;
+    }
+    WgradParams p;
+    p.x = (const __half*)x; p.dy = (const __half*)dy; p.dw = (__half*)dw;
+    p.n = n; p.groups = groups; p.cin = cin; p.cout = cout; p.h = h; p.w = wd;
+    p.kh = kh; p.kw = kw; p.pad_h = pad_h; p.pad_w = pad_w;
+    p.ho = h + 2 * pad_h - kh + 1;
+    p.wo = wd + 2 * pad_w - kw + 1;
+    LVG_REQUIRE(p.ho >= 1 && p.wo >= 1, "conv2d_wgrad: empty output");
+    if ((int64_t)cin * h * wd >= (1ll << 31) || (int64_t)cout * p.ho * p.wo >= (1ll << 31)) {
+        set_error("conv2d_wgrad: a group's activations exceed 32-bit offsets");
+        return LVG_UNSUPPORTED;
+    }
+    const int nt_max = kw == 3 ? 160 : 256;
+    const int ntiles = (cin + nt_max - 1) / nt_max;
+    p.nt = (((cin + ntiles - 1) / ntiles) + 15) / 16 * 16;
+    const int mt = (cout + kBM - 1) / kBM;
+    p.x_pair_ok = ((reinterpret_cast<uintptr_t>(x) & 3) == 0 && (wd & 1) == 0) ? 1 : 0;
+    p.dy_pair_ok = ((reinterpret_cast<uintptr_t>(dy) & 3) == 0 && (p.wo & 1) == 0) ? 1 : 0;
+    LVG_REQUIRE(groups <= 65535 && mt <= 65535, "conv2d_wgrad: too many groups / channel tiles for one launch");
+    const size_t stage = (size_t)kAStage + (size_t)kw * p.nt * 128;
+    size_t smem = 2 * stage;
+    const size_t tile_bytes = (size_t)kBM * (p.nt * kw + 2) * 2;
+    if (tile_bytes > smem) smem = tile_bytes;
+    smem += 1024;                                    // slack for the 1024-byte alignment of the swizzle atoms
+    if (smem < 120 * 1024) smem = 120 * 1024;        // one CTA per SM: each allocates all 512 TMEM columns
+    LVG_REQUIRE(smem <= 227 * 1024, "conv2d_wgrad: tile does not fit shared memory");
+    dim3 grid((unsigned)(ntiles * kh), (unsigned)mt, (unsigned)groups);
+    cudaStream_t s = (cudaStream_t)stream;
+    void (*k)(WgradParams) = kh == 3 ? ((pad_w & 1) ? conv_wgrad_tc_kernel<3, 3, 1> : conv_wgrad_tc_kernel<3, 3, 0>)
+                                     : ((pad_w & 1) ? conv_wgrad_tc_kernel<1, 1, 1> : conv_wgrad_tc_kernel<1, 1, 0>);
+    LVG_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<grid, kThreads, smem, s>>>(p);
+    LVG_LAUNCH_CHECK();
+    return LVG_OK;
+}
