@@ -145,10 +145,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_tc_kernel(WgradParams 
         for (int s = 0; s < kMaxA; s++) {
             const __half* row = rowa + s * a_rstride;
             const int hi = s < a_rows ? hi_a : 0;
-            if (dy_paired && hi_a >= 8 && s < a_rows) {      // interior chunk (warp-uniform up to the row count)
-#pragma unroll
-                for (int q = 0; q < 4; q++) pa[s][q] = __ldg(reinterpret_cast<const unsigned int*>(row) + q);
-            } else if (dy_paired) {  // even row length, aligned base: a pair is never half valid
+            if (dy_paired) {         // even row length, aligned base: a pair is never half valid
 #pragma unroll
                 for (int q = 0; q < 4; q++) {
                     uint32_t v = 0;
@@ -176,10 +173,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_tc_kernel(WgradParams 
             if (s < b_items) {
                 const __half* row = rowb + s * b_rstride;
                 const int lo = s < b_rows ? lo_b : 1 << 20;
-                if (x_paired && lo <= 0 && hi_b >= 2 * kNP) {      // interior window
-#pragma unroll
-                    for (int q = 0; q < kNP; q++) pb[s][q] = __ldg(reinterpret_cast<const unsigned int*>(row) + q);
-                } else if (x_paired) {      // lo and the row end are even
+                if (x_paired) {      // lo and the row end are even
 #pragma unroll
                     for (int q = 0; q < kNP; q++) {
                         uint32_t v = 0;
