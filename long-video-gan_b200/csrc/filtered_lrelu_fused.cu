@@ -86,13 +86,14 @@ __global__ void __launch_bounds__(kThreads, (TOH <= 24 ? 3 : 2)) filtered_lrelu_
     float* s_fd = s_fu + FU;
     uint8_t* s_code = reinterpret_cast<uint8_t*>(s_fd + FD);
 
-    const int tiles = p.tiles_x * p.tiles_y;
-    const int64_t plane = blockIdx.x / tiles;
-    const int tile = (int)(blockIdx.x - plane * tiles);
-    const int ty = tile / p.tiles_x, tx = tile - ty * p.tiles_x;
+    // (32-bit unsigned index arithmetic: the host bounds the grid by 2^31 - 1 CTAs)
+    const unsigned tiles = (unsigned)(p.tiles_x * p.tiles_y);
+    const unsigned plane = blockIdx.x / tiles;
+    const unsigned tile = blockIdx.x - plane * tiles;
+    const int ty = (int)(tile / (unsigned)p.tiles_x), tx = (int)tile - ty * p.tiles_x;
     const int ox0 = tx * TOW, oy0 = ty * TOH;
-    const int cc = (int)(plane % p.c);
-    const int nn = (int)(plane / p.c);
+    const int nn = (int)(plane / (unsigned)p.c);
+    const int cc = (int)(plane - (unsigned)nn * (unsigned)p.c);
 
     // The factor up^2 * gain that precedes the leaky ReLU is positive, so it is folded into the up-sampling
     // taps (its square root into each of the two passes) instead of costing a multiply per up-sampled sample.
@@ -124,24 +125,26 @@ __global__ void __launch_bounds__(kThreads, (TOH <= 24 ? 3 : 2)) filtered_lrelu_
         constexpr int kRowIters = (G::TIH + kWarps - 1) / kWarps;
         constexpr int kColIters = (G::TIW + 31) / 32;
         const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+        // offsets inside one (n, c) plane fit 32 bits (checked on the host): one IMAD per row, one add per element
+        const int xs2 = (int)p.xs[2], xs3 = (int)p.xs[3];
         bool colok[kColIters];
-        int64_t coloff[kColIters];
+        int coloff[kColIters];
 #pragma unroll
         for (int cj = 0; cj < kColIters; cj++) {
             const int ix = lane + 32 * cj, gx = m0x + ix;
             colok[cj] = ix < tiw_e && gx >= 0 && gx < p.iw;
-            coloff[cj] = (int64_t)gx * p.xs[3];
+            coloff[cj] = gx * xs3;
         }
         float v[kRowIters][kColIters];
 #pragma unroll
         for (int ri = 0; ri < kRowIters; ri++) {
             const int iy = warp + kWarps * ri, gy = m0y + iy;
             const bool rowok = iy < tih_e && gy >= 0 && gy < p.ih;
-            const T* xrow = xp + (int64_t)gy * p.xs[2];
+            const int rowoff = gy * xs2;
 #pragma unroll
             for (int cj = 0; cj < kColIters; cj++) {
                 v[ri][cj] = 0.f;
-                if (rowok && colok[cj]) v[ri][cj] = to_acc(xrow[coloff[cj]]) + bias;
+                if (rowok && colok[cj]) v[ri][cj] = to_acc(xp[rowoff + coloff[cj]]) + bias;
             }
         }
 #pragma unroll
@@ -393,6 +396,8 @@ extern "C" int lvg_filtered_lrelu(const void* x, const float* fu, const float* f
     }
     LVG_REQUIRE(x_shape[0] == y_shape[0] && x_shape[1] == y_shape[1], "filtered_lrelu: x and y disagree on batch/channels");
     LVG_REQUIRE(y_shape[2] * (y_stride[2] < 0 ? -y_stride[2] : y_stride[2]) < (1ll << 31), "filtered_lrelu: output plane too large");
+    LVG_REQUIRE(x_stride[2] >= 0 && x_stride[3] >= 0 &&
+                (x_shape[2] + 64) * x_stride[2] + (x_shape[3] + 64) * x_stride[3] < (1ll << 31), "filtered_lrelu: input plane too large");
     LVG_REQUIRE(!(write_signs && si), "filtered_lrelu: cannot read and write signs in one call");
     LVG_REQUIRE(!write_signs || so, "filtered_lrelu: write_signs needs an output sign buffer");
     LVG_REQUIRE(!(write_signs || si) || (s_h >= 1 && s_wbytes >= 1), "filtered_lrelu: bad sign tensor shape");

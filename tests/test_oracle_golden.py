@@ -70,3 +70,16 @@ def test_conv_and_fma():
     assert rel_err(orc.conv2d(g['plain_3x3/x'], g['plain_3x3/w'], padding=1), g['plain_3x3/y']) < 5e-6
     assert rel_err(orc.conv2d(g['fromrgb_1x1/x'], g['fromrgb_1x1/w']), g['fromrgb_1x1/y']) < 5e-6
     assert rel_err(orc.fma(g['fma/a'], g['fma/b'], g['fma/c']), g['fma/o']) < 1e-6
+
+
+def test_conv2d_wgrad_restatement_matches_torch_autograd():
+    # the float64 restatement used to check lvg_conv2d_wgrad against the weight gradient torch derives for F.conv2d
+    import torch
+    gen = torch.Generator().manual_seed(1)
+    for (n, g, cin, cout, h, w, k, pad) in ((2, 2, 3, 4, 5, 7, 3, 1), (1, 1, 5, 2, 6, 4, 3, 2), (3, 2, 4, 4, 5, 5, 1, 0)):
+        x = torch.randn(n, g * cin, h, w, generator=gen)
+        dy = torch.randn(n, g * cout, h + 2 * pad - k + 1, w + 2 * pad - k + 1, generator=gen)
+        wt = torch.zeros(g * cout, cin, k, k, requires_grad=True)
+        ref, = torch.autograd.grad(torch.nn.functional.conv2d(x, wt, padding=pad, groups=g), [wt], dy)
+        got = orc.conv2d_wgrad(x.numpy(), dy.numpy(), tuple(wt.shape), padding=pad, groups=g)
+        assert rel_err(got, ref.numpy()) < 1e-5
