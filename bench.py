@@ -118,7 +118,11 @@ class Replay:
                 y = self._fwd(it, it['x'])
                 it['dy'] = self._buf('dy', list(y.shape), y.dtype)
                 it['bytes_fwd'] = (it['x'].numel() + y.numel()) * y.element_size()
-                it['bytes_bwd'] = it['bytes_fwd'] + (y.numel() * y.element_size() if it['c']['op'] == 'bias_act' else 0)
+                # bias_act: relu / lrelu keep 2-bit codes for the backward pass (x + y + n/4 forward with grad, dy + dx + n/4
+                # backward); other activations re-read y in the backward pass (dy + y + dx)
+                coded = it['c']['op'] == 'bias_act' and it['c']['act'] in ('relu', 'lrelu')
+                it['bytes_fwd_grad'] = it['bytes_fwd'] + (y.numel() // 4 if coded else 0)
+                it['bytes_bwd'] = it['bytes_fwd'] + (y.numel() // 4 if coded else (y.numel() * y.element_size() if it['c']['op'] == 'bias_act' else 0))
                 del y
 
     def _buf(self, kind, shape, dt):
@@ -165,7 +169,7 @@ class Replay:
             if timer is not None and it['c']['op'] == timer.op:
                 timer.start()
                 y = self._fwd(it, x)
-                timer.stop(it['bytes_fwd'])
+                timer.stop(it['bytes_fwd_grad'])
                 if y.requires_grad:
                     timer.start()
                     run_backward(y, leaves, it['dy'])
@@ -510,7 +514,7 @@ def main():
                'config': config, 'gpu_launches': int(launches),
                'e2e': {'value': e2e_value, 'unit': 'frames/s', 'h2d_bytes_per_step': host_video.numel() * 4, 'd2h_bytes_per_step': 4,
                        'eager_value': frames_per_step * args.steps / (ms_e2e_eager / 1000.0)},
-               'roofline': {'bound': 'hbm', 'kernel': 'bias_act (vector kernel, forward + fused dx/db backward)' if dominant_op == 'bias_act' else
+               'roofline': {'bound': 'hbm', 'kernel': 'bias_act (vector kernel: forward writing 2-bit sign/clamp codes + backward from the codes with fused dx/db)' if dominant_op == 'bias_act' else
                             'filtered_lrelu (fused up-FIR / lrelu / down-FIR; FP32-issue-bound, its HBM figure is shown for reference)',
                             'achieved': achieved,
                             'peak': peak, 'peak_source': peak_src, 'unit': 'GB/s', 'frac': achieved / peak if peak else None,

@@ -84,6 +84,25 @@ int lvg_bias_act_grad_db(const void* dy_in, const void* b, const void* xref,
                          const void* yref, void* dx, float* db_f32, int dtype,
                          int64_t n, int64_t size_b, int64_t step_b, int act,
                          float alpha, float gain, float clamp, void* stream);
+/*
+ * relu / lrelu with 2-bit codes instead of a saved output. The gradient of these activations depends on the
+ * forward output only through "was it positive" and "was it saturated by the clamp"; the forward pass can
+ * emit exactly those two bits per element (bit 0 = not positive, bit 1 = clamped) and the backward pass then
+ * reads dy + codes (2 n s + n / 4 bytes) instead of dy + y (3 n s) -- same results as lvg_bias_act(grad = 1) /
+ * lvg_bias_act_grad_db with yref = y (the reference always re-reads y: bias_act.py:160-172, bias_act.cu:60-118).
+ * The codes buffer is opaque (tile-local word order of the kernels), 8-byte aligned, lvg_bias_act_codes_bytes(dtype, n)
+ * bytes long (about n / 4), and only meaningful to lvg_bias_act_bwd_codes for a dy with the memory layout of x.
+ * fwd: y and codes from x (+ b). bwd: dx from dy and codes; db_f32 != NULL also accumulates the bias gradient
+ * (zero-initialised fp32 [size_b], bias along a non-contiguous dimension). Returns -1 when the activation is not
+ * relu / lrelu, the type not fp32 / fp16, n not a multiple of the 16-byte pack or an operand unaligned.
+ */
+int lvg_bias_act_fwd_codes(const void* x, const void* b, void* y, void* codes, int dtype, int64_t n,
+                           int64_t size_b, int64_t step_b, int act, float alpha, float gain, float clamp,
+                           void* stream);
+int lvg_bias_act_bwd_codes(const void* dy, const void* codes, void* dx, float* db_f32, int dtype, int64_t n,
+                           int64_t size_b, int64_t step_b, int act, float alpha, float gain, float clamp,
+                           void* stream);
+int64_t lvg_bias_act_codes_bytes(int dtype, int64_t n);
 
 /*
  * upfirdn2d -- replaces upfirdn2d_plugin.upfirdn2d (torch_utils/ops/upfirdn2d.cpp:16-98,

@@ -27,6 +27,7 @@ struct BiasActParams {
     const void* dy;
     void* y;
     float* db;        // fused bias-gradient accumulators (grad=1 only) or NULL
+    uint8_t* codes;   // 2-bit sign / clamp codes (relu, lrelu): written by the forward pass, read INSTEAD of yref by the backward pass
     int64_t n;
     int64_t size_b;
     int64_t step_b;
@@ -161,13 +162,20 @@ __device__ __forceinline__ void fetch_bias(typename Acc<T>::type (&bias)[VecOf<T
 
 // Vector kernel: n_pack packs of VecOf<T>::N elements, all operands 16-byte aligned.
 // G is a template parameter so that grad 0 carries no reference operands at all.
-template <class T, int A, int G, bool FUSE_DB>
+// CODES: 0 = none; 1 = forward pass that also writes the 2-bit codes of its (stored) output: bit 0 "not positive",
+// bit 1 "saturated by the clamp" -- everything the gradient of relu / lrelu depends on; 2 = backward pass that reads
+// those codes instead of the saved output (1 byte per 16-byte fp32 pack, 2 per fp16 pack: the backward pass moves
+// 2 n s + n / 4 bytes instead of 3 n s). The buffer is opaque to callers: a thread keeps the codes of the kUnroll packs
+// it handles in a tile together (one 4- or 8-byte word at index tile * kThreads + thread), so both passes move them
+// with one coalesced access per tile instead of kUnroll byte accesses.
+template <class T, int A, int G, bool FUSE_DB, int CODES = 0>
 __global__ void __launch_bounds__(kThreads, (G == 2 ? 2 : 4)) bias_act_vec_kernel(BiasActParams p, int64_t n_pack, int bmode)
 {
     typedef typename Acc<T>::type S;
     constexpr int N = VecOf<T>::N;
+    static_assert(CODES == 0 || ((A == LVG_ACT_RELU || A == LVG_ACT_LRELU) && (CODES == 1 ? G == 0 : G == 1)), "codes: relu / lrelu, forward writes, first-order backward reads");
     constexpr bool kUseX = (G > 0) && (A == LVG_ACT_SWISH);       // saved input
-    constexpr bool kUseY = (G > 0) && (A != LVG_ACT_SWISH);       // saved output
+    constexpr bool kUseY = (G > 0) && (A != LVG_ACT_SWISH) && CODES != 2;       // saved output
     constexpr bool kUseDy = (G == 2);
     const S alpha = (S)p.alpha, gain = (S)p.gain, clamp = (S)p.clamp;
     const S inv_gain = gain != (S)0 ? (S)1 / gain : (S)0;
@@ -205,12 +213,36 @@ __global__ void __launch_bounds__(kThreads, (G == 2 ? 2 : 4)) bias_act_vec_kerne
     for (int64_t t = run * kRun; t < t_end; t++) {
         const int64_t base = t * tile;
         Pack<T> vx[kUnroll], vref[kUnroll], vdy[kUnroll];
+        unsigned vcode[kUnroll];
         const T* __restrict__ pref = kUseX ? pxr : pyr;
+        uint2 cword = make_uint2(0u, 0u);            // this thread's codes of the tile: byte (fp32) / half-word (fp16) u = pack u
+        if (CODES == 2) {
+            if (N == 4) cword.x = __ldg(reinterpret_cast<const unsigned*>(p.codes) + t * kThreads + threadIdx.x);
+            else cword = __ldg(reinterpret_cast<const uint2*>(p.codes) + t * kThreads + threadIdx.x);
+        }
+        // Fused db: almost every tile lies inside ONE bias row (rows are ~100 tiles long in the networks). Two divisions
+        // per tile (CTA-uniform) establish that; its packs then need no per-pack row arithmetic and no warp collectives.
+        bool tile_one_row = false;
+        int64_t tile_idx = 0;
+        if (FUSE_DB && bmode == BIAS_PER_PACK) {
+            const int64_t last = (base + tile < n_pack ? base + tile : n_pack) - 1;
+            const int64_t r0 = bias_row(base * N, p), r1 = bias_row(last * N, p);
+            tile_one_row = r0 == r1;
+            if (tile_one_row) {
+                tile_idx = r0 - fast_div(r0, p.size_b, p.magic_size) * p.size_b;
+                if (r0 != run_row) {                    // CTA-uniform, hence warp-uniform
+                    warp_flush();
+                    run_row = r0; run_idx = tile_idx;
+                }
+            }
+        }
 #pragma unroll
         for (int u = 0; u < kUnroll; u++) {
             const int64_t pk = base + (int64_t)u * kThreads + threadIdx.x;
+            vcode[u] = (N == 4) ? (cword.x >> (8 * u)) & 0xffu : ((u < 2 ? cword.x : cword.y) >> (16 * (u & 1))) & 0xffffu;
             if (pk < n_pack) {
                 vx[u] = load_pack(px + pk * N);
+
                 if ((kUseX || kUseY) && pref) vref[u] = load_pack(pref + pk * N);
                 if (kUseDy && pdy) vdy[u] = load_pack(pdy + pk * N);
             }
@@ -218,13 +250,20 @@ __global__ void __launch_bounds__(kThreads, (G == 2 ? 2 : 4)) bias_act_vec_kerne
 #pragma unroll
         for (int u = 0; u < kUnroll; u++) {
             const int64_t pk = base + (int64_t)u * kThreads + threadIdx.x;
-            int64_t db_row = -1, db_idx = 0;      // fused bias gradient of this pack: row, bias index, value
+            int db_idx = -1;                    // tiles that straddle bias rows: this pack's bias index and sum
             float db_val = 0.f;
             if (pk < n_pack) {
                 const int64_t e0 = pk * N;
                 S bias[N];
                 int64_t bidx;
-                fetch_bias<T>(bias, bidx, pb, bmode, e0, p);
+                if (FUSE_DB && tile_one_row) {          // bias index known for the whole tile
+                    bidx = tile_idx;
+                    const S bv = pb ? to_acc(pb[tile_idx]) : (S)0;
+#pragma unroll
+                    for (int k = 0; k < N; k++) bias[k] = bv;
+                } else {
+                    fetch_bias<T>(bias, bidx, pb, bmode, e0, p);
+                }
 
                 S fx[N], fref[N], fdy[N], fo[N];
                 unpack<T>(vx[u], fx);
@@ -237,10 +276,44 @@ __global__ void __launch_bounds__(kThreads, (G == 2 ? 2 : 4)) bias_act_vec_kerne
                     S yr = (kUseY && pref) ? fref[k] : (S)0;
                     S dyv = (kUseDy && pdy) ? fdy[k] : (S)1;
                     if (G == 0) v += bias[k]; else xr += bias[k];
-                    fo[k] = bias_act_elem<S, A>(v, xr, yr, dyv, G, alpha, gain, inv_gain, clamp);
+                    if (CODES == 2) {
+                        // same arithmetic as the yref form: (not positive ? v * alpha | 0 : v) * gain, zero where the forward clamped
+                        const unsigned cbits = vcode[u] >> (2 * k);
+                        S o = (cbits & 1u) ? (A == LVG_ACT_LRELU ? v * alpha : (S)0) : v;
+                        o *= gain;
+                        fo[k] = (cbits & 2u) ? (S)0 : o;
+                    } else {
+                        fo[k] = bias_act_elem<S, A>(v, xr, yr, dyv, G, alpha, gain, inv_gain, clamp);
+                    }
                 }
                 const Pack<T> out = pack<T>(fo);
                 store_pack(py + e0, out);
+                if (CODES == 1) {
+                    // codes of what was STORED (after rounding to T), evaluated exactly like the backward pass evaluates yref:
+                    // positive <=> yref * (1 / gain) > 0; saturated <=> not (-clamp < yref < clamp)
+                    S ys[N];
+                    if (sizeof(T) == sizeof(S)) {
+#pragma unroll
+                        for (int k = 0; k < N; k++) ys[k] = fo[k];
+                    } else {
+                        unpack<T>(out, ys);
+                    }
+                    unsigned code = 0;
+                    if (inv_gain > (S)0) {          // the usual case (kernel-uniform): the sign of yref decides
+#pragma unroll
+                        for (int k = 0; k < N; k++) if (!(ys[k] > (S)0)) code |= 1u << (2 * k);
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < N; k++) if (!(ys[k] * inv_gain > (S)0)) code |= 1u << (2 * k);
+                    }
+                    if (clamp >= (S)0) {
+#pragma unroll
+                        for (int k = 0; k < N; k++) if (!(fabsf((float)ys[k]) < (float)clamp)) code |= 2u << (2 * k);
+                    }
+                    if (N == 4) cword.x |= code << (8 * u);
+                    else if (u < 2) cword.x |= code << (16 * u);
+                    else cword.y |= code << (16 * (u - 2));
+                }
                 if (FUSE_DB) {
                     // accumulate what was actually stored, like dx.sum() would see it
                     S fs[N];
@@ -249,30 +322,31 @@ __global__ void __launch_bounds__(kThreads, (G == 2 ? 2 : 4)) bias_act_vec_kerne
                         S s = (S)0;
 #pragma unroll
                         for (int k = 0; k < N; k++) s += fs[k];
-                        db_row = bias_row(e0, p); db_idx = bidx; db_val = (float)s;
+                        if (tile_one_row) run_sum += (float)s;
+                        else { db_idx = (int)bidx; db_val = (float)s; }
                     } else {
 #pragma unroll
                         for (int k = 0; k < N; k++) atomicAdd(p.db + bias_index(e0 + k, p), (float)fs[k]);
                     }
                 }
             }
-            if (FUSE_DB && bmode == BIAS_PER_PACK) {
-                // lane 0 holds the smallest pack index: if it is past the end, every lane is
-                const int64_t row0 = __shfl_sync(full, db_row, 0);
-                const int64_t idx0 = __shfl_sync(full, db_idx, 0);
-                const bool uniform = __all_sync(full, db_row < 0 || db_row == row0);
-                if (uniform) {
-                    if (row0 >= 0) {
-                        if (row0 != run_row) {          // warp-uniform branch
-                            warp_flush();
-                            run_row = row0; run_idx = idx0;
-                        }
-                        run_sum += db_val;              // lanes past the end add 0
-                    }
-                } else if (db_row >= 0) {
-                    atomicAdd(p.db + db_idx, db_val);   // a row boundary runs through this warp's 32 packs
+            if (FUSE_DB && bmode == BIAS_PER_PACK && !tile_one_row) {
+                // short rows (small tensors) or a row boundary inside the tile: the warp's 32 packs usually still share
+                // one bias index -> shuffle-reduce and one atomic; otherwise one atomic per lane. No state is carried.
+                const int idx0 = __shfl_sync(full, db_idx, 0);
+                if (__all_sync(full, db_idx == idx0 || db_idx < 0)) {
+                    float sred = db_val;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) sred += __shfl_xor_sync(full, sred, o);
+                    if ((threadIdx.x & 31) == 0 && idx0 >= 0) atomicAdd(p.db + idx0, sred);
+                } else if (db_idx >= 0) {
+                    atomicAdd(p.db + db_idx, db_val);
                 }
             }
+        }
+        if (CODES == 1) {
+            if (N == 4) reinterpret_cast<unsigned*>(p.codes)[t * kThreads + threadIdx.x] = cword.x;
+            else reinterpret_cast<uint2*>(p.codes)[t * kThreads + threadIdx.x] = cword;
         }
     }
     if (FUSE_DB && bmode == BIAS_PER_PACK) { warp_flush(); run_row = -1; }
@@ -370,6 +444,36 @@ int launch_act(int act, const BiasActParams& p, cudaStream_t s)
     return LVG_ERR_ARG;
 }
 
+// relu / lrelu with 2-bit codes: forward (write = true) or first-order backward (optionally with the fused db)
+template <class T, int A>
+int launch_codes(const BiasActParams& p, bool write, bool fuse_db, cudaStream_t stream)
+{
+    constexpr int N = VecOf<T>::N;
+    const bool vec_ok = aligned16(p.x) && aligned16(p.y) && (reinterpret_cast<uintptr_t>(p.codes) & 7) == 0 && p.n % N == 0;
+    if (!vec_ok || (fuse_db && p.step_b % N != 0)) {
+        set_error("bias_act codes: needs 16-byte aligned operands and a multiple of %d elements", N);
+        return LVG_UNSUPPORTED;
+    }
+    const int64_t n_pack = p.n / N;
+    int mode = BIAS_NONE;
+    if (p.b || fuse_db) {
+        if (p.step_b % N == 0) mode = BIAS_PER_PACK;
+        else if (p.step_b == 1 && p.size_b % N == 0 && (!p.b || aligned16(p.b))) mode = BIAS_PACKED;
+        else mode = BIAS_PER_ELEM;
+    }
+    const int64_t tile = (int64_t)kThreads * kUnroll;
+    int64_t blocks = (n_pack + tile - 1) / tile;
+    int64_t cap = (int64_t)num_sms() * 4 * 8;
+    if (fuse_db) { blocks = (blocks + 7) / 8; cap = (int64_t)num_sms() * 4; }
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    void (*k)(BiasActParams, int64_t, int) = write ? bias_act_vec_kernel<T, A, 0, false, 1>
+                                           : fuse_db ? bias_act_vec_kernel<T, A, 1, true, 2> : bias_act_vec_kernel<T, A, 1, false, 2>;
+    k<<<(unsigned)blocks, kThreads, 0, stream>>>(p, n_pack, mode);
+    LVG_LAUNCH_CHECK();
+    return LVG_OK;
+}
+
 uint64_t magic_for(int64_t d, int64_t n)
 {
     if (d <= 1 || d >= (1ll << 32) || n >= (1ll << 32)) return 0;
@@ -400,7 +504,7 @@ extern "C" int lvg_bias_act(const void* x, const void* b, const void* xref, cons
     if (rc) return rc;
     LVG_REQUIRE(grad >= 0 && grad <= 2, "bias_act: grad must be 0, 1 or 2 (got %d)", grad);
     if (n == 0) return LVG_OK;
-    BiasActParams p = {x, b, xref, yref, dy, y, nullptr, n, b ? size_b : 1, b ? step_b : 1, 0, 0, grad, alpha, gain, clamp};
+    BiasActParams p = {x, b, xref, yref, dy, y, nullptr, nullptr, n, b ? size_b : 1, b ? step_b : 1, 0, 0, grad, alpha, gain, clamp};
     p.magic_step = magic_for(p.step_b, n); p.magic_size = magic_for(p.size_b, n);
     cudaStream_t s = (cudaStream_t)stream;
     if (dtype == LVG_F32) return launch_act<float, false>(act, p, s);
@@ -427,9 +531,58 @@ extern "C" int lvg_bias_act_grad_db(const void* dy_in, const void* b, const void
         return LVG_UNSUPPORTED;
     }
     // b may be NULL here (bias values are only needed by swish); the index math still applies.
-    BiasActParams p = {dy_in, b, xref, yref, nullptr, dx, db_f32, n, size_b, step_b, 0, 0, 1, alpha, gain, clamp};
+    BiasActParams p = {dy_in, b, xref, yref, nullptr, dx, db_f32, nullptr, n, size_b, step_b, 0, 0, 1, alpha, gain, clamp};
     p.magic_step = magic_for(p.step_b, n); p.magic_size = magic_for(p.size_b, n);
     cudaStream_t s = (cudaStream_t)stream;
     if (dtype == LVG_F32) return launch_act<float, true>(act, p, s);
     return launch_act<__half, true>(act, p, s);
+}
+
+extern "C" int lvg_bias_act_fwd_codes(const void* x, const void* b, void* y, void* codes, int dtype, int64_t n,
+                                      int64_t size_b, int64_t step_b, int act, float alpha, float gain, float clamp,
+                                      void* stream)
+{
+    int rc = check_common(x, y, dtype, n, b, size_b, step_b, act);
+    if (rc) return rc;
+    LVG_REQUIRE(codes != nullptr, "bias_act_fwd_codes: codes buffer must not be NULL");
+    if ((act != LVG_ACT_RELU && act != LVG_ACT_LRELU) || (dtype != LVG_F32 && dtype != LVG_F16)) {
+        set_error("bias_act_fwd_codes: relu / lrelu in fp32 / fp16 only");
+        return LVG_UNSUPPORTED;
+    }
+    if (n == 0) return LVG_OK;
+    BiasActParams p = {x, b, nullptr, nullptr, nullptr, y, nullptr, (uint8_t*)codes, n, b ? size_b : 1, b ? step_b : 1, 0, 0, 0, alpha, gain, clamp};
+    p.magic_step = magic_for(p.step_b, n); p.magic_size = magic_for(p.size_b, n);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (dtype == LVG_F32) return act == LVG_ACT_RELU ? launch_codes<float, LVG_ACT_RELU>(p, true, false, s) : launch_codes<float, LVG_ACT_LRELU>(p, true, false, s);
+    return act == LVG_ACT_RELU ? launch_codes<__half, LVG_ACT_RELU>(p, true, false, s) : launch_codes<__half, LVG_ACT_LRELU>(p, true, false, s);
+}
+
+extern "C" int lvg_bias_act_bwd_codes(const void* dy, const void* codes, void* dx, float* db_f32, int dtype, int64_t n,
+                                      int64_t size_b, int64_t step_b, int act, float alpha, float gain, float clamp,
+                                      void* stream)
+{
+    int rc = check_common(dy, dx, dtype, n, nullptr, size_b, step_b, act);
+    if (rc) return rc;
+    LVG_REQUIRE(codes != nullptr, "bias_act_bwd_codes: codes buffer must not be NULL");
+    LVG_REQUIRE(!db_f32 || (size_b >= 1 && step_b >= 1), "bias_act_bwd_codes: db needs size_b >= 1 and step_b >= 1");
+    if ((act != LVG_ACT_RELU && act != LVG_ACT_LRELU) || (dtype != LVG_F32 && dtype != LVG_F16)) {
+        set_error("bias_act_bwd_codes: relu / lrelu in fp32 / fp16 only");
+        return LVG_UNSUPPORTED;
+    }
+    if (n == 0) return LVG_OK;
+    const bool fuse = db_f32 != nullptr;
+    BiasActParams p = {dy, nullptr, nullptr, nullptr, nullptr, dx, db_f32, (uint8_t*)codes, n, fuse ? size_b : 1, fuse ? step_b : 1, 0, 0, 1, alpha, gain, clamp};
+    p.magic_step = magic_for(p.step_b, n); p.magic_size = magic_for(p.size_b, n);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (dtype == LVG_F32) return act == LVG_ACT_RELU ? launch_codes<float, LVG_ACT_RELU>(p, false, fuse, s) : launch_codes<float, LVG_ACT_LRELU>(p, false, fuse, s);
+    return act == LVG_ACT_RELU ? launch_codes<__half, LVG_ACT_RELU>(p, false, fuse, s) : launch_codes<__half, LVG_ACT_LRELU>(p, false, fuse, s);
+}
+
+extern "C" int64_t lvg_bias_act_codes_bytes(int dtype, int64_t n)
+{
+    if (dtype != LVG_F32 && dtype != LVG_F16) return -1;
+    const int pack = dtype == LVG_F16 ? 8 : 4;
+    const int64_t tile = (int64_t)kThreads * kUnroll;
+    const int64_t tiles = ((n + pack - 1) / pack + tile - 1) / tile;
+    return tiles * kThreads * (dtype == LVG_F16 ? 8 : 4);
 }

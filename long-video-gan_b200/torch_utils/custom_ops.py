@@ -45,6 +45,9 @@ _SIGNATURES = {
     'lvg_grad_postprocess': (_c_int, [_c_void_p, _c_i64, _c_float, _c_float, _c_void_p]),
     'lvg_bias_act': (_c_int, [_c_void_p] * 6 + [_c_int, _c_i64, _c_i64, _c_i64, _c_int, _c_int, _c_float, _c_float, _c_float, _c_void_p]),
     'lvg_bias_act_grad_db': (_c_int, [_c_void_p] * 6 + [_c_int, _c_i64, _c_i64, _c_i64, _c_int, _c_float, _c_float, _c_float, _c_void_p]),
+    'lvg_bias_act_fwd_codes': (_c_int, [_c_void_p] * 4 + [_c_int, _c_i64, _c_i64, _c_i64, _c_int, _c_float, _c_float, _c_float, _c_void_p]),
+    'lvg_bias_act_codes_bytes': (_c_i64, [_c_int, _c_i64]),
+    'lvg_bias_act_bwd_codes': (_c_int, [_c_void_p] * 4 + [_c_int, _c_i64, _c_i64, _c_i64, _c_int, _c_float, _c_float, _c_float, _c_void_p]),
     'lvg_upfirdn2d': (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _I64x4, _I64x4, _I64x4, _I64x4, _c_int, _c_int, _c_i64, _c_i64]
                       + [_c_int] * 7 + [_c_float, _c_void_p]),
     'lvg_upfirdn2d_sep': (_c_int, [_c_void_p] * 4 + [_c_int, _I64x4, _I64x4, _I64x4, _I64x4] + [_c_int] * 9 + [_c_float, _c_void_p]),
@@ -222,6 +225,44 @@ class BiasActPlugin:
         if rc == LVG_UNSUPPORTED:
             return None     # layout not covered by the fused kernel: caller runs bias_act(grad=1) + sum
         return dx, db.to(dy.dtype)
+
+
+    def bias_act_fwd_codes(self, x, b, dim, act, alpha, gain, clamp):
+        """relu / lrelu forward that also emits 2-bit sign / clamp codes (uint8 [numel / 4]) for the backward pass.
+        Returns (y, codes), or None when the kernel does not cover the call (other activations, odd sizes, fp64)."""
+        if not x.is_cuda or x.dtype not in (torch.float16, torch.float32) or x.numel() == 0 or not _is_dense(x):
+            return None
+        size_b, step_b = 1, 1
+        if not _absent(b):
+            if b.dtype != x.dtype or b.device != x.device or b.ndim != 1 or b.numel() != x.shape[dim] or not b.is_contiguous():
+                return None         # let the general entry point produce the reference's error message
+            size_b, step_b = b.numel(), max(x.stride(dim), 1)
+        y = torch.empty_like(x)
+        nbytes = self._lib.lvg_bias_act_codes_bytes(_dtype_code(x, 'bias_act'), x.numel())
+        if nbytes < 0:
+            return None
+        codes = torch.empty([int(nbytes)], dtype=torch.uint8, device=x.device)
+        with _DeviceGuard(x):
+            rc = _check(self._lib.lvg_bias_act_fwd_codes(_ptr(x), _ptr(b), _ptr(y), _ptr(codes), _dtype_code(x, 'bias_act'),
+                                                         x.numel(), size_b, step_b, int(act), float(alpha), float(gain),
+                                                         float(clamp), _stream(x)), 'bias_act_fwd_codes')
+        return None if rc == LVG_UNSUPPORTED else (y, codes)
+
+    def bias_act_bwd_codes(self, dy, codes, dim, act, alpha, gain, clamp, want_db):
+        """dx (and the bias gradient when want_db and the layout allows fusing it) from dy and the forward's codes.
+        dy must have the memory layout of the forward's x. Returns (dx, db or None)."""
+        code = _dtype_code(dy, 'bias_act_bwd_codes')
+        dx = torch.empty_like(dy)
+        size_b, step_b = dy.shape[dim], max(dy.stride(dim), 1)
+        pack = 8 if dy.dtype == torch.float16 else 4
+        db = torch.zeros([size_b], dtype=torch.float32, device=dy.device) if (want_db and step_b % pack == 0) else None
+        with _DeviceGuard(dy):
+            rc = _check(self._lib.lvg_bias_act_bwd_codes(_ptr(dy), _ptr(codes), _ptr(dx), _ptr(db), code, dy.numel(), size_b, step_b,
+                                                         int(act), float(alpha), float(gain), float(clamp), _stream(dy)),
+                        'bias_act_bwd_codes')
+        if rc == LVG_UNSUPPORTED:
+            raise RuntimeError('bias_act_bwd_codes: ' + self._lib.lvg_last_error().decode())
+        return dx, (db.to(dy.dtype) if db is not None else None)
 
 
 class Upfirdn2dPlugin:

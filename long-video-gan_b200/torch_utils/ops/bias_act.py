@@ -8,6 +8,8 @@ composition of standard torch ops below, as in the reference.
 """
 import math
 
+import os
+
 import torch
 
 from .. import custom_ops
@@ -112,23 +114,59 @@ def _bias_act_cuda(dim=1, act='linear', alpha=None, gain=None, clamp=None):
     return _bias_act_cuda_cache.setdefault(key, cfg)
 
 
+def _use_codes(cfg, x):
+    # relu / lrelu: the backward pass only needs "positive?" and "clamped?" per element -- 2 bits instead of re-reading y
+    return (cfg.act in ('relu', 'lrelu') and x.dtype in (torch.float16, torch.float32) and x.numel() > 0
+            and hasattr(_plugin, 'bias_act_fwd_codes') and os.environ.get('LVG_BIAS_ACT_CODES', '1') != '0')
+
+
+def _dense_as(dy, shape, stride):
+    """dy with exactly the given (dense) layout: the codes are indexed by memory offset."""
+    if tuple(dy.shape) == tuple(shape) and tuple(dy.stride()) == tuple(stride):
+        return dy
+    out = torch.empty_strided(shape, stride, dtype=dy.dtype, device=dy.device)
+    out.copy_(dy)
+    return out
+
+
 class _BiasAct(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, b, cfg):
         x = as_dense(x)
         b = b.contiguous() if b is not None else None
+        ctx.cfg = cfg
+        ctx.has_b = b is not None
+        ctx.codes_layout = None
+        if (ctx.needs_input_grad[0] or ctx.needs_input_grad[1]) and _use_codes(cfg, x):
+            res = _plugin.bias_act_fwd_codes(x, b, cfg.dim, cfg.spec.cuda_idx, cfg.alpha, cfg.gain, cfg.clamp)
+            if res is not None:
+                y, codes = res
+                ctx.codes_layout = (tuple(y.shape), tuple(y.stride()))
+                ctx.save_for_backward(codes)
+                return y
         y = x
         if not cfg.is_identity or b is not None:
             y = cfg.call_plugin(x, b, None, None, None, 0)
         keep_x = 'x' in cfg.spec.ref or cfg.spec.has_2nd_grad
-        ctx.cfg = cfg
-        ctx.has_b = b is not None
         ctx.save_for_backward(x if keep_x else None, b if keep_x else None, y if 'y' in cfg.spec.ref else None)
         return y
 
     @staticmethod
     def backward(ctx, dy):
         cfg = ctx.cfg
+        if ctx.codes_layout is not None:
+            codes, = ctx.saved_tensors
+            dy = _dense_as(dy, *ctx.codes_layout)
+            need_x, need_b = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+            dx = db = None
+            if need_x or need_b:
+                if torch.is_grad_enabled():          # create_graph: stay differentiable in dy
+                    dx = _BiasActGradCodes.apply(dy, codes, cfg)
+                else:
+                    dx, db = _plugin.bias_act_bwd_codes(dy, codes, cfg.dim, cfg.spec.cuda_idx, cfg.alpha, cfg.gain, cfg.clamp, need_b)
+            if need_b and db is None:
+                db = cfg.reduce_bias_grad(dx)
+            return dx, db, None
         x, b, y = ctx.saved_tensors
         like = y if y is not None else x
         if like is not None:
@@ -153,6 +191,25 @@ class _BiasAct(torch.autograd.Function):
         if need_b and db is None:
             db = cfg.reduce_bias_grad(dx)
         return dx, db, None
+
+
+class _BiasActGradCodes(torch.autograd.Function):
+    """dx = dy * gain * act'(.) from the 2-bit codes; linear in dy, so its own gradient is the same map (R1 penalty path)."""
+
+    @staticmethod
+    def forward(ctx, dy, codes, cfg):
+        ctx.cfg = cfg
+        ctx.layout = (tuple(dy.shape), tuple(dy.stride()))
+        ctx.save_for_backward(codes)
+        return _plugin.bias_act_bwd_codes(dy, codes, cfg.dim, cfg.spec.cuda_idx, cfg.alpha, cfg.gain, cfg.clamp, False)[0]
+
+    @staticmethod
+    def backward(ctx, d_dx):
+        codes, = ctx.saved_tensors
+        d_dy = None
+        if ctx.needs_input_grad[0]:
+            d_dy = _BiasActGradCodes.apply(_dense_as(d_dx, *ctx.layout), codes, ctx.cfg)
+        return d_dy, None, None
 
 
 class _BiasActGrad(torch.autograd.Function):

@@ -113,6 +113,34 @@ def test_bias_act_layouts_and_alignment():
     assert_close(bias_act.bias_act(z, act='relu', gain=1), z.clamp(min=0), 1e-7)
 
 
+@pytest.mark.parametrize('dtype', [torch.float32, torch.float16])
+@pytest.mark.parametrize('act,clamp', [('lrelu', 0.7), ('lrelu', None), ('relu', 0.5)])
+def test_bias_act_code_path_is_bitwise_the_saved_output_path(act, clamp, dtype, monkeypatch):
+    # relu / lrelu keep 2-bit sign / clamp codes for the backward pass (lvg_bias_act_fwd_codes / _bwd_codes) instead of
+    # re-reading y; forward, dx, db and the double-backward must be the very same numbers as with the y-based kernels
+    gen = torch.Generator().manual_seed(17)
+    x = (torch.randn(3, 8, 5, 6, 8, generator=gen) * 0.6).to(dtype).to(DEV)
+    x[0, 0, 0, 0, :4] = 0                       # exact zeros: "not positive" must agree on both paths
+    b = torch.randn(8, generator=gen).to(dtype).to(DEV)
+    b[0] = 0
+    dy = torch.randn(x.shape, generator=gen).to(dtype).to(DEV)
+    out = {}
+    for mode in ('1', '0'):
+        monkeypatch.setenv('LVG_BIAS_ACT_CODES', mode)
+        xg, bg = x.clone().requires_grad_(True), b.clone().requires_grad_(True)
+        y = bias_act.bias_act(xg, bg, act=act, clamp=clamp)
+        dx, db = torch.autograd.grad(y, [xg, bg], dy, retain_graph=True)
+        dyg = dy.clone().requires_grad_(True)
+        gx2, = torch.autograd.grad(y, [xg], dyg, create_graph=True)
+        d_dy, = torch.autograd.grad(gx2.float().sum(), [dyg])
+        out[mode] = (y, dx, db, d_dy)
+    for a, c, what in zip(out['1'], out['0'], ('y', 'dx', 'db', 'd(dx)/d(dy)')):
+        if what == 'db':
+            assert_close(a, c, tol(dtype, 1e-5), what)      # different summation order of the fused reduction
+        else:
+            assert torch.equal(a, c), what
+
+
 def test_bias_act_matches_torch_at_scale():
     # lres generator's largest call: (N, 64, T, 36, 64); checked against torch's own kernels
     x = torch.randn(1, 64, 160, 36, 64, device=DEV)

@@ -66,9 +66,10 @@ def main():
             run(f'bias_act fwd ref(torch) {tag} {shape}', lambda: bias_act.bias_act(x, b, act='lrelu', clamp=256, impl='ref'), 2 * n * sz)
             xg = x.clone().requires_grad_(True)
             bg = b.clone().requires_grad_(True)
+            run(f'bias_act fwd lrelu (+2-bit codes for bwd) {tag} {shape}', lambda: bias_act.bias_act(xg, bg, act='lrelu', clamp=256), 2 * n * sz + n // 4)
             y = bias_act.bias_act(xg, bg, act='lrelu', clamp=256)
             dy = torch.randn_like(y)
-            run(f'bias_act bwd dx+db {tag} {shape}', lambda: torch.autograd.grad(y, [xg, bg], dy, retain_graph=True), 3 * n * sz)
+            run(f'bias_act bwd dx+db (from codes) {tag} {shape}', lambda: torch.autograd.grad(y, [xg, bg], dy, retain_graph=True), 2 * n * sz + n // 4)
             if len(shape) == 5:
                 from torch_utils import custom_ops
                 plug = custom_ops.get_plugin('bias_act_plugin')
