@@ -220,17 +220,20 @@ __global__ void __launch_bounds__(kThreads, (G == 2 ? 2 : 4)) bias_act_vec_kerne
             if (N == 4) cword.x = __ldg(reinterpret_cast<const unsigned*>(p.codes) + t * kThreads + threadIdx.x);
             else cword = __ldg(reinterpret_cast<const uint2*>(p.codes) + t * kThreads + threadIdx.x);
         }
-        // Fused db: almost every tile lies inside ONE bias row (rows are ~100 tiles long in the networks). Two divisions
-        // per tile (CTA-uniform) establish that; its packs then need no per-pack row arithmetic and no warp collectives.
+        // Bias along an outer dimension: almost every 16 KB tile lies inside ONE bias row (rows are ~100 tiles long in the
+        // networks). Two divisions per tile (CTA-uniform) establish that; its packs then need no per-pack row arithmetic,
+        // one bias value serves the whole tile, and the fused db needs no warp collectives.
         bool tile_one_row = false;
         int64_t tile_idx = 0;
-        if (FUSE_DB && bmode == BIAS_PER_PACK) {
+        S tile_bias = (S)0;
+        if (bmode == BIAS_PER_PACK) {
             const int64_t last = (base + tile < n_pack ? base + tile : n_pack) - 1;
             const int64_t r0 = bias_row(base * N, p), r1 = bias_row(last * N, p);
             tile_one_row = r0 == r1;
             if (tile_one_row) {
                 tile_idx = r0 - fast_div(r0, p.size_b, p.magic_size) * p.size_b;
-                if (r0 != run_row) {                    // CTA-uniform, hence warp-uniform
+                if (pb) tile_bias = to_acc(pb[tile_idx]);
+                if (FUSE_DB && r0 != run_row) {         // CTA-uniform, hence warp-uniform
                     warp_flush();
                     run_row = r0; run_idx = tile_idx;
                 }
@@ -256,11 +259,10 @@ __global__ void __launch_bounds__(kThreads, (G == 2 ? 2 : 4)) bias_act_vec_kerne
                 const int64_t e0 = pk * N;
                 S bias[N];
                 int64_t bidx;
-                if (FUSE_DB && tile_one_row) {          // bias index known for the whole tile
+                if (tile_one_row) {                     // bias index and value known for the whole tile
                     bidx = tile_idx;
-                    const S bv = pb ? to_acc(pb[tile_idx]) : (S)0;
 #pragma unroll
-                    for (int k = 0; k < N; k++) bias[k] = bv;
+                    for (int k = 0; k < N; k++) bias[k] = tile_bias;
                 } else {
                     fetch_bias<T>(bias, bidx, pb, bmode, e0, p);
                 }

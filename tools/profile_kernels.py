@@ -24,8 +24,9 @@ def run(name, fn):
 
 x = torch.randn(8, 64, 160, 36, 64, device=DEV)
 b = torch.randn(64, device=DEV)
-run('bias_act_fwd', lambda: bias_act.bias_act(x, b, act='lrelu', clamp=256))
 xg, bg = x.clone().requires_grad_(True), b.clone().requires_grad_(True)
+run('bias_act_fwd', lambda: bias_act.bias_act(xg, bg, act='lrelu', clamp=256))      # as in a training step: writes the 2-bit codes
+run('bias_act_fwd_nograd', lambda: bias_act.bias_act(x, b, act='lrelu', clamp=256))
 y = bias_act.bias_act(xg, bg, act='lrelu', clamp=256)
 dy = torch.randn_like(y)
 run('bias_act_bwd', lambda: torch.autograd.grad(y, [xg, bg], dy, retain_graph=True))
