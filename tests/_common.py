@@ -61,6 +61,39 @@ class OracleBiasActPlugin:
         return torch.empty_like(x).copy_(torch.from_numpy(out))   # same memory layout as x, like the real plugin
 
 
+class OracleBiasActCodesPlugin(OracleBiasActPlugin):
+    """Adds the relu / lrelu code-passing pair (lvg_bias_act_fwd_codes / _bwd_codes) so that the host logic that saves
+    2-bit codes instead of y runs on CPU. The codes buffer is opaque to the host code; here one byte per element."""
+
+    def __init__(self):
+        self.fwd_calls = self.bwd_calls = 0
+
+    def bias_act_fwd_codes(self, x, b, dim, act, alpha, gain, clamp):
+        name = {v: k for k, v in orc.ACT_CODES.items()}[act]
+        if name not in ('relu', 'lrelu'):
+            return None
+        self.fwd_calls += 1
+        y = self.bias_act(x, b, None, None, None, 0, dim, act, alpha, gain, clamp)
+        yn = y.detach().float().numpy()
+        inv_gain = 1.0 / gain if gain != 0 else 0.0
+        codes = (~(yn * np.float32(inv_gain) > 0)).astype(np.uint8) | ((clamp >= 0) & ~(np.abs(yn) < clamp)).astype(np.uint8) * 2
+        return y, torch.from_numpy(np.ascontiguousarray(codes.reshape(-1)))
+
+    def bias_act_bwd_codes(self, dy, codes, dim, act, alpha, gain, clamp, want_db):
+        name = {v: k for k, v in orc.ACT_CODES.items()}[act]
+        self.bwd_calls += 1
+        c = codes.numpy().reshape(dy.shape)          # test tensors are contiguous: memory order == index order
+        d = dy.detach().float().numpy()
+        slope = alpha if name == 'lrelu' else 0.0
+        dx = np.where(c & 1, d * np.float32(slope), d) * np.float32(gain)
+        dx = np.where(c & 2, 0, dx).astype(np.float32)
+        out = torch.empty_like(dy).copy_(torch.from_numpy(dx))
+        db = None
+        if want_db:
+            db = out.float().sum([i for i in range(out.ndim) if i != dim]).to(dy.dtype)
+        return out, db
+
+
 class OracleUpfirdn2dPlugin:
     def upfirdn2d(self, x, f, upx, upy, downx, downy, padx0, padx1, pady0, pady1, flip, gain):
         out = orc.upfirdn2d(_np(x), f.numpy(), [upx, upy], [downx, downy], [padx0, padx1, pady0, pady1], flip, gain)

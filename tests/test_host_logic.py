@@ -9,7 +9,7 @@ import pytest
 import torch
 
 from torch_utils.ops import bias_act, upfirdn2d, filtered_lrelu, conv2d_resample, conv2d_gradfix, fma, grid_sample_gradfix
-from _common import (golden, cases, assert_close, t, OracleBiasActPlugin, OracleUpfirdn2dPlugin,
+from _common import (golden, cases, assert_close, t, OracleBiasActPlugin, OracleBiasActCodesPlugin, OracleUpfirdn2dPlugin,
                      OracleFilteredLReluPlugin)
 
 ACTS = sorted(bias_act.activation_funcs)
@@ -52,6 +52,40 @@ def test_bias_act_autograd(oracle_plugins, act, clamp):
             assert_close(ddx, g[f'{tag}/ddx'], 2e-5, 'second order wrt x')
         else:
             assert ddx is None or float(ddx.abs().max()) == 0.0
+
+
+@pytest.mark.parametrize('act', ['relu', 'lrelu'])
+@pytest.mark.parametrize('clamp', [None, 0.7])
+@pytest.mark.parametrize('create_graph', [False, True])
+def test_bias_act_autograd_through_codes(monkeypatch, act, clamp, create_graph):
+    # relu / lrelu: the forward of a call that needs gradients hands 2-bit codes to the backward instead of saving y
+    plug = OracleBiasActCodesPlugin()
+    monkeypatch.setattr(bias_act, '_plugin', plug)
+    g = golden('bias_act')
+    tag = f'{act}_c{"n" if clamp is None else "y"}'
+    x, b, dy = t(g[f'{tag}/x'], grad=True), t(g[f'{tag}/b'], grad=True), t(g[f'{tag}/dy'], grad=True)
+    y = bias_act._bias_act_cuda(dim=1, act=act, clamp=clamp).apply(x, b)
+    assert plug.fwd_calls == 1
+    assert_close(y, g[f'{tag}/y'], 2e-6, 'forward')
+    dx, db = torch.autograd.grad(y, [x, b], dy, create_graph=create_graph)
+    assert plug.bwd_calls == 1
+    assert_close(dx, g[f'{tag}/dx'], 5e-6, 'dx')
+    assert_close(db, g[f'{tag}/db'], 1e-5, 'db')
+    if create_graph:
+        v = t(g[f'{tag}/v'])
+        ddy, ddx = torch.autograd.grad((dx * v).sum(), [dy, x], allow_unused=True)
+        assert_close(ddy, g[f'{tag}/ddy'], 5e-6, 'second order wrt dy')
+        assert ddx is None or float(ddx.abs().max()) == 0.0
+    # no gradient needed -> no codes are produced
+    with torch.no_grad():
+        bias_act._bias_act_cuda(dim=1, act=act, clamp=clamp).apply(x.detach(), b.detach())
+    assert plug.fwd_calls == 1
+    # opting out restores the save-y path
+    monkeypatch.setenv('LVG_BIAS_ACT_CODES', '0')
+    y2 = bias_act._bias_act_cuda(dim=1, act=act, clamp=clamp).apply(x, b)
+    dx2, = torch.autograd.grad(y2, [x], dy.detach())
+    assert plug.fwd_calls == 1
+    assert_close(dx2, g[f'{tag}/dx'], 5e-6, 'dx without codes')
 
 
 @pytest.mark.parametrize('act', ACTS)
