@@ -152,6 +152,70 @@ def test_bias_act_matches_torch_at_scale():
     assert_close(y2, 2 * bias_act.bias_act(x, b, act='lrelu', clamp=None), 1e-6)
 
 
+def test_bias_act_beyond_2_31_elements():
+    # The reference indexes with 32-bit ints and chunks its tensors below 2^31 elements (generator_lres.py:30-70);
+    # these kernels index with 64 bits. 2^31 + 2^21 fp16 elements (4.3 GB), forward and code-passing backward, checked
+    # on slices from both ends and around the 2^31 boundary against the same op on the slices alone.
+    n_ch, inner = 64, (1 << 25) + (1 << 15)
+    free, _ = torch.cuda.mem_get_info()
+    if free < 24 * (1 << 30):
+        pytest.skip('needs ~20 GB of free device memory')
+    x = torch.empty(1, n_ch, inner, device=DEV, dtype=torch.float16)
+    assert x.numel() > (1 << 31)
+    for c0 in range(0, n_ch, 8):
+        x[:, c0:c0 + 8].normal_()
+    b = torch.randn(n_ch, device=DEV, dtype=torch.float16)
+    xg = x.requires_grad_(True)
+    y = bias_act.bias_act(xg, b, act='lrelu', clamp=2.0)
+    dy = torch.empty_like(y)
+    for c0 in range(0, n_ch, 8):
+        dy[:, c0:c0 + 8].normal_()
+    dx, = torch.autograd.grad(y, [xg], dy)
+    for ch, lo in ((0, 0), (31, inner - 4096), (32, 0), (63, inner - 4096), (17, 12345 * 8)):
+        xs = x.detach()[:, ch:ch + 1, lo:lo + 4096].clone().requires_grad_(True)
+        ys = bias_act.bias_act(xs, b[ch:ch + 1], act='lrelu', clamp=2.0)
+        assert torch.equal(ys, y[:, ch:ch + 1, lo:lo + 4096]), (ch, lo)
+        dxs, = torch.autograd.grad(ys, [xs], dy[:, ch:ch + 1, lo:lo + 4096].clone())
+        assert torch.equal(dxs, dx[:, ch:ch + 1, lo:lo + 4096]), (ch, lo)
+
+
+def test_ops_are_cuda_graph_capturable():
+    # bench.py replays a whole training step from CUDA graphs: every op (forward and autograd backward) must capture --
+    # no synchronisation, no host-side reads -- and the replay must reproduce the eager results
+    f = upfirdn2d.setup_filter([1, 3, 3, 1], separable=True).to(DEV)
+    k = (torch.randn(12) / 3).to(DEV)
+    x = torch.randn(2, 8, 18, 32, device=DEV)
+    b = torch.randn(8, device=DEV)
+
+    def forward(xg, bg):
+        y = bias_act.bias_act(upfirdn2d.upsample2d(xg, f, up=2), bg, act='lrelu', clamp=256)
+        return filtered_lrelu.filtered_lrelu(y, k, k, bg, up=2, down=2, padding=[9, 8, 9, 8], clamp=256)
+
+    with torch.no_grad():
+        dy = torch.randn_like(forward(x, b))
+
+    def step():
+        xg, bg = x.detach().requires_grad_(True), b.detach().requires_grad_(True)
+        y = forward(xg, bg)
+        return (y,) + torch.autograd.grad(y, [xg, bg], dy)
+
+    ref = [v.clone() for v in step()]
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        step()                                              # warm-up on the capture stream
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=side, capture_error_mode='thread_local'):
+            out = step()
+    torch.cuda.current_stream().wait_stream(side)
+    for v in out:
+        v.zero_()
+    g.replay()
+    torch.cuda.synchronize()
+    for got, want, what in zip(out, ref, ('y', 'dx', 'db')):
+        assert_close(got, want, 1e-6, what)
+
+
 # ------------------------------------------------------------------ upfirdn2d
 
 _UP = golden('upfirdn2d')
