@@ -275,6 +275,91 @@ __global__ void __launch_bounds__(kThreads) upfirdn2d_stream_kernel(StreamParams
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// 12-tap 2x resampling along the contiguous axis only (the Kaiser filters of TemporalKaiserDownsample,
+// model/generator_lres.py:219-262, applied to [N, C, L, 1] tensors that reach this file as [N*C, 1, L] rows, and
+// their adjoints). Rows are short and there are many of them: a thread produces one 16-byte (DOWN2) or 32-byte (UP2)
+// piece of an output row straight from 3-6 aligned vector loads of the input row; neighbouring threads re-read the
+// halo through L1. No shared memory, no shuffles, every vector is either entirely inside the row or entirely padding.
+//   DOWN2 (pad0 5): out[o] = sum_t g[t] in[2 o - 5 + t]
+//   UP2   (pad0 6): out[2 q] = sum_k g[2 k] in[q + k - 3],  out[2 q + 1] = sum_k g[2 k + 1] in[q + k - 2]
+constexpr int kF12 = 12;
+
+struct Row12Params {
+    const void* x;
+    void* y;
+    const float* f;
+    int64_t fs;
+    int flip;
+    float gain;
+    int64_t rows;        // planes * height
+    int iw, ow, strips;
+};
+
+template <class T> __device__ __forceinline__ void load4(const T* p, float (&v)[4]) { load_strip<T, 4>(p, v); }
+
+template <class T, bool UP>
+__global__ void __launch_bounds__(kThreads) upfirdn2d_row12_kernel(Row12Params p)
+{
+    const int64_t gid = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    const int64_t row = gid / p.strips;
+    const int s = (int)(gid - row * p.strips);
+    if (row >= p.rows) return;
+    float g[kF12];
+#pragma unroll
+    for (int t = 0; t < kF12; t++) g[t] = __ldg(p.f + (p.flip ? t : kF12 - 1 - t) * p.fs) * p.gain;
+    const T* xr = (const T*)p.x + row * p.iw;
+    T* yr = (T*)p.y + row * p.ow;
+    constexpr int NV = UP ? 3 : 6;                       // aligned 4-element vectors that cover the taps of this thread
+    const int i0 = UP ? 4 * s - 4 : 8 * s - 8;           // input index of e[0]
+    float e[4 * NV];
+#pragma unroll
+    for (int v = 0; v < NV; v++) {
+        float q[4] = {0.f, 0.f, 0.f, 0.f};
+        const int i = i0 + 4 * v;
+        if (i >= 0 && i < p.iw) load4<T>(xr + i, q);      // iw % 4 == 0: a vector never straddles the row end
+#pragma unroll
+        for (int k = 0; k < 4; k++) e[4 * v + k] = q[k];
+    }
+    if (UP) {
+        float o[8];
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+            for (int k = 0; k < kF12 / 2; k++) {
+                a0 = fmaf(g[2 * k], e[c + k + 1], a0);
+                a1 = fmaf(g[2 * k + 1], e[c + k + 2], a1);
+            }
+            o[2 * c] = a0; o[2 * c + 1] = a1;
+        }
+        store_strip<T, 8>(yr + 8 * s, o);
+    } else {
+        float o[4];
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            float a = 0.f;
+#pragma unroll
+            for (int t = 0; t < kF12; t++) a = fmaf(g[t], e[2 * c + t + 3], a);
+            o[c] = a;
+        }
+        store_strip<T, 4>(yr + 4 * s, o);
+    }
+}
+
+template <class T>
+int launch_row12(Row12Params& p, bool up, cudaStream_t s)
+{
+    const int64_t threads = p.rows * p.strips;
+    const int64_t blocks = (threads + kThreads - 1) / kThreads;
+    if (blocks > INT32_MAX) return LVG_UNSUPPORTED;
+    if (up) upfirdn2d_row12_kernel<T, true><<<(unsigned)blocks, kThreads, 0, s>>>(p);
+    else    upfirdn2d_row12_kernel<T, false><<<(unsigned)blocks, kThreads, 0, s>>>(p);
+    LVG_LAUNCH_CHECK();
+    return LVG_OK;
+}
+
 int classify(bool has_filter, int taps, int up, int down, int pad0, int in, int out)
 {
     if (!has_filter) return (up == 1 && down == 1 && pad0 == 0 && out == in) ? K_ID : -1;
@@ -333,9 +418,22 @@ int upfirdn2d_stream(const void* x, const float* fx, int64_t fsx, const float* f
     const int64_t n = xsh[0], c = xsh[1], ih = xsh[2], iw = xsh[3], oh = ysh[2], ow = ysh[3];
     if (n * c < 1 || ih < 1 || iw < 1 || ih > (1 << 24) || iw > (1 << 24) || oh > (1 << 24) || ow > (1 << 24)) return LVG_UNSUPPORTED;
     // dense NCHW on both sides
-    if (xst[3] != 1 || xst[2] != iw || xst[1] != ih * iw || (n > 1 && xst[0] != c * ih * iw)) return LVG_UNSUPPORTED;
-    if (yst[3] != 1 || yst[2] != ow || yst[1] != oh * ow || (n > 1 && yst[0] != c * oh * ow)) return LVG_UNSUPPORTED;
+    // (the stride of a size-1 dimension is arbitrary: [N, C, L, 1] tensors arrive here as the view [N, C, 1, L])
+    if (xst[3] != 1 || (ih > 1 && xst[2] != iw) || (c > 1 && xst[1] != ih * iw) || (n > 1 && xst[0] != c * ih * iw)) return LVG_UNSUPPORTED;
+    if (yst[3] != 1 || (oh > 1 && yst[2] != ow) || (c > 1 && yst[1] != oh * ow) || (n > 1 && yst[0] != c * oh * ow)) return LVG_UNSUPPORTED;
     if (!aligned16(x) || !aligned16(y)) return LVG_UNSUPPORTED;
+    // 12 taps along x only (temporal Kaiser resampling on the transposed [N*C, 1, L] view, or any [.., H, W] with a [1, 12] filter)
+    if (fx != nullptr && fy == nullptr && fw == kF12 && fh == 1 && upy == 1 && downy == 1 && pady0 == 0 && oh == ih) {
+        const bool up = upx == 2 && downx == 1 && padx0 == 6 && ow == 2 * iw;
+        const bool down = upx == 1 && downx == 2 && padx0 == 5 && iw % 2 == 0 && ow == iw / 2;
+        const int vec = dtype == LVG_F16 ? 8 : 4;       // the 8-byte fp16 loads of the strip helpers need 4-element alignment, stores up to 8
+        if ((up || down) && iw % 4 == 0 && ow % 4 == 0 && (dtype == LVG_F32 || (up ? ow % vec == 0 : true))) {
+            Row12Params q;
+            q.x = x; q.y = y; q.f = fx; q.fs = fsx; q.flip = flip ? 1 : 0; q.gain = gain;
+            q.rows = n * c * ih; q.iw = (int)iw; q.ow = (int)ow; q.strips = up ? (int)iw / 4 : (int)ow / 4;
+            return dtype == LVG_F32 ? launch_row12<float>(q, up, s) : launch_row12<__half>(q, up, s);
+        }
+    }
     const int kx = classify(fx != nullptr, fw, upx, downx, padx0, (int)iw, (int)ow);
     const int ky = classify(fy != nullptr, fh, upy, downy, pady0, (int)ih, (int)oh);
     if (kx < 0 || ky < 0 || (kx == K_ID && ky == K_ID)) return LVG_UNSUPPORTED;

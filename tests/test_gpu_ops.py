@@ -313,6 +313,25 @@ def test_upfirdn2d_streamed_signatures_vs_oracle(shape, kw, dtype):
 
 
 @pytest.mark.parametrize('dtype', [torch.float32, torch.float16])
+@pytest.mark.parametrize('shape', [(2, 16, 672, 1), (1, 5, 84, 1), (3, 7, 168, 1), (1, 4, 42, 1), (2, 3, 6, 40)])
+def test_upfirdn2d_kaiser12_rows_vs_oracle(shape, dtype):
+    # TemporalKaiserDownsample (generator_lres.py:219-262): 12 taps, down 2 along T on [N, C, T, 1] (and [N, C, T, H*W]) tensors,
+    # forward and adjoint (up 2, pad 6); lengths that are / are not multiples of the vector width (42 -> 21 takes the tiled kernel)
+    gen = torch.Generator().manual_seed(shape[2])
+    f = (torch.rand(12, 1, generator=gen) - 0.3) / 4
+    kw = dict(down=[1, 2], padding=[0, 0, 5, 5])
+    x = torch.randn(*shape, generator=gen).to(dtype)
+    xd = x.to(DEV).requires_grad_(True)
+    y = upfirdn2d.upfirdn2d(xd, f.to(DEV), **kw)
+    assert_close(y, orc.upfirdn2d(x.float().numpy(), f.numpy(), **kw), tol(dtype, 1e-5), 'down 2')
+    dy = torch.randn(y.shape, generator=gen).to(dtype)
+    dx, = torch.autograd.grad(y, [xd], dy.to(DEV))
+    assert_close(dx, orc.upfirdn2d_adjoint(dy.float().numpy(), f.numpy(), x.shape, **kw), tol(dtype, 1e-5), 'adjoint (up 2)')
+    yf = upfirdn2d.upfirdn2d(x.to(DEV), f.to(DEV), flip_filter=True, gain=1.5, **kw)
+    assert_close(yf, orc.upfirdn2d(x.float().numpy(), f.numpy(), flip_filter=True, gain=1.5, **kw), tol(dtype, 1e-5), 'flipped, gain')
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.float16])
 def test_upfirdn2d_temporal_axis_vs_oracle(dtype):
     # filters along H only on [N, C, T, H*W] tensors (U1, U2, U5)
     gen = torch.Generator().manual_seed(11)
