@@ -31,6 +31,7 @@ struct BiasActParams {
     int64_t n;
     int64_t size_b;
     int64_t step_b;
+    int run_tiles;    // fused db: consecutive tiles per run (see the kernel)
     uint64_t magic_step, magic_size;   // ceil(2^64 / d): exact quotients for operands < 2^32 (0 = divide for real)
     int grad;
     float alpha, gain, clamp;
@@ -186,7 +187,8 @@ __global__ void __launch_bounds__(kThreads, (G == 2 ? 2 : 4)) bias_act_vec_kerne
     const T* __restrict__ pdy = kUseDy ? (const T*)p.dy : nullptr;
     T* __restrict__ py = (T*)p.y;
 
-    // Fused bias gradient (FUSE_DB): the tiles are walked in RUNS of kRun consecutive tiles (128 KB of each operand),
+    // Fused bias gradient (FUSE_DB): the tiles are walked in RUNS of p.run_tiles (8) consecutive tiles (128 KB of each operand; two
+    // resident waves of CTAs measured best: 0.93 of the copy rate, one wave 0.81-0.89, runs of 4 tiles 0.7-0.8),
     // runs interleaved over the CTAs like single tiles are in the forward pass -- concurrently resident CTAs stream
     // one contiguous window of memory, which HBM rewards (a fully contiguous per-CTA range measured 0.75 of the copy
     // rate, single interleaved tiles with one atomic per warp and tile 0.5: ~100 consecutive tiles share a bias row
@@ -194,7 +196,7 @@ __global__ void __launch_bounds__(kThreads, (G == 2 ? 2 : 4)) bias_act_vec_kerne
     // step_b elements sharing a bias index) for many packs: each lane keeps a running sum for the warp's current
     // row; only when the row changes or the run ends the warp reduces by shuffle and issues ONE global atomic.
     // No shared memory, no block barriers in the streaming loop.
-    constexpr int kRun = FUSE_DB ? 8 : 1;
+    const int kRun = FUSE_DB ? p.run_tiles : 1;
     const int64_t tile = (int64_t)kThreads * kUnroll;
     const int64_t n_tiles = (n_pack + tile - 1) / tile;
     float run_sum = 0.f;           // this lane's share of the warp's current row
@@ -377,6 +379,10 @@ __global__ void __launch_bounds__(kThreads) bias_act_scalar_kernel(BiasActParams
     }
 }
 
+// tuning knobs of the fused bias-gradient passes (environment overrides for experiments)
+inline int fused_run_tiles() { static const int v = [] { const char* e = getenv("LVG_BA_RUN"); const int x = e ? atoi(e) : 0; return x >= 1 && x <= 64 ? x : 8; }(); return v; }
+inline int fused_waves() { static const int v = [] { const char* e = getenv("LVG_BA_WAVES"); const int x = e ? atoi(e) : 0; return x >= 1 && x <= 16 ? x : 2; }(); return v; }
+
 template <class T> struct HasVecPath { static constexpr bool value = true; };
 template <> struct HasVecPath<double> { static constexpr bool value = false; };   // fp64 is a side path: scalar only
 
@@ -402,9 +408,9 @@ int launch_typed(const BiasActParams& p, cudaStream_t stream)
             int64_t blocks = (n_pack + tile - 1) / tile;
             // whole waves of 4 CTAs per SM; beyond 8 waves the grid-stride loop takes over
             int64_t cap = (int64_t)sms * 4 * 8;
-            if (FUSE_DB) {          // runs of 8 tiles (kRun in the kernel), one resident wave so that every CTA gets ~the same number
-                blocks = (blocks + 7) / 8;
-                cap = (int64_t)sms * 4;
+            if (FUSE_DB) {          // runs of p.run_tiles tiles, whole resident waves so that every CTA gets ~the same number
+                blocks = (blocks + p.run_tiles - 1) / p.run_tiles;
+                cap = (int64_t)sms * 4 * fused_waves();
             }
             if (blocks > cap) blocks = cap;
             void (*k)(BiasActParams, int64_t, int) = nullptr;
@@ -466,7 +472,7 @@ int launch_codes(const BiasActParams& p, bool write, bool fuse_db, cudaStream_t 
     const int64_t tile = (int64_t)kThreads * kUnroll;
     int64_t blocks = (n_pack + tile - 1) / tile;
     int64_t cap = (int64_t)num_sms() * 4 * 8;
-    if (fuse_db) { blocks = (blocks + 7) / 8; cap = (int64_t)num_sms() * 4; }
+    if (fuse_db) { blocks = (blocks + p.run_tiles - 1) / p.run_tiles; cap = (int64_t)num_sms() * 4 * fused_waves(); }
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     void (*k)(BiasActParams, int64_t, int) = write ? bias_act_vec_kernel<T, A, 0, false, 1>
@@ -506,7 +512,7 @@ extern "C" int lvg_bias_act(const void* x, const void* b, const void* xref, cons
     if (rc) return rc;
     LVG_REQUIRE(grad >= 0 && grad <= 2, "bias_act: grad must be 0, 1 or 2 (got %d)", grad);
     if (n == 0) return LVG_OK;
-    BiasActParams p = {x, b, xref, yref, dy, y, nullptr, nullptr, n, b ? size_b : 1, b ? step_b : 1, 0, 0, grad, alpha, gain, clamp};
+    BiasActParams p = {x, b, xref, yref, dy, y, nullptr, nullptr, n, b ? size_b : 1, b ? step_b : 1, 1, 0, 0, grad, alpha, gain, clamp};
     p.magic_step = magic_for(p.step_b, n); p.magic_size = magic_for(p.size_b, n);
     cudaStream_t s = (cudaStream_t)stream;
     if (dtype == LVG_F32) return launch_act<float, false>(act, p, s);
@@ -533,7 +539,7 @@ extern "C" int lvg_bias_act_grad_db(const void* dy_in, const void* b, const void
         return LVG_UNSUPPORTED;
     }
     // b may be NULL here (bias values are only needed by swish); the index math still applies.
-    BiasActParams p = {dy_in, b, xref, yref, nullptr, dx, db_f32, nullptr, n, size_b, step_b, 0, 0, 1, alpha, gain, clamp};
+    BiasActParams p = {dy_in, b, xref, yref, nullptr, dx, db_f32, nullptr, n, size_b, step_b, fused_run_tiles(), 0, 0, 1, alpha, gain, clamp};
     p.magic_step = magic_for(p.step_b, n); p.magic_size = magic_for(p.size_b, n);
     cudaStream_t s = (cudaStream_t)stream;
     if (dtype == LVG_F32) return launch_act<float, true>(act, p, s);
@@ -552,7 +558,7 @@ extern "C" int lvg_bias_act_fwd_codes(const void* x, const void* b, void* y, voi
         return LVG_UNSUPPORTED;
     }
     if (n == 0) return LVG_OK;
-    BiasActParams p = {x, b, nullptr, nullptr, nullptr, y, nullptr, (uint8_t*)codes, n, b ? size_b : 1, b ? step_b : 1, 0, 0, 0, alpha, gain, clamp};
+    BiasActParams p = {x, b, nullptr, nullptr, nullptr, y, nullptr, (uint8_t*)codes, n, b ? size_b : 1, b ? step_b : 1, 1, 0, 0, 0, alpha, gain, clamp};
     p.magic_step = magic_for(p.step_b, n); p.magic_size = magic_for(p.size_b, n);
     cudaStream_t s = (cudaStream_t)stream;
     if (dtype == LVG_F32) return act == LVG_ACT_RELU ? launch_codes<float, LVG_ACT_RELU>(p, true, false, s) : launch_codes<float, LVG_ACT_LRELU>(p, true, false, s);
@@ -573,7 +579,7 @@ extern "C" int lvg_bias_act_bwd_codes(const void* dy, const void* codes, void* d
     }
     if (n == 0) return LVG_OK;
     const bool fuse = db_f32 != nullptr;
-    BiasActParams p = {dy, nullptr, nullptr, nullptr, nullptr, dx, db_f32, (uint8_t*)codes, n, fuse ? size_b : 1, fuse ? step_b : 1, 0, 0, 1, alpha, gain, clamp};
+    BiasActParams p = {dy, nullptr, nullptr, nullptr, nullptr, dx, db_f32, (uint8_t*)codes, n, fuse ? size_b : 1, fuse ? step_b : 1, fused_run_tiles(), 0, 0, 1, alpha, gain, clamp};
     p.magic_step = magic_for(p.step_b, n); p.magic_size = magic_for(p.size_b, n);
     cudaStream_t s = (cudaStream_t)stream;
     if (dtype == LVG_F32) return act == LVG_ACT_RELU ? launch_codes<float, LVG_ACT_RELU>(p, false, fuse, s) : launch_codes<float, LVG_ACT_LRELU>(p, false, fuse, s);
