@@ -152,8 +152,8 @@ class Replay:
             for it in self.items:
                 self._fwd(it, it['x'])
 
-    def forward_backward(self, timer=None):
-        for it in self.items:
+    def forward_backward(self, timer=None, lo=0, hi=None):
+        for it in self.items[lo:hi]:
             x = it['x'].detach().requires_grad_(True)
             leaves = [x]
             b = it.get('b')
@@ -333,7 +333,7 @@ def main():
                           f'{frames} frames/sample, {"64x36" if args.workload == "lres" else "256x144 from 64x36"}',
               'global_batch': batch * world, 'parallelism': f'dp{world}',
               'l2': 'inputs and outputs of the replayed calls exceed L2 (largest tensors 0.75 GB); buffers shared per shape',
-              'launch': 'cuda_graph (step captured once, replayed; NCCL all-reduces eager between the two graphs)' if args.launch == 'graph'
+              'launch': ('cuda_graph (step captured once, replayed' + ('; bucketed NCCL all-reduces between the graph segments, overlapping the rest of the backward pass)' if world > 1 else ')')) if args.launch == 'graph'
                         else 'eager (every call launched from Python)'}
 
     if args.impl == 'reference':
@@ -379,38 +379,55 @@ def main():
     dev_video = torch.empty(vid_shape, dtype=torch.float32, device=device)
     host_out = torch.empty(1, dtype=torch.float32).pin_memory()
 
-    def part_a(timer=None):                 # update_G: G fwd+bwd, D fwd+bwd
-        G.forward_backward(timer)
-        D.forward_backward(timer)
+    # One step = update_G (G fwd+bwd, D fwd+bwd) then update_D (G fwd, D fwd+bwd on fakes, D fwd+bwd on reals).
+    # Each half is a list of SEGMENTS. With one GPU a half is one segment. With several GPUs the network whose
+    # gradients the half exchanges goes last and its second half is cut into kBuckets segments: after each of them the
+    # all-reduce of the corresponding bucket of the flat gradient buffer starts asynchronously (NCCL's own stream) and
+    # overlaps the remaining segments -- the schedule of lvg_dist.FlatGradSync(overlap=True), whose hooks release a
+    # bucket as soon as backward has produced its gradients; only the last bucket's exchange is exposed.
+    kBuckets = 4
 
-    def part_b(timer=None):                 # update_D: G fwd, D fwd+bwd (fake), D fwd+bwd (real)
-        G.forward_only()
-        D.forward_backward(timer)
-        D.forward_backward(timer)
+    def tail_cuts(n):
+        half = n // 2
+        return [half + (n - half) * k // kBuckets for k in range(kBuckets + 1)]
+
+    if world == 1:
+        segs_a = [lambda timer=None: (G.forward_backward(timer), D.forward_backward(timer))]
+        segs_b = [lambda timer=None: (G.forward_only(), D.forward_backward(timer), D.forward_backward(timer))]
+    else:
+        ca, cb = tail_cuts(len(G.items)), tail_cuts(len(D.items))
+        segs_a = [lambda timer=None: (D.forward_backward(timer), G.forward_backward(timer, 0, ca[0]))]
+        segs_a += [(lambda timer=None, k=k: G.forward_backward(timer, ca[k], ca[k + 1])) for k in range(kBuckets)]
+        segs_b = [lambda timer=None: (G.forward_only(), D.forward_backward(timer), D.forward_backward(timer, 0, cb[0]))]
+        segs_b += [(lambda timer=None, k=k: D.forward_backward(timer, cb[k], cb[k + 1])) for k in range(kBuckets)]
+
+    def bucket(flat, k):                     # bucket k of kBuckets (k = 0 leaves first)
+        n = flat.numel()
+        return flat[n * k // kBuckets: n * (k + 1) // kBuckets]
 
     graphs = {}
+
+    def run_half(name, segs, flat, timer, eager, prefill):
+        if prefill:                          # see the roofline pass below
+            torch.cuda._sleep(prefill)
+        works = []
+        for i, seg in enumerate(segs):
+            if graphs and not eager:
+                graphs[name][i].replay()
+            else:
+                seg(timer)
+            if world > 1 and i >= 1:
+                works.append(dist.all_reduce(bucket(flat, i - 1), async_op=True))
+        if world > 1:
+            for w in works:
+                w.wait()
+            postprocess_(flat, 1.0 / world)
 
     def step(timer=None, e2e=False, eager=False, prefill=False):
         if e2e:
             dev_video.copy_(host_video, non_blocking=True)
-        if prefill:                          # see the roofline pass below
-            torch.cuda._sleep(prefill)
-        if graphs and not eager:
-            graphs['a'].replay()
-        else:
-            part_a(timer)
-        if world > 1:
-            dist.all_reduce(flat_g)
-            postprocess_(flat_g, 1.0 / world)
-        if prefill:
-            torch.cuda._sleep(prefill)
-        if graphs and not eager:
-            graphs['b'].replay()
-        else:
-            part_b(timer)
-        if world > 1:
-            dist.all_reduce(flat_d)
-            postprocess_(flat_d, 1.0 / world)
+        run_half('a', segs_a, flat_g, timer, eager, prefill)
+        run_half('b', segs_b, flat_d, timer, eager, prefill)
         if e2e:
             host_out.copy_(dev_video.view(-1)[:1], non_blocking=True)
 
@@ -450,12 +467,16 @@ def main():
         side.wait_stream(torch.cuda.current_stream())
         launches0 = custom_ops.launch_count()
         with torch.cuda.stream(side):
-            for name, fn in (('a', part_a), ('b', part_b)):
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g, pool=pool, stream=side, capture_error_mode='thread_local'):
-                    fn()
-                pool = g.pool()
-                graphs[name] = g
+            captured = {}
+            for name, segs in (('a', segs_a), ('b', segs_b)):
+                captured[name] = []
+                for seg in segs:
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, pool=pool, stream=side, capture_error_mode='thread_local'):
+                        seg()
+                    pool = g.pool()
+                    captured[name].append(g)
+            graphs.update(captured)
         torch.cuda.current_stream().wait_stream(side)
         launches_per_step = custom_ops.launch_count() - launches0
         for _ in range(3):

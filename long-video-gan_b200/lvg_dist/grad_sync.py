@@ -11,6 +11,12 @@ it, so backward writes gradients in place; the exchange is ONE NCCL all-reduce o
 NVLink 5 / NVSwitch (in-switch NVLS reduction when NCCL enables it) followed by ONE in-place
 kernel (``lvg_grad_postprocess``: scale + NaN/Inf clamp). Same results as the reference's
 ``sync_grads`` (up to the summation order inside NCCL).
+
+``overlap=True`` additionally hides the exchange behind the backward pass: the flat buffer is cut into
+buckets in reverse parameter order (the order in which autograd finishes gradients), and a
+post-accumulate-grad hook starts the asynchronous all-reduce of a bucket as soon as its last gradient has
+been written -- NCCL runs it on its own stream while the remaining backward kernels execute; ``sync()``
+then only waits for the tail and runs the post kernel. The reference exchanges after the whole backward.
 """
 import ctypes
 
@@ -28,9 +34,11 @@ class FlatGradSync:
     >>> sync.sync(gain=1.0)               # all-reduce mean, sanitise -- replaces utils.sync_grads(G)
     """
 
-    def __init__(self, module, group=None):
+    def __init__(self, module, group=None, overlap=False, buckets=4):
         self.params = [p for p in module.parameters() if p.requires_grad]
         self.group = group
+        self.overlap = bool(overlap)
+        self._pending, self._works, self._bucket_of, self._slices, self._hooks = [], [], {}, [], []
         if not self.params:
             self.flat = torch.zeros(0)
             return
@@ -46,6 +54,52 @@ class FlatGradSync:
             p.grad = view
             self._views.append(view)
             ofs += p.numel()
+        if self.overlap:
+            self._make_buckets(max(1, int(buckets)))
+
+    # ---- overlap with the backward pass -------------------------------------------------------------------
+    def _make_buckets(self, n_buckets):
+        """Contiguous slices of the flat buffer of ~equal size; bucket 0 holds the LAST parameters (ready first)."""
+        total = self.flat.numel()
+        target = (total + n_buckets - 1) // n_buckets
+        bounds, ofs, start, count = [], 0, 0, 0          # (first param index, flat start)
+        groups, cur = [], []
+        for i, p in enumerate(self.params):
+            cur.append(i)
+            count += p.numel()
+            ofs += p.numel()
+            if count >= target or i == len(self.params) - 1:
+                groups.append((cur, start, ofs))
+                cur, start, count = [], ofs, 0
+        groups.reverse()
+        self._slices = [(a, b) for _, a, b in groups]
+        self._members = [len(idx) for idx, _, _ in groups]
+        for b, (idx, _, _) in enumerate(groups):
+            for i in idx:
+                self._bucket_of[i] = b
+        self._arm()
+        for i, p in enumerate(self.params):
+            self._hooks.append(p.register_post_accumulate_grad_hook(self._make_hook(i)))
+
+    def _arm(self):
+        self._pending = list(self._members)
+        self._works = [None] * len(self._members)
+
+    def _make_hook(self, i):
+        def hook(param):
+            b = self._bucket_of[i]
+            view = self._views[i]
+            if param.grad is not None and param.grad.data_ptr() != view.data_ptr():
+                view.copy_(param.grad)                   # a replaced .grad: fold it back before the bucket leaves
+                param.grad = view
+            self._pending[b] -= 1
+            if self._pending[b] == 0 and self._world() > 1:
+                a, e = self._slices[b]
+                self._works[b] = dist.all_reduce(self.flat[a:e], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+        return hook
+
+    def _world(self):
+        return dist.get_world_size(self.group) if dist.is_available() and dist.is_initialized() else 1
 
     def zero_grad(self):
         """Zero in place (``set_to_none`` would detach the views from the flat buffer)."""
@@ -65,10 +119,20 @@ class FlatGradSync:
         """Average the gradients over the process group, scale by `gain`, sanitise NaN/Inf."""
         if self.flat.numel() == 0:
             return
-        self._reattach()
-        world = dist.get_world_size(self.group) if dist.is_available() and dist.is_initialized() else 1
-        if world > 1:
-            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
+        world = self._world()
+        if self.overlap:
+            # buckets whose hooks all fired are already in flight; anything else (parameters that received no gradient
+            # in this backward pass) is exchanged now
+            for b, (a, e) in enumerate(self._slices):
+                if self._works[b] is not None:
+                    self._works[b].wait()
+                elif world > 1:
+                    dist.all_reduce(self.flat[a:e], op=dist.ReduceOp.SUM, group=self.group)
+            self._arm()
+        else:
+            self._reattach()
+            if world > 1:
+                dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
         postprocess_(self.flat, scale=float(gain) / world, limit=_GRAD_LIMIT)
 
 

@@ -90,3 +90,49 @@ def test_single_process_is_a_plain_postprocess():
     assert torch.allclose(sync.flat, before * 2.0)
     sync.zero_grad()
     assert float(sync.flat.abs().sum()) == 0 and lin.weight.grad.data_ptr() == sync.flat.data_ptr()
+
+
+def _overlap_worker(rank, world, port, ret):
+    sys.path.insert(0, os.path.join(ROOT, 'long-video-gan_b200'))
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        from lvg_dist.grad_sync import FlatGradSync
+        outs = []
+        for overlap in (False, True):
+            torch.manual_seed(0)
+            net = torch.nn.Sequential(torch.nn.Linear(6, 16), torch.nn.Tanh(), torch.nn.Linear(16, 16), torch.nn.Tanh(),
+                                      torch.nn.Linear(16, 3))
+            extra = torch.nn.Parameter(torch.ones(5))          # never used in the loss: its bucket gets no hook call
+            net.register_parameter('unused', extra)
+            sync = FlatGradSync(net, overlap=overlap, buckets=3)
+            gen = torch.Generator().manual_seed(10 + rank)
+            for it in range(3):                                # several steps: the hook bookkeeping must re-arm
+                sync.zero_grad()
+                x = torch.randn(8, 6, generator=gen)
+                net(x).square().mean().backward()
+                if overlap and it == 1:
+                    assert any(w is not None for w in sync._works)     # buckets left during the backward pass
+                sync.sync(gain=0.5)
+                outs.append(sync.flat.clone())
+        ret[rank] = outs
+    finally:
+        dist.destroy_process_group()
+
+
+def test_overlapped_buckets_give_the_same_gradients_world2():
+    # overlap=True starts the all-reduce of a bucket from a post-accumulate-grad hook while backward is still running;
+    # the exchanged gradients must equal the single all-reduce after backward, step after step
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_overlap_worker, args=(world, port, ret), nprocs=world, join=True)
+    for r in range(world):
+        outs = ret[r]
+        plain, over = outs[:3], outs[3:]
+        for a, b in zip(plain, over):
+            assert torch.allclose(a, b, rtol=1e-6, atol=1e-8)
+    for a, b in zip(ret[0], ret[1]):
+        assert torch.equal(a, b)                                # both ranks hold the same averaged gradients
