@@ -1,9 +1,8 @@
 """2-D convolution with optional FIR up/down-sampling (``torch_utils.ops.conv2d_resample``).
 
-Signature and padding conventions as in the reference (conv2d_resample.py:45-141).
-The operator is a composition of ``upfirdn2d`` and ``conv2d_gradfix.conv2d`` /
-``conv_transpose2d``; the order of the stages per case is part of the numerics
-(fp16 rounding points) and is kept:
+Signature and padding conventions as in the reference (conv2d_resample.py:45-141). The operator is a chain of
+``upfirdn2d`` and ``conv2d_gradfix.conv2d`` / ``conv_transpose2d`` stages; which chain is used for which case is part
+of the numerics (fp16 rounding points) and is kept:
 
     1x1 kernel, down only : FIR-decimate, then convolve
     1x1 kernel, up only   : convolve, then zero-insert + FIR
@@ -11,13 +10,15 @@ The operator is a composition of ``upfirdn2d`` and ``conv2d_gradfix.conv2d`` /
     up (optionally down)  : transposed strided convolution, then FIR (then FIR-decimate)
     no resampling         : plain convolution when the padding is symmetric and >= 0
     otherwise             : up-FIR, convolve, FIR-decimate
+
+Here the case analysis is separated from the execution: ``_plan`` turns the arguments into a short list of stage
+descriptions, ``_run`` executes them.
 """
 import torch
 
 from . import conv2d_gradfix
 from . import upfirdn2d
-from .upfirdn2d import _parse_padding
-from .upfirdn2d import _get_filter_size
+from .upfirdn2d import _get_filter_size, _parse_padding
 
 
 def _get_weight_shape(w):
@@ -26,11 +27,78 @@ def _get_weight_shape(w):
 
 def _conv2d_wrapper(x, w, stride=1, padding=0, groups=1, transpose=False, flip_weight=True):
     """conv2d is a correlation; ``flip_weight=False`` asks for a true convolution (mirrored kernel)."""
-    _oc, _icpg, kh, kw = _get_weight_shape(w)
-    if not flip_weight and (kw > 1 or kh > 1):
+    kh, kw = _get_weight_shape(w)[2:]
+    if (kh > 1 or kw > 1) and not flip_weight:
         w = w.flip([2, 3])
-    op = conv2d_gradfix.conv_transpose2d if transpose else conv2d_gradfix.conv2d
-    return op(x, w, stride=stride, padding=padding, groups=groups)
+    conv = conv2d_gradfix.conv_transpose2d if transpose else conv2d_gradfix.conv2d
+    return conv(x, w, stride=stride, padding=padding, groups=groups)
+
+
+def _footprint(taps, factor, upsampling):
+    """Padding (before, after) that centres a `taps`-tap resampling filter for the given factor."""
+    if upsampling:
+        return (taps + factor - 1) // 2, (taps - factor) // 2
+    return (taps - factor + 1) // 2, (taps - factor) // 2
+
+
+def _to_transposed_layout(w, groups):
+    """[Cout, Cin/g, kh, kw] -> the [Cin, Cout/g, kh, kw] layout conv_transpose2d expects."""
+    if groups == 1:
+        return w.transpose(0, 1)
+    cout, cin_g, kh, kw = _get_weight_shape(w)
+    w = w.reshape(groups, cout // groups, cin_g, kh, kw).transpose(1, 2)
+    return w.reshape(groups * cin_g, cout // groups, kh, kw)
+
+
+def _plan(kw, kh, fw, fh, up, down, padding):
+    """Stage list for one call. A stage is ('fir', kwargs of upfirdn2d) or ('conv', kwargs of _conv2d_wrapper);
+    'conv' stages may carry 'transposed_weight': True (the weight is re-laid-out before the call)."""
+    px0, px1, py0, py1 = _parse_padding(padding)
+    if up > 1:          # fold the resampling filters' own footprint into the padding
+        (ax, bx), (ay, by) = _footprint(fw, up, True), _footprint(fh, up, True)
+        px0, px1, py0, py1 = px0 + ax, px1 + bx, py0 + ay, py1 + by
+    if down > 1:
+        (ax, bx), (ay, by) = _footprint(fw, down, False), _footprint(fh, down, False)
+        px0, px1, py0, py1 = px0 + ax, px1 + bx, py0 + ay, py1 + by
+    pad = [px0, px1, py0, py1]
+    pointwise = kw == 1 and kh == 1
+    gain = up ** 2
+
+    if pointwise and up == 1 and down > 1:
+        return [('fir', dict(down=down, padding=pad)), ('conv', dict())]
+    if pointwise and down == 1 and up > 1:
+        return [('conv', dict()), ('fir', dict(up=up, padding=pad, gain=gain))]
+    if up == 1 and down > 1:
+        return [('fir', dict(padding=pad)), ('conv', dict(stride=down))]
+    if up > 1:
+        # the transposed convolution absorbs as much of the (now possibly negative) padding as it can
+        px0, px1, py0, py1 = px0 - (kw - 1), px1 - (kw - up), py0 - (kh - 1), py1 - (kh - up)
+        pxt, pyt = max(min(-px0, -px1), 0), max(min(-py0, -py1), 0)
+        stages = [('conv', dict(stride=up, padding=[pyt, pxt], transpose=True, transposed_weight=True)),
+                  ('fir', dict(padding=[px0 + pxt, px1 + pxt, py0 + pyt, py1 + pyt], gain=gain))]
+        if down > 1:
+            stages.append(('fir', dict(down=down)))
+        return stages
+    if down == 1 and px0 == px1 and py0 == py1 and min(px0, py0) >= 0:
+        return [('conv', dict(padding=[py0, px0]))]
+    stages = [('fir', dict(up=up, padding=pad, gain=gain, no_filter=(up == 1))), ('conv', dict())]
+    if down > 1:
+        stages.append(('fir', dict(down=down)))
+    return stages
+
+
+def _run(stages, x, w, f, groups, flip_weight, flip_filter):
+    for kind, kwargs in stages:
+        kwargs = dict(kwargs)
+        if kind == 'fir':
+            filt = None if kwargs.pop('no_filter', False) else f
+            x = upfirdn2d.upfirdn2d(x=x, f=filt, flip_filter=flip_filter, **kwargs)
+        else:
+            transposed = kwargs.pop('transposed_weight', False)
+            weight = _to_transposed_layout(w, groups) if transposed else w
+            # the transposed convolution mirrors the kernel once more, hence the inverted flag
+            x = _conv2d_wrapper(x=x, w=weight, groups=groups, flip_weight=(flip_weight != transposed), **kwargs)
+    return x
 
 
 def conv2d_resample(x, w, f=None, up=1, down=1, padding=0, groups=1, flip_weight=True, flip_filter=False):
@@ -42,63 +110,6 @@ def conv2d_resample(x, w, f=None, up=1, down=1, padding=0, groups=1, flip_weight
     assert isinstance(up, int) and (up >= 1)
     assert isinstance(down, int) and (down >= 1)
     assert isinstance(groups, int) and (groups >= 1)
-    out_channels, in_channels_per_group, kh, kw = _get_weight_shape(w)
+    kh, kw = _get_weight_shape(w)[2:]
     fw, fh = _get_filter_size(f)
-    px0, px1, py0, py1 = _parse_padding(padding)
-
-    # fold the resampling filters' own footprint into the padding
-    if up > 1:
-        px0 += (fw + up - 1) // 2
-        px1 += (fw - up) // 2
-        py0 += (fh + up - 1) // 2
-        py1 += (fh - up) // 2
-    if down > 1:
-        px0 += (fw - down + 1) // 2
-        px1 += (fw - down) // 2
-        py0 += (fh - down + 1) // 2
-        py1 += (fh - down) // 2
-    pad = [px0, px1, py0, py1]
-    pointwise = (kw == 1 and kh == 1)
-
-    if pointwise and down > 1 and up == 1:
-        x = upfirdn2d.upfirdn2d(x=x, f=f, down=down, padding=pad, flip_filter=flip_filter)
-        return _conv2d_wrapper(x=x, w=w, groups=groups, flip_weight=flip_weight)
-
-    if pointwise and up > 1 and down == 1:
-        x = _conv2d_wrapper(x=x, w=w, groups=groups, flip_weight=flip_weight)
-        return upfirdn2d.upfirdn2d(x=x, f=f, up=up, padding=pad, gain=up ** 2, flip_filter=flip_filter)
-
-    if down > 1 and up == 1:
-        x = upfirdn2d.upfirdn2d(x=x, f=f, padding=pad, flip_filter=flip_filter)
-        return _conv2d_wrapper(x=x, w=w, stride=down, groups=groups, flip_weight=flip_weight)
-
-    if up > 1:
-        # transposed convolution wants [Cin, Cout/groups, kh, kw]
-        if groups == 1:
-            w = w.transpose(0, 1)
-        else:
-            w = w.reshape(groups, out_channels // groups, in_channels_per_group, kh, kw)
-            w = w.transpose(1, 2)
-            w = w.reshape(groups * in_channels_per_group, out_channels // groups, kh, kw)
-        px0 -= kw - 1
-        px1 -= kw - up
-        py0 -= kh - 1
-        py1 -= kh - up
-        pxt = max(min(-px0, -px1), 0)
-        pyt = max(min(-py0, -py1), 0)
-        x = _conv2d_wrapper(x=x, w=w, stride=up, padding=[pyt, pxt], groups=groups, transpose=True,
-                            flip_weight=(not flip_weight))
-        x = upfirdn2d.upfirdn2d(x=x, f=f, padding=[px0 + pxt, px1 + pxt, py0 + pyt, py1 + pyt], gain=up ** 2,
-                                flip_filter=flip_filter)
-        if down > 1:
-            x = upfirdn2d.upfirdn2d(x=x, f=f, down=down, flip_filter=flip_filter)
-        return x
-
-    if up == 1 and down == 1 and px0 == px1 and py0 == py1 and px0 >= 0 and py0 >= 0:
-        return _conv2d_wrapper(x=x, w=w, padding=[py0, px0], groups=groups, flip_weight=flip_weight)
-
-    x = upfirdn2d.upfirdn2d(x=x, f=(f if up > 1 else None), up=up, padding=pad, gain=up ** 2, flip_filter=flip_filter)
-    x = _conv2d_wrapper(x=x, w=w, groups=groups, flip_weight=flip_weight)
-    if down > 1:
-        x = upfirdn2d.upfirdn2d(x=x, f=f, down=down, flip_filter=flip_filter)
-    return x
+    return _run(_plan(kw, kh, fw, fh, up, down, padding), x, w, f, groups, flip_weight, flip_filter)
