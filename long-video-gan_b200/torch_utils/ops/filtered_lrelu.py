@@ -28,25 +28,22 @@ def _init():
     return True
 
 
-def _get_filter_size(f):
-    if f is None:
-        return 1, 1
-    assert isinstance(f, torch.Tensor)
-    assert 1 <= f.ndim <= 2
-    return f.shape[-1], f.shape[0]  # width, height
+_get_filter_size = upfirdn2d._get_filter_size      # (width, height) of a [taps] / [fh, fw] filter, (1, 1) for None
+_parse_padding = upfirdn2d._parse_padding          # int | [x, y] | [x0, x1, y0, y1] -> (px0, px1, py0, py1)
 
 
-def _parse_padding(padding):
-    if isinstance(padding, int):
-        padding = [padding, padding]
-    assert isinstance(padding, (list, tuple))
-    assert all(isinstance(v, (int, np.integer)) for v in padding)
-    padding = [int(v) for v in padding]
-    if len(padding) == 2:
-        px, py = padding
-        padding = [px, px, py, py]
-    px0, px1, py0, py1 = padding
-    return px0, px1, py0, py1
+def _check_scalars(up, down, gain, slope, clamp):
+    """Argument contract shared by both implementations (filtered_lrelu.py:121-135 of the reference)."""
+    for name, v in (('up', up), ('down', down)):
+        assert isinstance(v, int) and v >= 1, name
+    assert gain == float(gain) and gain > 0
+    assert slope == float(slope) and slope >= 0
+    assert clamp is None or (clamp == float(clamp) and clamp >= 0)
+
+
+def _output_extent(n_in, up, down, pad0, pad1, taps_up, taps_down):
+    """Samples left after up-sampling by `up`, padding, the two FIR filters and decimation by `down`."""
+    return (n_in * up + (pad0 + pad1) - (taps_up - 1) - (taps_down - 1) + (down - 1)) // down
 
 
 def filtered_lrelu(x, fu=None, fd=None, b=None, up=1, down=1, padding=0, gain=np.sqrt(2), slope=0.2, clamp=None,
@@ -72,31 +69,22 @@ def _filtered_lrelu_ref(x, fu=None, fd=None, b=None, up=1, down=1, padding=0, ga
                         flip_filter=False):
     """Composition of bias_act and upfirdn2d (CPU tensors, ``impl='ref'``)."""
     assert isinstance(x, torch.Tensor) and x.ndim == 4
-    fu_w, fu_h = _get_filter_size(fu)
-    fd_w, fd_h = _get_filter_size(fd)
+    _check_scalars(up, down, gain, slope, clamp)
     if b is not None:
         assert isinstance(b, torch.Tensor) and b.dtype == x.dtype
         assert b.ndim == 1 and b.shape[0] == x.shape[1]
-    assert isinstance(up, int) and up >= 1
-    assert isinstance(down, int) and down >= 1
+    (fu_w, fu_h), (fd_w, fd_h) = _get_filter_size(fu), _get_filter_size(fd)
     px0, px1, py0, py1 = _parse_padding(padding)
-    assert gain == float(gain) and gain > 0
-    assert slope == float(slope) and slope >= 0
-    assert clamp is None or (clamp == float(clamp) and clamp >= 0)
+    expect = [x.shape[0], x.shape[1], _output_extent(x.shape[2], up, down, py0, py1, fu_h, fd_h),
+              _output_extent(x.shape[3], up, down, px0, px1, fu_w, fd_w)]
+    dtype = x.dtype
 
-    n, c, in_h, in_w = x.shape
-    in_dtype = x.dtype
-    out_w = (in_w * up + (px0 + px1) - (fu_w - 1) - (fd_w - 1) + (down - 1)) // down
-    out_h = (in_h * up + (py0 + py1) - (fu_h - 1) - (fd_h - 1) + (down - 1)) // down
-
-    x = bias_act.bias_act(x=x, b=b)
-    x = upfirdn2d.upfirdn2d(x=x, f=fu, up=up, padding=[px0, px1, py0, py1], gain=up ** 2, flip_filter=flip_filter)
-    x = bias_act.bias_act(x=x, act='lrelu', alpha=slope, gain=gain, clamp=clamp)
-    x = upfirdn2d.upfirdn2d(x=x, f=fd, down=down, flip_filter=flip_filter)
-
-    assert list(x.shape) == [n, c, out_h, out_w]
-    assert x.dtype == in_dtype
-    return x
+    y = bias_act.bias_act(x=x, b=b)                                                            # bias
+    y = upfirdn2d.upfirdn2d(x=y, f=fu, up=up, padding=[px0, px1, py0, py1], gain=up ** 2, flip_filter=flip_filter)
+    y = bias_act.bias_act(x=y, act='lrelu', alpha=slope, gain=gain, clamp=clamp)               # gain, lrelu, clamp
+    y = upfirdn2d.upfirdn2d(x=y, f=fd, down=down, flip_filter=flip_filter)
+    assert list(y.shape) == expect and y.dtype == dtype
+    return y
 
 
 class _Config:
@@ -104,13 +92,9 @@ class _Config:
     __slots__ = ('up', 'down', 'px0', 'px1', 'py0', 'py1', 'gain', 'slope', 'clamp', 'flip')
 
     def __init__(self, up, down, padding, gain, slope, clamp, flip_filter):
-        assert isinstance(up, int) and up >= 1
-        assert isinstance(down, int) and down >= 1
+        _check_scalars(up, down, gain, slope, clamp)
         self.up, self.down = up, down
         self.px0, self.px1, self.py0, self.py1 = _parse_padding(padding)
-        assert gain == float(gain) and gain > 0
-        assert slope == float(slope) and slope >= 0
-        assert clamp is None or (clamp == float(clamp) and clamp >= 0)
         self.gain, self.slope = float(gain), float(slope)
         self.clamp = float(clamp if clamp is not None else 'inf')
         self.flip = bool(flip_filter)
@@ -130,34 +114,34 @@ def _filtered_lrelu_cuda(up=1, down=1, padding=0, gain=np.sqrt(2), slope=0.2, cl
     return _filtered_lrelu_cuda_cache.setdefault(cfg.key(), cfg)
 
 
+def _as_kernel_filter(f, factor, device):
+    """None -> exact 1x1 full filter; a separable single tap without resampling -> the full 1x1 filter f*f."""
+    if f is None:
+        return torch.ones([1, 1], dtype=torch.float32, device=device)
+    assert 1 <= f.ndim <= 2
+    if factor == 1 and f.ndim == 1 and f.shape[0] == 1:
+        return f.square()[None]
+    return f
+
+
+def _warn_if_permuted(x):
+    steps = [x.stride(d) for d in range(x.ndim) if x.size(d) > 1]
+    if any(a < b for a, b in zip(steps, steps[1:])):
+        warnings.warn('low-performance memory layout detected in filtered_lrelu input', RuntimeWarning)
+
+
 class _FilteredLRelu(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, fu, fd, b, si, sx, sy, cfg):
         assert isinstance(x, torch.Tensor) and x.ndim == 4
         c = cfg
-        # absent filters are exact 1x1 full filters
-        if fu is None:
-            fu = torch.ones([1, 1], dtype=torch.float32, device=x.device)
-        if fd is None:
-            fd = torch.ones([1, 1], dtype=torch.float32, device=x.device)
-        assert 1 <= fu.ndim <= 2
-        assert 1 <= fd.ndim <= 2
-        # a separable single tap without resampling is the full 1x1 filter f*f
-        if c.up == 1 and fu.ndim == 1 and fu.shape[0] == 1:
-            fu = fu.square()[None]
-        if c.down == 1 and fd.ndim == 1 and fd.shape[0] == 1:
-            fd = fd.square()[None]
-        if si is None:
-            si = torch.empty([0])
-        if b is None:
-            b = torch.zeros([x.shape[1]], dtype=x.dtype, device=x.device)
-
+        fu = _as_kernel_filter(fu, c.up, x.device)
+        fd = _as_kernel_filter(fd, c.down, x.device)
+        si = torch.empty([0]) if si is None else si
+        b = torch.zeros([x.shape[1]], dtype=x.dtype, device=x.device) if b is None else b
         # the 2-bit sign tensor is only produced when somebody will differentiate
         write_signs = (si.numel() == 0) and (x.requires_grad or b.requires_grad)
-
-        strides = [x.stride(i) for i in range(x.ndim) if x.size(i) > 1]
-        if any(s0 < s1 for s0, s1 in zip(strides[:-1], strides[1:])):
-            warnings.warn('low-performance memory layout detected in filtered_lrelu input', RuntimeWarning)
+        _warn_if_permuted(x)
 
         y = so = None
         rc = -1
