@@ -89,7 +89,7 @@ __device__ __forceinline__ uint32_t load_pair(const __half* row, int e, int lo, 
     return v;
 }
 
-template <int KH, int KW, int SH>
+template <int KH, int KW, int SH, int NB>     // NB = NT / 8 = x rows per producer warp (compile time: the row loops unroll without guards)
 __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_tc_kernel(WgradParams p)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_tc_kernel(WgradParams 
     // swizzle atoms must sit on 1024-byte boundaries of the shared-memory address space
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
 
-    const int NT = p.nt;
+    constexpr int NT = NB * 8;
     const int b_copy = NT * 128;                 // bytes of one shifted copy: NT rows x 64 pixels
     const int stage_bytes = kAStage + KW * b_copy;
     const int nti = blockIdx.x / KH, ky = blockIdx.x - nti * KH;
@@ -130,14 +130,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_tc_kernel(WgradParams 
 
     // Producer warp w moves rows w, w + 8, ...; lane l moves pixel pair l of the stage's 64 pixels.
     // Row r of an operand tile: byte (r / 8) * 1024 + (r % 8) * 128 + ((chunk ^ (r % 8)) * 16) + 4 * (l % 4), chunk = l / 4.
-    const int nb_rows = NT / 8;                                       // B rows per warp (NT % 8 == 0)
+    constexpr int nb_rows = NB;                                       // B rows per warp
     const int a_valid = min(kRowsA, max(0, (p.cout - co0 - warp + 7) / 8));    // rows of this warp with a real co
     const int b_valid = min(nb_rows, max(0, (p.cin - ci0 - warp + 7) / 8));    // ... with a real ci
     const int row_lo = (warp % 8) * 128 + (((lane / 4) ^ (warp % 8)) * 16) + (lane % 4) * 4;     // + 1024 per row step (r += 8)
     const int a_rstride = 8 * p.ho * p.wo, b_rstride = 8 * p.h * p.w;
 
     // Two register sets: the loads of stage s + 1 are in flight while stage s is written to shared memory.
-    struct Regs { uint32_t pa[kRowsA], pb[kRowsB][NPB]; };
+    struct Regs { uint32_t pa[kRowsA], pb[NB][NPB]; };
     Regs R0, R1;
     int pf_inst = 0, pf_oy = 0, pf_xs = 0;       // the next stage to fetch
 
@@ -172,18 +172,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_tc_kernel(WgradParams 
 #pragma unroll
         for (int q = 0; q < NPB; q++) in[q] = 2 * (lane + q) >= lo && 2 * (lane + q) < hi;
 #pragma unroll
-        for (int j = 0; j < kRowsB; j++) {
-            if (j < nb_rows) {
-                const __half* row = rowb + j * b_rstride;
+        for (int j = 0; j < NB; j++) {
+            const __half* row = rowb + j * b_rstride;
+            const bool rv = j < b_valid;
 #pragma unroll
-                for (int q = 0; q < NPB; q++) {
-                    uint32_t v = 0;
-                    if (j < b_valid) {
-                        if (x_paired) { if (in[q]) v = __ldg(reinterpret_cast<const unsigned int*>(row) + lane + q); }
-                        else v = load_pair(row, 2 * (lane + q), lo, hi, false);
-                    }
-                    R.pb[j][q] = v;
-                }
+            for (int q = 0; q < NPB; q++) {
+                uint32_t v = 0;
+                if (x_paired) { if (rv && in[q]) v = __ldg(reinterpret_cast<const unsigned int*>(row) + lane + q); }
+                else if (rv) v = load_pair(row, 2 * (lane + q), lo, hi, false);
+                R.pb[j][q] = v;
             }
         }
         // advance to the following stage
@@ -195,12 +192,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_tc_kernel(WgradParams 
         for (int j = 0; j < kRowsA; j++) *reinterpret_cast<uint32_t*>(da + j * 1024) = R.pa[j];
         unsigned char* db = buf + kAStage + row_lo;
 #pragma unroll
-        for (int j = 0; j < kRowsB; j++) {
-            if (j < nb_rows) {
-                *reinterpret_cast<uint32_t*>(db + j * 1024) = shifted<SH, NPB>(R.pb[j]);
-                if constexpr (KW > 1) *reinterpret_cast<uint32_t*>(db + b_copy + j * 1024) = shifted<SH + 1, NPB>(R.pb[j]);
-                if constexpr (KW > 2) *reinterpret_cast<uint32_t*>(db + 2 * b_copy + j * 1024) = shifted<SH + 2, NPB>(R.pb[j]);
-            }
+        for (int j = 0; j < NB; j++) {
+            *reinterpret_cast<uint32_t*>(db + j * 1024) = shifted<SH, NPB>(R.pb[j]);
+            if constexpr (KW > 1) *reinterpret_cast<uint32_t*>(db + b_copy + j * 1024) = shifted<SH + 1, NPB>(R.pb[j]);
+            if constexpr (KW > 2) *reinterpret_cast<uint32_t*>(db + 2 * b_copy + j * 1024) = shifted<SH + 2, NPB>(R.pb[j]);
         }
     };
 
@@ -326,9 +321,9 @@ extern "C" int lvg_conv2d_wgrad(const void* x, const void* dy, void* dw, int dty
         set_error("conv2d_wgrad: a group's activations exceed 32-bit offsets");
         return LVG_UNSUPPORTED;
     }
-    const int nt_max = kw == 3 ? 160 : 256;
+    const int nt_max = 160;
     const int ntiles = (cin + nt_max - 1) / nt_max;
-    p.nt = (((cin + ntiles - 1) / ntiles) + 15) / 16 * 16;
+    p.nt = (((cin + ntiles - 1) / ntiles) + 31) / 32 * 32;        // multiples of 32 only (template instantiations)
     const int mt = (cout + kBM - 1) / kBM;
     p.x_pair_ok = ((reinterpret_cast<uintptr_t>(x) & 3) == 0 && (wd & 1) == 0) ? 1 : 0;
     p.dy_pair_ok = ((reinterpret_cast<uintptr_t>(dy) & 3) == 0 && (p.wo & 1) == 0) ? 1 : 0;
@@ -342,8 +337,13 @@ extern "C" int lvg_conv2d_wgrad(const void* x, const void* dy, void* dw, int dty
     LVG_REQUIRE(smem <= 227 * 1024, "conv2d_wgrad: tile does not fit shared memory");
     dim3 grid((unsigned)(ntiles * kh), (unsigned)mt, (unsigned)groups);
     cudaStream_t s = (cudaStream_t)stream;
-    void (*k)(WgradParams) = kh == 3 ? ((pad_w & 1) ? conv_wgrad_tc_kernel<3, 3, 1> : conv_wgrad_tc_kernel<3, 3, 0>)
-                                     : ((pad_w & 1) ? conv_wgrad_tc_kernel<1, 1, 1> : conv_wgrad_tc_kernel<1, 1, 0>);
+    // rows per producer warp are a template parameter: NT is rounded up to 32, 64, 96, 128 or 160
+    void (*k)(WgradParams) = nullptr;
+#define LVG_WG_CASE(nb) if (p.nt == (nb) * 8) k = kh == 3 ? ((pad_w & 1) ? conv_wgrad_tc_kernel<3, 3, 1, nb> : conv_wgrad_tc_kernel<3, 3, 0, nb>) \
+                                                         : ((pad_w & 1) ? conv_wgrad_tc_kernel<1, 1, 1, nb> : conv_wgrad_tc_kernel<1, 1, 0, nb>);
+    LVG_WG_CASE(4) LVG_WG_CASE(8) LVG_WG_CASE(12) LVG_WG_CASE(16) LVG_WG_CASE(20)
+#undef LVG_WG_CASE
+    LVG_REQUIRE(k != nullptr, "conv2d_wgrad: no kernel for NT = %d", p.nt);
     LVG_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k<<<grid, kThreads, smem, s>>>(p);
     LVG_LAUNCH_CHECK();
