@@ -112,7 +112,13 @@ def _ptr(t):
     return t.data_ptr()
 
 
+_raw_stream = getattr(torch._C, '_cuda_getCurrentRawStream', None)
+
+
 def _stream(t):
+    """cudaStream_t of torch's current stream on t's device (the raw-handle accessor skips building a Stream object)."""
+    if _raw_stream is not None and t.device.index is not None:
+        return _raw_stream(t.device.index)
     return torch.cuda.current_stream(t.device).cuda_stream
 
 
@@ -136,6 +142,8 @@ def _same_layout(a, b):
 
 
 def _is_dense(x):
+    if x.is_contiguous():
+        return True
     dims = sorted((d for d in range(x.ndim) if x.shape[d] != 1), key=lambda d: x.stride(d))
     expect = 1
     for d in dims:

@@ -36,6 +36,8 @@ def dense_like(t, like):
 
 def is_dense(x):
     """True when x occupies numel() consecutive elements in SOME dimension order (no gaps, no overlap)."""
+    if x.is_contiguous():
+        return True
     dims = sorted((d for d in range(x.ndim) if x.shape[d] != 1), key=lambda d: x.stride(d))
     expect = 1
     for d in dims:
