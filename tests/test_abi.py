@@ -43,6 +43,21 @@ def test_argument_errors_are_reported_without_a_gpu():
     assert rc == 1
 
 
+def test_host_only_queries_answer_without_a_gpu():
+    lib = custom_ops.load_library()
+    # size of the opaque relu / lrelu code buffer: one 4-byte (fp32) or 8-byte (fp16) word per thread and 1024-pack tile
+    assert lib.lvg_bias_act_codes_bytes(0, 4 * 1024 * 7) == 7 * 256 * 4
+    assert lib.lvg_bias_act_codes_bytes(0, 4 * 1024 * 7 + 4) == 8 * 256 * 4
+    assert lib.lvg_bias_act_codes_bytes(1, 8 * 1024 * 3) == 3 * 256 * 8
+    assert lib.lvg_bias_act_codes_bytes(2, 100) == -1                      # fp64 has no code path
+    for n in (4, 1000, 1 << 20, (1 << 31) + 4096):
+        assert lib.lvg_bias_act_codes_bytes(0, n) * 4 >= n                 # at least 2 bits per element
+    # envelope of the tensor-core convolution: fp16 (dtype code 1), stride 1, 3x3 / 1x1
+    assert lib.lvg_conv2d_fprop_workspace(1, 1, 4, 32, 64, 20, 20, 3, 3, 1, 1, 1) > 0
+    assert lib.lvg_conv2d_fprop_workspace(0, 1, 4, 32, 64, 20, 20, 3, 3, 1, 1, 1) == -1
+    assert lib.lvg_conv2d_fprop_workspace(1, 1, 4, 32, 64, 20, 20, 3, 3, 2, 1, 1) == -1
+
+
 def test_plugins_reject_cpu_tensors():
     import torch
     p = custom_ops.get_plugin('bias_act_plugin')
