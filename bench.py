@@ -79,10 +79,13 @@ def run_backward(y, leaves, dy):
 
 
 class Replay:
-    def __init__(self, calls, batch, device, dtype_policy):
-        from torch_utils.ops import bias_act, upfirdn2d, filtered_lrelu, conv2d_resample, conv2d_gradfix
-        self.ops = dict(bias_act=bias_act, upfirdn2d=upfirdn2d, filtered_lrelu=filtered_lrelu, conv2d_resample=conv2d_resample,
-                        conv2d=conv2d_gradfix)
+    def __init__(self, calls, batch, device, dtype_policy, ops=None):
+        if ops is None:
+            from torch_utils.ops import bias_act, upfirdn2d, filtered_lrelu, conv2d_resample, conv2d_gradfix
+            ops = dict(bias_act=bias_act, upfirdn2d=upfirdn2d, filtered_lrelu=filtered_lrelu, conv2d_resample=conv2d_resample,
+                       conv2d=conv2d_gradfix)
+        self.ops = ops
+        self.last_y = None
         self.device = device
         self.pool = {}
         self.items = []
@@ -150,7 +153,7 @@ class Replay:
     def forward_only(self):
         with torch.no_grad():
             for it in self.items:
-                self._fwd(it, it['x'])
+                self.last_y = self._fwd(it, it['x'])
 
     def forward_backward(self, timer=None, lo=0, hi=None):
         for it in self.items[lo:hi]:
@@ -178,6 +181,7 @@ class Replay:
                 y = self._fwd(it, x)
                 if y.requires_grad:
                     run_backward(y, leaves, it['dy'])
+            self.last_y = y.detach()
             it['b'] = saved_b
             if saved_w is not None:
                 it['w'] = saved_w
@@ -261,13 +265,95 @@ def measured_peak():
 
 
 # ---------------------------------------------------------------------------------------------
-# CPU arm: the oracle (port of the reference's _ref path) on a bounded sample of the same trace
+# CPU arms (reported-only baselines, host cores of the box)
 
-def cpu_sample(workload, budget_s=20.0):
-    """The CPU oracle on a bounded sample of the same trace: repeated forward passes of every hot-path
-    op call of one G+D pass at batch 1 (fresh synthetic inputs of the recorded shapes) until the time
-    budget is used. Returns (frames/s equivalent for a whole training step, description, threads)."""
+def _host_threads():
+    """All host cores, whatever OMP_NUM_THREADS says (torchrun exports OMP_NUM_THREADS=1 to every rank)."""
+    n = os.cpu_count() or 1
+    torch.set_num_threads(n)
+    return n
+
+
+def cpu_sample_reference(workload, budget_s=20.0):
+    """The REFERENCE'S OWN pure-PyTorch `_ref` op path (bias_act.py:91-120, upfirdn2d.py:167-211, filtered_lrelu.py:121-153,
+    conv2d_resample.py over F.conv2d; staged unmodified at oracle/_ref/src) on CPU tensors, all host cores: forward AND
+    backward (autograd) of the hot-path op calls of one G+D pass at batch 1, in trace order, until the time budget is
+    used; the covered share of the pass's algorithmic bytes extrapolates to the whole pass. One training step = G ops
+    2x forward + 1x backward, D ops 3x (forward + backward). -> (frames/s, description, threads, kind) or None."""
+    from oracle import ref_cuda
+    if not ref_cuda.available():
+        return None
+    threads = _host_threads()
+    ref = ref_cuda.load()
+    ops = dict(bias_act=ref.bias_act, upfirdn2d=ref.upfirdn2d, filtered_lrelu=ref.filtered_lrelu,
+               conv2d_resample=ref.conv2d_resample, conv2d=ref.conv2d_gradfix)
+    g_calls, d_calls, batch, frames = load_trace(workload)
+    # groups = (network, op): sampled calls of a group extrapolate to the group's bytes (cost per byte differs by op);
+    # calls are visited largest first within a fixed round-robin over the groups: a short budget samples every group and
+    # measures the calls that carry most of the time directly
+    groups = {}
+    for net, calls in (('G', g_calls), ('D', d_calls)):
+        for c in calls:
+            groups.setdefault((net, c['op']), []).append(c)
+    for k in groups:
+        groups[k].sort(key=lambda c: -int(np.prod(c['x'])))
+    stat = {k: dict(tf=0.0, tb=0.0, done=0, total=sum(int(np.prod(c['x'])) for c in v)) for k, v in groups.items()}
+    order, depth = [], 0
+    while True:
+        row = [(k, v[depth]) for k, v in groups.items() if depth < len(v)]
+        if not row:
+            break
+        order += row
+        depth += 1
+    n_done = 0
+    t_start = time.perf_counter()
+    for key, c in order:
+        if time.perf_counter() - t_start > budget_s:
+            break
+        rp = Replay([c], 1, torch.device('cpu'), 'fp32', ops=ops)     # fp32 on CPU, as the reference's CPU path runs
+        it = rp.items[0]
+        x = it['x'].detach().requires_grad_(True)
+        leaves = [x]
+        if it.get('b') is not None:
+            it['b'] = it['b'].detach().requires_grad_(True)
+            leaves.append(it['b'])
+        if it.get('w') is not None:
+            it['w'] = it['w'].detach().requires_grad_(True)
+            leaves.append(it['w'])
+        t0 = time.perf_counter()
+        y = rp._fwd(it, x)
+        t1 = time.perf_counter()
+        if y.requires_grad:
+            torch.autograd.grad(y, leaves, it['dy'], allow_unused=True)
+        t2 = time.perf_counter()
+        st = stat[key]
+        st['tf'] += t1 - t0
+        st['tb'] += t2 - t1
+        st['done'] += int(np.prod(c['x']))
+        n_done += 1
+    if any(st['done'] == 0 for st in stat.values()):
+        return None
+    est = 0.0
+    for (net, _), st in stat.items():
+        mult_f, mult_b = (2.0, 1.0) if net == 'G' else (3.0, 3.0)
+        est += (mult_f * st['tf'] + mult_b * st['tb']) * st['total'] / st['done']
+    done_bytes = {'all': sum(st['done'] for st in stat.values())}
+    all_bytes = {'all': sum(st['total'] for st in stat.values())}
+    fps = frames / est
+    used = time.perf_counter() - t_start
+    desc = (f"reference's own _ref ops (oracle/_ref/src, torch {torch.__version__} CPU, {threads} threads): forward+backward of {n_done} of "
+            f"{len(order)} hot-path op calls of one G+D pass at batch 1 (of {batch}), {used:.1f} s, covering "
+            f"{100.0 * sum(done_bytes.values()) / max(1, sum(all_bytes.values())):.0f} % of the pass's elements (rest extrapolated per (network, op) group by elements); "
+            f"step = G 2 fwd + 1 bwd, D 3 fwd + 3 bwd")
+    return fps, desc, threads, 'reference'
+
+
+def cpu_sample_port(workload, budget_s=20.0):
+    """The CPU oracle (oracle/lvg_oracle.c, a float64 restatement) on a bounded sample of the same trace: repeated forward
+    passes of every hot-path op call of one G+D pass at batch 1 until the time budget is used."""
     from oracle import oracle as orc
+    threads = _host_threads()
+    orc.set_num_threads(threads)
     g_calls, d_calls, batch, frames = load_trace(workload)
     gen = torch.Generator().manual_seed(0)
     rng = np.random.default_rng(0)
@@ -305,88 +391,114 @@ def cpu_sample(workload, budget_s=20.0):
     step_s_batch1 = (t_used / passes) * 4.5
     fps = frames / step_s_batch1
     desc = (f'{passes} forward passes of all {len(prepared)} hot-path op calls of one G+D pass at batch 1 (of {batch}) through the '
-            f'CPU oracle, {t_used:.1f} s; x4.5 forward-equivalents per training step')
-    return fps, desc, orc.num_threads()
+            f'CPU oracle (float64, {orc.num_threads()} OpenMP threads), {t_used:.1f} s; x4.5 forward-equivalents per training step')
+    return fps, desc, orc.num_threads(), 'port'
+
+
+def cpu_sample(workload, budget_s=20.0):
+    """(frames/s, description, threads, kind): the reference's own CPU path when oracle/_ref is staged, else the port."""
+    r = None
+    try:
+        r = cpu_sample_reference(workload, budget_s)
+    except Exception as e:       # a broken stage must not take the bench down; say so
+        sys.stderr.write(f'bench: reference _ref CPU arm unavailable ({type(e).__name__}: {e}); using the oracle port\n')
+    return r if r is not None else cpu_sample_port(workload, budget_s)
+
+
+# ---------------------------------------------------------------------------------------------
+# multi-GPU: real Parameters + real autograd backward feeding lvg_dist.FlatGradSync(overlap=True)
+
+class _InjectGrad(torch.autograd.Function):
+    """Scalar node whose backward hands `g` to the parameter: what a weight-gradient kernel's output is to autograd."""
+
+    @staticmethod
+    def forward(ctx, p, g):
+        ctx.save_for_backward(g)
+        return p.new_zeros(())
+
+    @staticmethod
+    def backward(ctx, go):
+        g, = ctx.saved_tensors
+        return g, None
+
+
+class GradExchange:
+    """The gradient side of a network for the data-parallel step: `n_elems` fp32 parameters in tensors of the sizes a
+    conv stack has, registered with FlatGradSync(overlap=True): each backward_bucket(k) runs a REAL autograd backward
+    over the parameters of bucket k (AccumulateGrad -> post-accumulate hooks -> the bucket's asynchronous NCCL
+    all-reduce starts while the remaining segments of the pass execute), finish() = FlatGradSync.sync()."""
+
+    def __init__(self, n_elems, device, buckets):
+        from lvg_dist.grad_sync import FlatGradSync
+        n_tensors = 96
+        sizes = [n_elems // n_tensors] * n_tensors
+        sizes[-1] += n_elems - sum(sizes)
+        self.module = torch.nn.Module()
+        self.module.ps = torch.nn.ParameterList([torch.nn.Parameter(torch.zeros(sz, device=device)) for sz in sizes])
+        self.sync = FlatGradSync(self.module, overlap=True, buckets=buckets, backwards_per_sync=1)
+        self.grads = [torch.randn(sz, device=device) * 1e-3 for sz in sizes]
+        self.members = [[] for _ in range(len(self.sync._slices))]
+        for i, b in self.sync._bucket_of.items():
+            self.members[b].append(i)
+
+    def backward_bucket(self, k):
+        ps = self.sync.params
+        outs = [_InjectGrad.apply(ps[i], self.grads[i]) for i in self.members[k]]
+        torch.autograd.backward(outs)
+
+    def finish(self, gain):
+        self.sync.sync(gain=gain)
+
+    def begin(self):
+        self.sync.zero_grad()
 
 
 # ---------------------------------------------------------------------------------------------
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=10)
-    ap.add_argument('--warmup', type=int, default=3)
-    ap.add_argument('--workload', default='lres', choices=sorted(WORKLOADS))
-    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--cpu-budget', type=float, default=20.0)
-    ap.add_argument('--no-cpu', action='store_true')
-    ap.add_argument('--launch', default='graph', choices=['graph', 'eager'],
-                    help='graph: the step is captured once into CUDA graphs and replayed (default); eager: every call launched from Python')
-    args = ap.parse_args()
-
-    rank = int(os.environ.get('RANK', 0))
-    world = int(os.environ.get('WORLD_SIZE', 1))
-    local_rank = int(os.environ.get('LOCAL_RANK', 0))
-    g_calls, d_calls, batch, frames = load_trace(args.workload)
-    metric = 'frames/sec (G+D train step, hot-path operator trace)'
-    config = {'workload': f'{args.workload}: train_{args.workload} op trace (torch_utils.ops calls of G+D update), per-GPU batch {batch}, '
-                          f'{frames} frames/sample, {"64x36" if args.workload == "lres" else "256x144 from 64x36"}',
-              'global_batch': batch * world, 'parallelism': f'dp{world}',
-              'l2': 'inputs and outputs of the replayed calls exceed L2 (largest tensors 0.75 GB); buffers shared per shape',
-              'launch': ('cuda_graph (step captured once, replayed' + ('; bucketed NCCL all-reduces between the graph segments, overlapping the rest of the backward pass)' if world > 1 else ')')) if args.launch == 'graph'
-                        else 'eager (every call launched from Python)'}
-
-    if args.impl == 'reference':
-        if rank != 0:
-            return
-        steps = max(1, args.steps)
-        vals = []
-        for _ in range(max(0, min(args.warmup, 1))):
-            cpu_sample(args.workload, budget_s=min(args.cpu_budget, 5.0))
-        for _ in range(steps):
-            fps, desc, threads = cpu_sample(args.workload, budget_s=args.cpu_budget)
-            vals.append(fps)
-        v = float(np.mean(vals))
-        print(json.dumps({'impl': 'reference', 'metric': metric, 'value': v, 'unit': 'frames/s', 'n_gpus': args.gpus, 'steps': steps,
-                          'warmup': args.warmup, 'ms_per_step': 1000.0 * frames / v, 'higher_is_better': True, 'scaling': 'weak',
-                          'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': config,
-                          'cpu_baseline': {'value': v, 'unit': 'frames/s', 'cores': threads, 'kind': 'port', 'sample': desc},
-                          'e2e': {'value': v, 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}))
-        return
-
-    assert torch.cuda.is_available(), 'bench.py needs a CUDA device (the ops have no CPU fallback for the product path)'
-    torch.cuda.set_device(local_rank)
-    device = torch.device('cuda', local_rank)
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group('nccl', device_id=device)
+def run_ours(args, workload, steps, rank, world, local_rank, device, with_cpu, with_refcuda):
+    """One workload through this repository's ops on the GPU -> the JSON fields of its line."""
+    import torch.distributed as dist
     from torch_utils import custom_ops
-    from lvg_dist.grad_sync import postprocess_
-    custom_ops.load_library()
-
-    policy = 'mixed' if args.workload == 'sres' else 'fp32'
+    g_calls, d_calls, batch, frames = load_trace(workload)
+    policy = 'mixed' if workload == 'sres' else 'fp32'
     G = Replay(g_calls, batch, device, policy)
     D = Replay(d_calls, batch, device, policy)
-    flat_g = flat_d = None
+    kBuckets = 4
+    ex_g = ex_d = None
     if world > 1:
-        ng, nd = GRAD_ELEMS[args.workload]
-        flat_g = torch.randn(ng, device=device) * 1e-3
-        flat_d = torch.randn(nd, device=device) * 1e-3
+        ng, nd = GRAD_ELEMS[workload]
+        ex_g, ex_d = GradExchange(ng, device, kBuckets), GradExchange(nd, device, kBuckets)
 
-    # e2e buffers: the real-video batch of the step comes from pinned host memory; the result goes back
-    vid_shape = (batch, 3, frames, 36, 64) if args.workload == 'lres' else (batch, 3, frames, 144, 256)
-    host_video = torch.empty(vid_shape, dtype=torch.float32).uniform_(-1, 1).pin_memory()
-    dev_video = torch.empty(vid_shape, dtype=torch.float32, device=device)
+    # e2e: the step's real-video batch comes from pinned host memory and ENTERS the replay: lres -- the discriminator's
+    # first layer (pad to 64x64, 1x1x1 conv 3->32, discriminator_lres.py:135-213; a library conv, row N1) is computed from
+    # the copied video into the input buffer of the first replayed D op; sres -- the copied low-res clip IS the input of
+    # the first replayed D op (upfirdn2d of (N, 3T, 36, 64), discriminator_sres.py:512). The value read back is the first
+    # element of the last D op's output of that step (a computed result).
+    entry = D.items[0]
+    if workload == 'lres':
+        host_video = torch.empty((batch, 3, frames, 36, 64), dtype=torch.float32).uniform_(-1, 1).pin_memory()
+        dev_video = torch.empty_like(host_video, device=device)
+        w_in = torch.randn(entry['x'].shape[1], 3, 1, 1, 1, device=device) / 3 ** 0.5
+        assert tuple(entry['x'].shape) == (batch, w_in.shape[0], frames, 64, 64), entry['x'].shape
+
+        def ingest():
+            dev_video.copy_(host_video, non_blocking=True)
+            v = torch.nn.functional.pad(dev_video, (0, 0, 14, 14))
+            entry['x'].copy_(torch.nn.functional.conv3d(v, w_in))
+    else:
+        host_video = torch.empty(tuple(entry['x'].shape), dtype=torch.float32).uniform_(-1, 1).pin_memory()
+        stage = torch.empty_like(host_video, device=device)
+
+        def ingest():
+            stage.copy_(host_video, non_blocking=True)
+            entry['x'].copy_(stage)          # fp32 -> the layer's dtype
     host_out = torch.empty(1, dtype=torch.float32).pin_memory()
 
     # One step = update_G (G fwd+bwd, D fwd+bwd) then update_D (G fwd, D fwd+bwd on fakes, D fwd+bwd on reals).
     # Each half is a list of SEGMENTS. With one GPU a half is one segment. With several GPUs the network whose
-    # gradients the half exchanges goes last and its second half is cut into kBuckets segments: after each of them the
-    # all-reduce of the corresponding bucket of the flat gradient buffer starts asynchronously (NCCL's own stream) and
-    # overlaps the remaining segments -- the schedule of lvg_dist.FlatGradSync(overlap=True), whose hooks release a
-    # bucket as soon as backward has produced its gradients; only the last bucket's exchange is exposed.
-    kBuckets = 4
-
+    # gradients the half exchanges goes last and its second half is cut into kBuckets segments: after segment k a real
+    # autograd backward over the parameters of bucket k runs, whose FlatGradSync hooks start that bucket's all-reduce
+    # asynchronously (NCCL's own stream), overlapping the remaining segments; only the last bucket's exchange is exposed.
     def tail_cuts(n):
         half = n // 2
         return [half + (n - half) * k // kBuckets for k in range(kBuckets + 1)]
@@ -401,35 +513,30 @@ def main():
         segs_b = [lambda timer=None: (G.forward_only(), D.forward_backward(timer), D.forward_backward(timer, 0, cb[0]))]
         segs_b += [(lambda timer=None, k=k: D.forward_backward(timer, cb[k], cb[k + 1])) for k in range(kBuckets)]
 
-    def bucket(flat, k):                     # bucket k of kBuckets (k = 0 leaves first)
-        n = flat.numel()
-        return flat[n * k // kBuckets: n * (k + 1) // kBuckets]
-
     graphs = {}
 
-    def run_half(name, segs, flat, timer, eager, prefill):
+    def run_half(name, segs, ex, timer, eager, prefill):
         if prefill:                          # see the roofline pass below
             torch.cuda._sleep(prefill)
-        works = []
+        if ex is not None:
+            ex.begin()
         for i, seg in enumerate(segs):
             if graphs and not eager:
                 graphs[name][i].replay()
             else:
                 seg(timer)
-            if world > 1 and i >= 1:
-                works.append(dist.all_reduce(bucket(flat, i - 1), async_op=True))
-        if world > 1:
-            for w in works:
-                w.wait()
-            postprocess_(flat, 1.0 / world)
+            if ex is not None and i >= 1:
+                ex.backward_bucket(i - 1)
+        if ex is not None:
+            ex.finish(gain=1.0)
 
     def step(timer=None, e2e=False, eager=False, prefill=False):
         if e2e:
-            dev_video.copy_(host_video, non_blocking=True)
-        run_half('a', segs_a, flat_g, timer, eager, prefill)
-        run_half('b', segs_b, flat_d, timer, eager, prefill)
+            ingest()
+        run_half('a', segs_a, ex_g, timer, eager, prefill)
+        run_half('b', segs_b, ex_d, timer, eager, prefill)
         if e2e:
-            host_out.copy_(dev_video.view(-1)[:1], non_blocking=True)
+            host_out.copy_(D.last_y.reshape(-1)[:1].float(), non_blocking=True)
 
     def barrier():
         if world > 1:
@@ -449,18 +556,14 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
-    # warm-up: at least W (>= 3) steps AND at least 2 s, so that a cold box (first CUDA process after boot: page
-    # cache, allocator growth, clock ramp) does not leak into the timed region
-    warm_steps, t_warm = 0, time.perf_counter()
-    # (with several ranks the count must be identical everywhere -- the step contains collectives -- so it is fixed)
-    while (warm_steps < max(3, args.warmup) + (8 if world > 1 else 0)) or (world == 1 and time.perf_counter() - t_warm < 2.0):
+    warm = max(3, args.warmup)               # W >= 3 untimed steps, exactly as asked
+    for _ in range(warm):
         step()
-        torch.cuda.synchronize()
-        warm_steps += 1
-    dominant_op = 'bias_act' if args.workload == 'lres' else 'filtered_lrelu'
+    torch.cuda.synchronize()
+    dominant_op = 'bias_act' if workload == 'lres' else 'filtered_lrelu'
     launches_per_step = None
     if args.launch == 'graph':
-        # Capture the two halves of the step (the gradient all-reduces stay outside: eager NCCL calls between the replays).
+        # Capture the two halves of the step (the gradient exchange stays outside: eager autograd + NCCL between the replays).
         # Launch counting happens while capturing: exactly one step's kernels.
         pool = None
         side = torch.cuda.Stream()
@@ -479,24 +582,23 @@ def main():
             graphs.update(captured)
         torch.cuda.current_stream().wait_stream(side)
         launches_per_step = custom_ops.launch_count() - launches0
-        for _ in range(3):
-            step()
+        step()                               # first replay (untimed)
         torch.cuda.synchronize()
     else:
         step(KernelTimer(dominant_op))       # untimed: same code path as the timed region (event pairs included)
     launches0 = custom_ops.launch_count()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     timer = KernelTimer(dominant_op)
-    ms_total = timed(args.steps, e2e=False, timer=None if graphs else timer)
-    launches = launches_per_step * args.steps if graphs else custom_ops.launch_count() - launches0
+    ms_total = timed(steps, e2e=False, timer=None if graphs else timer)
+    launches = launches_per_step * steps if graphs else custom_ops.launch_count() - launches0
     step(e2e=True)                           # untimed warm-up of the host-copy flavour
-    ms_e2e = timed(args.steps, e2e=True)
-    ms_e2e_eager = timed(args.steps, e2e=True, eager=True) if graphs else ms_e2e
+    ms_e2e = timed(steps, e2e=True)
+    ms_e2e_eager = timed(steps, e2e=True, eager=True) if graphs else ms_e2e
     clocks = sampler.finish() if sampler is not None else None
     if graphs:
         # Per-kernel timing for the roofline: graph nodes cannot carry timing events, so one extra EAGER step is timed
-        # with an event pair around every bias_act call. The stream is pre-filled with a ~30 ms spin kernel before
-        # each half so that the host runs ahead and the pairs bracket kernel execution, not Python launch latency.
+        # with an event pair around every call of the dominant op. The stream is pre-filled with a ~30 ms spin kernel
+        # before each half so that the host runs ahead and the pairs bracket kernel execution, not Python launch latency.
         spin = int(0.03 * 1.9e9)
         step(KernelTimer(dominant_op), eager=True, prefill=spin)
         torch.cuda.synchronize()
@@ -504,48 +606,164 @@ def main():
         torch.cuda.synchronize()
 
     frames_per_step = batch * frames * world
-    value = frames_per_step * args.steps / (ms_total / 1000.0)
-    e2e_value = frames_per_step * args.steps / (ms_e2e / 1000.0)
+    value = frames_per_step * steps / (ms_total / 1000.0)
+    e2e_value = frames_per_step * steps / (ms_e2e / 1000.0)
     k_ms, k_bytes, k_n = timer.summary()
     peak, peak_src = measured_peak()
     achieved = k_bytes / (k_ms / 1000.0) / 1e9 if k_ms > 0 else 0.0
     if graphs:
-        k_share = k_ms / (ms_total / args.steps) if ms_total else None
-        k_how = ('CUDA events around every bias_act call of one extra eager step (stream pre-filled by a spin kernel so that the '
+        k_share = k_ms / (ms_total / steps) if ms_total else None
+        k_how = (f'CUDA events around every {dominant_op} call of one extra eager step (stream pre-filled by a spin kernel so that the '
                  'pairs bracket execution, not launch latency); the timed region itself replays CUDA graphs')
     else:
         k_share = k_ms / ms_total if ms_total else None
-        k_how = 'CUDA events around every bias_act call inside the timed region'
+        k_how = f'CUDA events around every {dominant_op} call inside the timed region'
 
     traffic, traffic_note = None, None
-    try:        # DRAM bytes of the dominant kernel from the committed ncu --set full capture (bench.py never runs under ncu)
-        tr = json.load(open(os.path.join(ROOT, 'profiles', 'r01_traffic.json')))
-        f, b = tr['bias_act_fwd'], tr['bias_act_bwd_fused_db']
-        traffic = (f['dram_read'] + f['dram_write'] + b['dram_read'] + b['dram_write']) / 2.0
-        traffic_note = (f"mean DRAM bytes per launch (one forward + one fused backward launch) at {tr['shape']}; algorithmic "
-                        f"{(f['algorithmic'] + b['algorithmic']) / 2.0:.0f} B; {tr['source']}")
-    except Exception:
-        pass
-    if rank == 0 and args.workload != 'lres':
-        traffic, traffic_note = None, None
+    if workload == 'lres':
+        try:    # DRAM bytes of the dominant kernel from the committed ncu --set full capture (bench.py never runs under ncu)
+            tr = json.load(open(os.path.join(ROOT, 'profiles', 'r01_traffic.json')))
+            f, b = tr['bias_act_fwd'], tr['bias_act_bwd_fused_db']
+            traffic = (f['dram_read'] + f['dram_write'] + b['dram_read'] + b['dram_write']) / 2.0
+            traffic_note = (f"mean DRAM bytes per launch (one forward + one fused backward launch) at {tr['shape']}; algorithmic "
+                            f"{(f['algorithmic'] + b['algorithmic']) / 2.0:.0f} B; {tr['source']}")
+        except Exception:
+            pass
+    res = config = None
     if rank == 0:
-        out = {'metric': metric, 'value': value, 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps, 'warmup': warm_steps + 1,
-               'ms_per_step': ms_total / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-               'dtype': 'f32' if policy == 'fp32' else 'f16/f32 mixed (fp16 layers as the reference config)', 'data': 'synthetic',
+        config = {'workload': f'{workload}: train_{workload} op trace (torch_utils.ops calls of G+D update), per-GPU batch {batch}, '
+                              f'{frames} frames/sample, {"64x36" if workload == "lres" else "256x144 from 64x36"}',
+                  'global_batch': batch * world, 'parallelism': f'dp{world}',
+                  'l2': 'inputs and outputs of the replayed calls exceed L2 (largest tensors 0.75 GB); buffers shared per shape',
+                  'launch': ('cuda_graph (step captured once, replayed' + ('; between the graph segments: real autograd backward over real Parameters -> lvg_dist.FlatGradSync(overlap=True) hooks -> bucketed NCCL all-reduces overlapping the rest of the pass)' if world > 1 else ')')) if args.launch == 'graph'
+                            else 'eager (every call launched from Python)'}
+        res = {'value': value, 'unit': 'frames/s', 'n_gpus': world, 'steps': steps, 'warmup': warm,
+               'ms_per_step': ms_total / steps,
+               'dtype': 'f32' if policy == 'fp32' else 'f16/f32 mixed (fp16 layers as the reference config)',
                'config': config, 'gpu_launches': int(launches),
                'e2e': {'value': e2e_value, 'unit': 'frames/s', 'h2d_bytes_per_step': host_video.numel() * 4, 'd2h_bytes_per_step': 4,
-                       'eager_value': frames_per_step * args.steps / (ms_e2e_eager / 1000.0)},
+                       'eager_value': frames_per_step * steps / (ms_e2e_eager / 1000.0),
+                       'path': 'pinned host video -> device -> first replayed discriminator op; first element of the last discriminator output -> host'},
                'roofline': {'bound': 'hbm', 'kernel': 'bias_act (vector kernel: forward writing 2-bit sign/clamp codes + backward from the codes with fused dx/db)' if dominant_op == 'bias_act' else
                             'filtered_lrelu (fused up-FIR / lrelu / down-FIR; FP32-issue-bound, its HBM figure is shown for reference)',
                             'achieved': achieved,
                             'peak': peak, 'peak_source': peak_src, 'unit': 'GB/s', 'frac': achieved / peak if peak else None,
                             'launches_timed': k_n, 'share_of_step': k_share, 'traffic': traffic, 'traffic_note': traffic_note, 'timing': k_how},
                'clocks': clocks}
-        if not args.no_cpu:
-            fps, desc, threads = cpu_sample(args.workload, budget_s=args.cpu_budget)
-            out['cpu_baseline'] = {'value': fps, 'unit': 'frames/s', 'cores': threads, 'kind': 'port', 'sample': desc}
+    # the same trace through the REFERENCE'S OWN CUDA ops on this GPU (oracle/_ref: its plugins built unmodified for sm_100a,
+    # its Python wrappers, cuDNN for its convolutions) -- eager on both sides, N = 1 only: the "beat-this" baseline
+    if rank == 0 and world == 1 and with_refcuda:
+        try:
+            from oracle import ref_cuda
+            if ref_cuda.available():
+                del G, D
+                graphs.clear()
+                torch.cuda.empty_cache()
+                ref = ref_cuda.load()
+                rops = dict(bias_act=ref.bias_act, upfirdn2d=ref.upfirdn2d, filtered_lrelu=ref.filtered_lrelu,
+                            conv2d_resample=ref.conv2d_resample, conv2d=ref.conv2d_gradfix)
+                RG, RD = Replay(g_calls, batch, device, policy, ops=rops), Replay(d_calls, batch, device, policy, ops=rops)
+
+                def rstep():
+                    RG.forward_backward(); RD.forward_backward()
+                    RG.forward_only(); RD.forward_backward(); RD.forward_backward()
+                nref = max(2, min(steps, 5))
+                for _ in range(2):
+                    rstep()
+                torch.cuda.synchronize()
+                t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                t0.record()
+                for _ in range(nref):
+                    rstep()
+                t1.record()
+                torch.cuda.synchronize()
+                rms = t0.elapsed_time(t1) / nref
+                res['ref_cuda'] = {'value': batch * frames / (rms / 1000.0), 'unit': 'frames/s', 'ms_per_step': rms, 'steps': nref,
+                                   'launch': 'eager', 'ours_eager_ms_per_step': ms_e2e_eager / steps,
+                                   'what': "the same op trace through the reference's own CUDA plugins (built unmodified for sm_100a, "
+                                           "oracle/_ref) and Python wrappers on this GPU; compare with ours_eager_ms_per_step (eager, incl. the e2e copies)"}
+                del RG, RD
+                torch.cuda.empty_cache()
+        except Exception as e:
+            res['ref_cuda'] = {'unavailable': f'{type(e).__name__}: {e}'}
+    if rank == 0 and with_cpu:
+        fps, desc, threads, kind = cpu_sample(workload, budget_s=args.cpu_budget)
+        res['cpu_baseline'] = {'value': fps, 'unit': 'frames/s', 'cores': threads, 'kind': kind, 'sample': desc}
+    return res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--workload', default='both', choices=sorted(WORKLOADS) + ['both'],
+                    help="both (default): the line's value is the lres step (BASELINE configs[1]); the sres step (configs[2]) is measured in the same run and reported under the key sres")
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--cpu-budget', type=float, default=12.0)
+    ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--no-ref-cuda', action='store_true')
+    ap.add_argument('--launch', default='graph', choices=['graph', 'eager'],
+                    help='graph: the step is captured once into CUDA graphs and replayed (default); eager: every call launched from Python')
+    args = ap.parse_args()
+
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    local_rank = int(os.environ.get('LOCAL_RANK', 0))
+    primary = 'lres' if args.workload == 'both' else args.workload
+    metric = 'frames/sec (G+D train step, hot-path operator trace)'
+
+    if args.impl == 'reference':
+        # the reference's own CPU implementation of the path on the box's host cores (rank 0 only; all host threads)
+        if rank != 0:
+            return
+        _, _, batch, frames = load_trace(primary)
+        steps = max(1, args.steps)
+        for _ in range(max(0, min(args.warmup, 1))):
+            cpu_sample(primary, budget_s=min(args.cpu_budget, 4.0))
+        vals = []
+        for _ in range(steps):
+            fps, desc, threads, kind = cpu_sample(primary, budget_s=args.cpu_budget)
+            vals.append(fps)
+        v = float(np.mean(vals))
+        config = {'workload': f'{primary}: train_{primary} op trace (torch_utils.ops calls of G+D update), per-GPU batch {batch}, '
+                              f'{frames} frames/sample, {"64x36" if primary == "lres" else "256x144 from 64x36"}',
+                  'global_batch': batch, 'parallelism': 'cpu'}
+        print(json.dumps({'impl': 'reference', 'metric': metric, 'value': v, 'unit': 'frames/s', 'n_gpus': args.gpus, 'steps': steps,
+                          'warmup': args.warmup, 'ms_per_step': 1000.0 * frames / v, 'higher_is_better': True, 'scaling': 'weak',
+                          'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': config,
+                          'cpu_baseline': {'value': v, 'unit': 'frames/s', 'cores': threads, 'kind': kind, 'sample': desc},
+                          'e2e': {'value': v, 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}))
+        return
+
+    assert torch.cuda.is_available(), 'bench.py needs a CUDA device (the ops have no CPU fallback for the product path)'
+    torch.cuda.set_device(local_rank)
+    device = torch.device('cuda', local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=device)
+    from torch_utils import custom_ops
+    custom_ops.load_library()
+
+    res = run_ours(args, primary, args.steps, rank, world, local_rank, device, with_cpu=not args.no_cpu, with_refcuda=not args.no_ref_cuda)
+    sres = None
+    if args.workload == 'both':
+        torch.cuda.empty_cache()
+        sres = run_ours(args, 'sres', max(2, min(args.steps, 5)), rank, world, local_rank, device, with_cpu=False,
+                        with_refcuda=not args.no_ref_cuda)
+    if rank == 0:
+        out = {'metric': metric, 'value': res['value'], 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps, 'warmup': res['warmup'],
+               'ms_per_step': res['ms_per_step'], 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+               'dtype': res['dtype'], 'data': 'synthetic'}
+        for k in ('config', 'gpu_launches', 'e2e', 'roofline', 'clocks', 'ref_cuda', 'cpu_baseline'):
+            if k in res:
+                out[k] = res[k]
+        if sres is not None:
+            out['sres'] = {k: sres[k] for k in ('value', 'unit', 'steps', 'warmup', 'ms_per_step', 'dtype', 'config', 'gpu_launches', 'e2e',
+                                                'roofline', 'ref_cuda') if k in sres}
         print(json.dumps(out))
     if world > 1:
+        import torch.distributed as dist
         dist.destroy_process_group()
 
 

@@ -32,12 +32,29 @@ class FlatGradSync:
     >>> sync = FlatGradSync(G)            # once, after building the module
     >>> loss.backward()                   # grads land in sync.flat through the .grad views
     >>> sync.sync(gain=1.0)               # all-reduce mean, sanitise -- replaces utils.sync_grads(G)
+
+    The buffer spans ALL parameters of the module, whatever their ``requires_grad`` flag at construction: the
+    reference's loop calls ``sync_grads`` right after ``network.requires_grad_(False)`` (video_gan_lres.py:126-129,
+    171-174) and, like ``utils.sync_grads`` (utils.py:116-124), what takes part in an exchange is decided at sync time:
+    the parameters whose ``.grad`` is not None. A parameter without a gradient keeps ``.grad is None`` (so Adam skips
+    it, as with the reference); its slice of the buffer is exchanged as zeros, which keeps the collective's size
+    identical on every rank.
+
+    ``overlap=True``: see the module docstring. A bucket may only leave once EVERY backward pass of the current
+    update has written into it -- the reference runs several per sync (``fake_loss.backward()`` then
+    ``real_loss.backward()`` in ``update_D``, times ``*_grad_accum``; video_gan_lres.py:135-176). State the number
+    with ``backwards_per_sync`` (hooks then count that many gradient arrivals per parameter), or keep the default of
+    1 and wrap the LAST backward of an update in ``with sync.final_backward():`` -- outside that context the hooks of
+    a ``backwards_per_sync=None`` instance do nothing. A gradient that arrives for a bucket that has already left
+    raises (it would silently not be exchanged otherwise). Whatever has not left by ``sync()`` is exchanged there.
     """
 
-    def __init__(self, module, group=None, overlap=False, buckets=4):
-        self.params = [p for p in module.parameters() if p.requires_grad]
+    def __init__(self, module, group=None, overlap=False, buckets=4, backwards_per_sync=1):
+        self.params = list(module.parameters())
         self.group = group
         self.overlap = bool(overlap)
+        self.backwards_per_sync = backwards_per_sync
+        self._live = backwards_per_sync is not None
         self._pending, self._works, self._bucket_of, self._slices, self._hooks = [], [], {}, [], []
         if not self.params:
             self.flat = torch.zeros(0)
@@ -51,7 +68,10 @@ class FlatGradSync:
             if p.dtype != torch.float32:
                 raise RuntimeError('FlatGradSync expects fp32 master parameters (as the reference trains)')
             view = self.flat[ofs:ofs + p.numel()].view_as(p)
-            p.grad = view
+            if p.requires_grad or p.grad is not None:
+                if p.grad is not None:
+                    view.copy_(p.grad)
+                p.grad = view
             self._views.append(view)
             ofs += p.numel()
         if self.overlap:
@@ -62,7 +82,7 @@ class FlatGradSync:
         """Contiguous slices of the flat buffer of ~equal size; bucket 0 holds the LAST parameters (ready first)."""
         total = self.flat.numel()
         target = (total + n_buckets - 1) // n_buckets
-        bounds, ofs, start, count = [], 0, 0, 0          # (first param index, flat start)
+        ofs, start, count = 0, 0, 0
         groups, cur = [], []
         for i, p in enumerate(self.params):
             cur.append(i)
@@ -79,11 +99,30 @@ class FlatGradSync:
                 self._bucket_of[i] = b
         self._arm()
         for i, p in enumerate(self.params):
+            was = p.requires_grad                        # hooks can only be registered while the flag is set; they stay
+            p.requires_grad_(True)
             self._hooks.append(p.register_post_accumulate_grad_hook(self._make_hook(i)))
+            p.requires_grad_(was)
 
     def _arm(self):
-        self._pending = list(self._members)
+        k = self.backwards_per_sync or 1
+        self._pending = [m * k for m in self._members]
         self._works = [None] * len(self._members)
+
+    def final_backward(self):
+        """Context for the last backward pass of an update (``backwards_per_sync=None`` instances): buckets leave as
+        soon as that pass has written their last gradient."""
+        owner = self
+
+        class _Ctx:
+            def __enter__(self):
+                owner._pending = list(owner._members)
+                owner._live = True
+
+            def __exit__(self, *exc):
+                owner._live = False
+                return False
+        return _Ctx()
 
     def _make_hook(self, i):
         def hook(param):
@@ -92,6 +131,12 @@ class FlatGradSync:
             if param.grad is not None and param.grad.data_ptr() != view.data_ptr():
                 view.copy_(param.grad)                   # a replaced .grad: fold it back before the bucket leaves
                 param.grad = view
+            if self._works[b] is not None:
+                raise RuntimeError('FlatGradSync(overlap=True): a gradient arrived for a bucket whose all-reduce has already '
+                                   'started -- more backward passes per sync() than backwards_per_sync; pass the right count '
+                                   'or use final_backward()')
+            if not self._live:
+                return
             self._pending[b] -= 1
             if self._pending[b] == 0 and self._world() > 1:
                 a, e = self._slices[b]
@@ -106,23 +151,31 @@ class FlatGradSync:
         self.flat.zero_()
 
     def _reattach(self):
-        # optimizers / user code may have replaced p.grad: fold such gradients back into the flat buffer
+        # optimizers / user code may have replaced p.grad (``zero_grad(set_to_none=True)`` then backward, as the reference
+        # loop does): fold such gradients back into the flat buffer with ONE multi-tensor copy; parameters without a
+        # gradient stay without one (utils.py:117) and contribute zeros
+        src, dst = [], []
         for p, view in zip(self.params, self._views):
             if p.grad is None:
                 view.zero_()
-                p.grad = view
             elif p.grad.data_ptr() != view.data_ptr():
-                view.copy_(p.grad)
+                src.append(p.grad.reshape(view.shape).to(torch.float32))
+                dst.append(view)
                 p.grad = view
+        if src:
+            torch._foreach_copy_(dst, src)
 
-    def sync(self, gain=1.0):
-        """Average the gradients over the process group, scale by `gain`, sanitise NaN/Inf."""
+    def sync(self, gain=None):
+        """Average the gradients over the process group, scale by `gain` (None = 1, utils.py:120), sanitise NaN/Inf."""
         if self.flat.numel() == 0:
             return
         world = self._world()
         if self.overlap:
             # buckets whose hooks all fired are already in flight; anything else (parameters that received no gradient
-            # in this backward pass) is exchanged now
+            # in this update, or fewer backward passes than announced) is exchanged now
+            pending = [b for b in range(len(self._slices)) if self._works[b] is None]
+            if pending:
+                self._reattach()
             for b, (a, e) in enumerate(self._slices):
                 if self._works[b] is not None:
                     self._works[b].wait()
@@ -133,7 +186,9 @@ class FlatGradSync:
             self._reattach()
             if world > 1:
                 dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
-        postprocess_(self.flat, scale=float(gain) / world, limit=_GRAD_LIMIT)
+        if isinstance(gain, torch.Tensor):
+            gain = gain.item()
+        postprocess_(self.flat, scale=(1.0 if gain is None else float(gain)) / world, limit=_GRAD_LIMIT)
 
 
 def postprocess_(flat, scale, limit=_GRAD_LIMIT):
@@ -153,8 +208,10 @@ def postprocess_(flat, scale, limit=_GRAD_LIMIT):
     return flat
 
 
-def sync_grads(module, gain=1.0, _cache={}):
-    """Drop-in for ``utils.sync_grads(network, gain)`` (utils.py:116): keeps one FlatGradSync per module."""
+def sync_grads(module, gain=None, _cache={}):
+    """Drop-in for ``utils.sync_grads(network, gain=None)`` (utils.py:116): keeps one FlatGradSync per module. Works
+    with the reference loop as it is: ``requires_grad_(False)`` before the call, ``zero_grad(set_to_none=True)`` after
+    the optimiser step (the next backward's fresh ``.grad`` tensors are folded into the buffer by one multi-tensor copy)."""
     key = id(module)
     if key not in _cache:
         _cache[key] = FlatGradSync(module)

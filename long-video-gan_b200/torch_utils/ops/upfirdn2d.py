@@ -147,15 +147,49 @@ class _Config:
     def run(self, x, f):
         """Launch for a rank-2 (full) or rank-1 (separable) filter."""
         c = self
-        if f.ndim == 2:
-            return _plugin.upfirdn2d(x, f, c.upx, c.upy, c.downx, c.downy, c.px0, c.px1, c.py0, c.py1, c.flip, c.gain)
         sep = getattr(_plugin, 'upfirdn2d_sep', None)
+        if f.ndim == 2:
+            # `setup_filter([1,3,3,1])` (< 8 taps) hands the networks the OUTER PRODUCT as a full 4x4 filter
+            # (upfirdn2d.py:103-108; every conv2d_resample of the super-res discriminator): rank 1, so the two 1-D passes
+            # of the single-launch separable kernels apply
+            fac = _rank1_factors(f) if (sep is not None and min(f.shape) > 1) else None
+            if fac is not None:
+                y = sep(x, fac[0], fac[1], c.upx, c.upy, c.downx, c.downy, c.px0, c.px1, c.py0, c.py1, c.flip, c.gain)
+                if y is not None:
+                    return y
+            return _plugin.upfirdn2d(x, f, c.upx, c.upy, c.downx, c.downy, c.px0, c.px1, c.py0, c.py1, c.flip, c.gain)
         if sep is not None:
             y = sep(x, f, f, c.upx, c.upy, c.downx, c.downy, c.px0, c.px1, c.py0, c.py1, c.flip, c.gain)
             if y is not None:
                 return y
         y = _plugin.upfirdn2d(x, f.unsqueeze(0), c.upx, 1, c.downx, 1, c.px0, c.px1, 0, 0, c.flip, 1.0)
         return _plugin.upfirdn2d(y, f.unsqueeze(1), 1, c.upy, 1, c.downy, 0, 0, c.py0, c.py1, c.flip, c.gain)
+
+
+_rank1_cache = dict()     # (device, data_ptr, shape, stride, version) -> (storage kept alive, (fx, fy) or None)
+
+
+def _rank1_factors(f):
+    """(fx, fy) with f == outer(fy, fx) for a full 2-D filter of rank 1, else None. Decided ONCE per filter tensor on the
+    host (one small device->host copy; the entry keeps the filter's storage alive so its address cannot be recycled, an
+    in-place update changes `_version`), never during CUDA-graph capture."""
+    key = (f.device, f.data_ptr(), tuple(f.shape), tuple(f.stride()), f._version)
+    hit = _rank1_cache.get(key)
+    if hit is not None:
+        return hit[1]
+    if f.is_cuda and torch.cuda.is_current_stream_capturing():
+        return None
+    a = f.detach().to('cpu', torch.float64)
+    i, j = divmod(int(a.abs().argmax()), a.shape[1])
+    fac = None
+    if float(a[i, j]) != 0.0:
+        fy, fx = a[:, j].clone(), a[i, :] / a[i, j]
+        if float((torch.outer(fy, fx) - a).abs().max()) <= 1e-6 * float(a.abs().max()):
+            fac = (fx.to(torch.float32).to(f.device).contiguous(), fy.to(torch.float32).to(f.device).contiguous())
+    if len(_rank1_cache) >= 64:
+        _rank1_cache.pop(next(iter(_rank1_cache)))
+    _rank1_cache[key] = (f.untyped_storage(), fac)
+    return fac
 
 
 _upfirdn2d_cuda_cache = dict()

@@ -60,7 +60,7 @@ lr = (torch.rand(2, 3, 2 + 8, 36, 64, generator=torch.Generator().manual_seed(13
 hr = S(lr)
 out['sres_G'] = hr.detach().float().cpu()
 tgt = torch.randn(hr.shape, generator=torch.Generator().manual_seed(14)).to(dev)
-(hr.float() * tgt).mean().backward()
+(hr.float() * tgt).sum().backward()        # O(1) gradients: fp16 layers do not underflow (no loss scaling in the reference)
 out['sres_G_grad'] = grads(S).cpu()
 del S
 
@@ -70,7 +70,7 @@ SD = discriminator_sres.VideoDiscriminator(channels=3, seq_length=2, lr_height=3
 hrv = hr.detach().float().clamp(-1, 1).requires_grad_(True)
 logits = SD(lr[:, :, 4:-4], hrv)
 out['sres_D'] = logits.detach().float().cpu()
-torch.nn.functional.softplus(logits.float()).mean().backward()
+(torch.nn.functional.softplus(logits.float()).mean() * 4096.0).backward()   # scaled: the fp16 blocks' gradients stay normal numbers
 out['sres_D_grad'] = grads(SD).cpu()
 out['sres_D_gx'] = hrv.grad.cpu()
 torch.save(out, sys.argv[1])

@@ -136,3 +136,87 @@ def test_overlapped_buckets_give_the_same_gradients_world2():
             assert torch.allclose(a, b, rtol=1e-6, atol=1e-8)
     for a, b in zip(ret[0], ret[1]):
         assert torch.equal(a, b)                                # both ranks hold the same averaged gradients
+
+
+def _loop_worker(rank, world, port, ret):
+    """The reference's update loop shape (video_gan_lres.py:100-176): requires_grad_(True) -> two backward passes ->
+    requires_grad_(False) -> sync_grads(net, gain) -> opt.step() -> zero_grad(set_to_none=True)."""
+    sys.path.insert(0, os.path.join(ROOT, 'long-video-gan_b200'))
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        from lvg_dist import grad_sync
+        res = {}
+        for mode in ('reference', 'dropin', 'overlap2', 'final'):
+            torch.manual_seed(0)
+            net = torch.nn.Sequential(torch.nn.Linear(6, 16), torch.nn.Tanh(), torch.nn.Linear(16, 3))
+            net.register_parameter('unused', torch.nn.Parameter(torch.ones(5)))
+            net.requires_grad_(False)                       # as between updates in the reference loop
+            opt = torch.optim.Adam(net.parameters(), lr=1e-2)
+            sync = None
+            if mode == 'overlap2':
+                sync = grad_sync.FlatGradSync(net, overlap=True, buckets=2, backwards_per_sync=2)
+            elif mode == 'final':
+                sync = grad_sync.FlatGradSync(net, overlap=True, buckets=2, backwards_per_sync=None)
+            gen = torch.Generator().manual_seed(20 + rank)
+            for it in range(3):
+                net.requires_grad_(True)
+                xa, xb = torch.randn(8, 6, generator=gen), torch.randn(8, 6, generator=gen)
+                net(xa).square().mean().backward()
+                if mode == 'final':
+                    with sync.final_backward():
+                        net(xb).tanh().mean().backward()
+                else:
+                    net(xb).tanh().mean().backward()
+                net.requires_grad_(False)
+                gain = None if it == 0 else 0.5
+                if mode == 'reference':                     # utils.py:116-124 restated
+                    ps = [p for p in net.parameters() if p.grad is not None]
+                    flat = torch.cat([p.grad.flatten() for p in ps])
+                    dist.all_reduce(flat)
+                    flat = flat / world
+                    flat = flat if gain is None else flat * gain
+                    torch.nan_to_num(flat, nan=0, posinf=1e5, neginf=-1e5, out=flat)
+                    for p, g in zip(ps, flat.split([p.numel() for p in ps])):
+                        p.grad = g.reshape(p.shape)
+                elif mode == 'dropin':
+                    s = grad_sync.sync_grads(net, gain=gain)
+                    assert s.flat.numel() == sum(p.numel() for p in net.parameters())     # built although requires_grad was False
+                else:
+                    if it == 1:
+                        assert any(w is not None for w in sync._works)                 # buckets left during backward
+                    sync.sync(gain=gain)
+                assert net.unused.grad is None              # no gradient -> stays None (Adam skips it, as in the reference)
+                opt.step()
+                opt.zero_grad(set_to_none=True)
+            res[mode] = torch.cat([p.detach().flatten() for p in net.parameters()])
+        # a gradient arriving after its bucket left must raise, not be dropped
+        net = torch.nn.Linear(4, 4)
+        sync = grad_sync.FlatGradSync(net, overlap=True, buckets=1, backwards_per_sync=1)
+        net(torch.ones(2, 4)).sum().backward()
+        try:
+            net(torch.ones(2, 4)).sum().backward()
+            res['raised'] = False
+        except RuntimeError as e:
+            res['raised'] = 'backwards_per_sync' in str(e)
+        sync.sync()
+        ret[rank] = res
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sync_grads_in_the_reference_loop_shape_world2():
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    port = 33500 + (os.getpid() % 2000)
+    mp.spawn(_loop_worker, args=(world, port, ret), nprocs=world, join=True)
+    for r in range(world):
+        res = ret[r]
+        assert res['raised'] is True
+        for mode in ('dropin', 'overlap2', 'final'):
+            assert torch.allclose(res[mode], res['reference'], rtol=1e-5, atol=1e-7), mode
+        assert not torch.equal(res['reference'], torch.zeros_like(res['reference']))
+    for mode in ('reference', 'dropin', 'overlap2', 'final'):
+        assert torch.equal(ret[0][mode], ret[1][mode]), mode         # replicas stay identical

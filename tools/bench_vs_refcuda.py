@@ -94,7 +94,7 @@ def main():
 
     # ---- upfirdn2d
     lin = (torch.tensor(F4, device=DEV) / 8)[:, None]
-    f4 = upfirdn2d.setup_filter(F4).to(DEV)
+    f4 = upfirdn2d.setup_filter(F4, separable=True).to(DEV)      # the low-res networks pass the 1-D taps (generator_lres.py:171-174)
     f44 = upfirdn2d.setup_filter(F4, separable=False).to(DEV)
     ups = [
         ('U1 kaiser tdown (8,1024,640,1)', (8, 1024, 640, 1), kaiser(12, 2)[:, None], dict(down=[1, 2], padding=[0, 0, 5, 5]), torch.float32),
