@@ -217,6 +217,37 @@ int lvg_conv2d_wgrad(const void* x, const void* dy, void* dw, int dtype,
                      int kh, int kw, int stride, int pad_h, int pad_w, void* stream);
 
 /*
+ * Grouped 1-D / 2-D / 3-D convolution (cross-correlation) on tcgen05 tensor cores, TMA-fed (csrc/conv_igemm.cu): one
+ * engine for conv2d_gradfix.conv2d / conv_transpose2d (conv2d_gradfix.py:37-45), the F.conv3d calls of the low-res
+ * networks (generator_lres.py:119,578; discriminator_lres.py:172) and the F.conv1d calls of the low-res discriminator
+ * (discriminator_lres.py:108-127).
+ *   x [N][G*Cin][T][H][W]   w [G*Cout][Cin][kt][kh][kw]   y [N][G*Cout][To][Ho][Wo]      (dense; 2-D: T = kt = 1)
+ * stride 1, kh*kw <= 9, kt <= 7. dtype LVG_F16: fp16 operands, fp32 accumulation, fp16 result. dtype LVG_F32: operands
+ * split into bf16 hi + lo halves, hi*hi + lo*hi + hi*lo accumulated in fp32 (fp32-grade result, relative error
+ * ~2^-16; the reference runs these layers in strict fp32, train_lres.py:269). Optional fused epilogue on fprop:
+ * act 0 = none, 1 = (y + bias[co]) * gain clamped, 2 = lrelu(y + bias[co], alpha) * gain clamped (bias_act semantics,
+ * bias_act.py:52-86; clamp < 0 = none; bias indexed g*Cout + co, may be NULL).
+ * dgrad / wgrad: gradients with respect to x / w; their argument lists describe the FORWARD convolution.
+ * `workspace`: lvg_convnd_workspace (fprop, dgrad) or lvg_convnd_wgrad_workspace bytes, 16-byte aligned, holds the
+ * re-tiled operands (and the split-K partial sums of wgrad). Return LVG_UNSUPPORTED (-1 from the size queries) outside
+ * the envelope.
+ */
+int64_t lvg_convnd_workspace(int dtype, int n, int groups, int cin, int cout, int t, int h, int wd,
+                             int kt, int kh, int kw, int pad_t, int pad_h, int pad_w);
+int lvg_convnd_fprop(const void* x, const void* w, void* y, int dtype, int n, int groups, int cin, int cout,
+                     int t, int h, int wd, int kt, int kh, int kw, int pad_t, int pad_h, int pad_w,
+                     const float* bias, int act, float alpha, float gain, float clamp,
+                     void* workspace, int64_t workspace_bytes, void* stream);
+int lvg_convnd_dgrad(const void* dy, const void* w, void* dx, int dtype, int n, int groups, int cin, int cout,
+                     int t, int h, int wd, int kt, int kh, int kw, int pad_t, int pad_h, int pad_w,
+                     void* workspace, int64_t workspace_bytes, void* stream);
+int64_t lvg_convnd_wgrad_workspace(int dtype, int n, int groups, int cin, int cout, int t, int h, int wd,
+                                   int kt, int kh, int kw, int pad_t, int pad_h, int pad_w);
+int lvg_convnd_wgrad(const void* x, const void* dy, void* dw, int dtype, int n, int groups, int cin, int cout,
+                     int t, int h, int wd, int kt, int kh, int kw, int pad_t, int pad_h, int pad_w,
+                     void* workspace, int64_t workspace_bytes, void* stream);
+
+/*
  * Post-processing of an all-reduced flat gradient buffer, in place and in one pass:
  *   g = g * scale;  NaN -> 0, +inf -> +limit, -inf -> -limit  (finite values untouched)
  * -- the `/ world_size * gain` + `nan_to_num(nan=0, posinf=1e5, neginf=-1e5)` tail of

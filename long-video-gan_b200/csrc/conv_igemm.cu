@@ -1,0 +1,853 @@
+// Grouped 1-D / 2-D / 3-D convolution (cross-correlation) as a TMA-fed implicit GEMM on tcgen05 tensor cores.
+//
+// One engine for every dense contraction on the path:
+//   conv2d_gradfix.conv2d / conv_transpose2d          (torch_utils/ops/conv2d_gradfix.py:37-45; modulated convolutions of
+//                                                      model/generator_sres.py:63-65, discriminator convs of conv2d_resample.py:29-41)
+//   F.conv3d of the low-res networks                  (model/generator_lres.py:119,578, model/discriminator_lres.py:172)
+//   F.conv1d of the low-res discriminator epilogue    (model/discriminator_lres.py:108-127)
+// fp16 tensors run fp16 x fp16 -> fp32; fp32 tensors (the reference keeps TF32 off, train_lres.py:269) are split into
+// bf16 hi + lo halves and accumulate hi*hi + lo*hi + hi*lo in fp32 (relative error ~2^-16, three tensor-core products
+// instead of one SIMT fp32 pass).
+//
+// Data layout. Activations are first re-tiled (conv_pack_act_kernel, one streaming pass) from NC(T)HW to channel blocks
+// of 8:   X8[instance][block][t][h][w][8]   (16 bytes per pixel and block; instance = sample x group).
+// In this layout
+//   * a TMA tensor map (8, W, H, T, instance*block) addresses any halo tile with hardware zero fill -- no alignment
+//     constraints from odd row pitches (the fp16 NCHW rows of the super-res layers are 4 mod 8 elements long);
+//   * the tile lands in shared memory as [block][row][pixel][16 B], which IS the canonical K-major no-swizzle operand
+//     layout with the pixel index running linearly at 16 bytes: a filter tap (ky, kx) is nothing but a descriptor start
+//     address advanced by (ky * tile_width + kx) * 16 bytes. No shifted copies, no register staging.
+//   * N of one MMA runs linearly over the tile INCLUDING its halo columns; the accumulator columns that straddle two rows
+//     are computed and dropped in the epilogue (kw - 1 of every tile_width columns).
+// GEMM view per instance:  D[co][pix] = sum_{kt} sum_{ci} sum_{ky,kx} W[co][ci][kt][ky][kx] * X[ci][t + kt][y + ky][x + kx]
+//   M = 128 output channels, N = TH x (WT + kw - 1) pixels (<= 256 TMEM columns, 2 CTAs per SM),
+//   K = 16 channels per MMA; the K loop runs over (kt, 16-channel step), every stage issues kh*kw MMAs (one per tap).
+// Weights are re-tiled per call into 128 x 16 K-major images per (m-tile, k-step, tap) (conv_pack_w_kernel) and arrive
+// with one cp.async.bulk per stage.
+//
+// Roles (192 threads): warp 0 = TMA producer (one lane), warp 1 = MMA issuer (one lane, owns TMEM), warps 2-5 = epilogue
+// (TMEM -> registers -> [bias, lrelu, gain, clamp] -> NC(T)HW global). Stages hand over through full/empty mbarriers.
+
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "tcgen05.cuh"
+
+namespace lvg {
+namespace {
+
+using namespace tc;
+
+constexpr int kBM = 128;
+constexpr int kATile = kBM * 16 * 2;          // one 128 x 16 weight image: 4096 bytes
+constexpr int kThreads = 192;
+constexpr int kMaxStages = 4;
+
+struct IgemmParams {
+    const unsigned char* wp;     // packed weights [wgroups][mt][kc][taps_all][4096]
+    void* y;
+    const float* bias;           // per output channel (group-local index g*cout + co), or nullptr
+    int act;                     // 0 = none, 1 = (x + b) * gain clamped, 2 = lrelu(x + b, alpha) * gain clamped
+    float alpha, gain, clamp;    // clamp < 0: none
+    int out_f32;
+    int bf16;                    // operands are bf16 (split fp32) instead of fp16
+    int wgroups, cout, mt, kc;   // kc = 16-channel steps of the packed K axis
+    int nblk;                    // channel blocks per instance in X8
+    int kb_wrap;                 // split mode: source block of packed block kb is kb < kb_wrap ? kb : kb - kb_wrap
+    int to, ho, wo;              // output extent
+    int kt, kh, kw, pad_t, pad_h, pad_w;
+    int th, wt, wtb, thb;        // tile rows / cols, box cols / rows
+    int ncols;                   // accumulator columns (multiple of 16, <= 256)
+    int tmem_cols;               // power of two >= ncols
+    int tiles_x, tiles_y;
+    int ks;                      // k-steps per stage (> 1 only when kt == 1)
+    int stages;
+    int a_stage, b_step, b_bytes, stage_bytes;    // bytes: A per stage, B stride / payload per k-step, whole stage
+    int64_t y_cs;                // output channel stride (= to*ho*wo)
+};
+
+// ------------------------------------------------------------------------------------------------ re-tiling passes
+
+__device__ __forceinline__ unsigned short bf16_bits(float v) { return __bfloat16_as_ushort(__float2bfloat16_rn(v)); }
+__device__ __forceinline__ float bf16_val(unsigned short b) { return __uint_as_float((uint32_t)b << 16); }
+
+// NC(T)HW -> X8. One thread = one pixel of one channel block: 8 strided reads (coalesced across the warp), one or two
+// 16-byte writes. SPLIT: fp32 in, bf16 hi blocks [0, cblk) and lo blocks [cblk, 2 cblk) out.
+template <class TIn, bool SPLIT>
+__global__ void __launch_bounds__(256) conv_pack_act_kernel(const TIn* __restrict__ x, uint4* __restrict__ y, int64_t inst, int c,
+                                                             int cblk, int64_t thw)
+{
+    const int64_t total = inst * cblk * thw;
+    const int nblk = SPLIT ? 2 * cblk : cblk;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t p = i % thw;
+        const int64_t r = i / thw;
+        const int blk = (int)(r % cblk);
+        const int64_t in = r / cblk;
+        const int c0 = blk * 8;
+        const TIn* src = x + ((int64_t)in * c + c0) * thw + p;
+        if constexpr (!SPLIT) {
+            alignas(16) unsigned short v[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) v[j] = (c0 + j < c) ? __half_as_ushort(__ldg(reinterpret_cast<const __half*>(src) + (int64_t)j * thw)) : (unsigned short)0;
+            y[((int64_t)in * nblk + blk) * thw + p] = *reinterpret_cast<const uint4*>(v);
+        } else {
+            alignas(16) unsigned short hi[8], lo[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const float f = (c0 + j < c) ? __ldg(reinterpret_cast<const float*>(src) + (int64_t)j * thw) : 0.f;
+                hi[j] = bf16_bits(f);
+                lo[j] = bf16_bits(f - bf16_val(hi[j]));
+            }
+            y[((int64_t)in * nblk + blk) * thw + p] = *reinterpret_cast<const uint4*>(hi);
+            y[((int64_t)in * nblk + cblk + blk) * thw + p] = *reinterpret_cast<const uint4*>(lo);
+        }
+    }
+}
+
+// weights -> tile images.  Element (m, k, tap) of the logical A matrix of group g sits at
+//   w[g * gstride + m * sm + k * sk + (flip ? taps-1-tap : tap)]
+// fprop: m = co, k = ci (sm = cin*taps, sk = taps); dgrad: m = ci, k = co (sm = taps, sk = cin*taps), taps mirrored.
+// Image of one 128 x 16 tile (K-major, no swizzle): byte offset(m, k) = (k/8)*2048 + (m/8)*128 + (m%8)*16 + (k%8)*2.
+// SPLIT: the packed K axis is three segments of kpad channels [hi | hi | lo], matching the activation blocks
+// [hi | lo | hi] visited by the main loop: hi*hi + lo*hi + hi*lo.
+template <class TIn, bool SPLIT>
+__global__ void __launch_bounds__(256) conv_pack_w_kernel(const TIn* __restrict__ w, unsigned char* __restrict__ wp, int groups, int m_total,
+                                                           int k_total, int kpad, int taps, int64_t gstride, int64_t sm, int64_t sk, int flip,
+                                                           int mt, int kc)
+{
+    const int64_t total = (int64_t)groups * mt * kc * taps * (kATile / 16);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t r = i;
+        const int tap = (int)(r % taps); r /= taps;
+        const int k8 = (int)(r % 2); r /= 2;
+        const int mrow = (int)(r % kBM); r /= kBM;
+        const int kci = (int)(r % kc); r /= kc;
+        const int mti = (int)(r % mt);
+        const int g = (int)(r / mt);
+        const int m = mti * kBM + mrow;
+        const int kp0 = kci * 16 + k8 * 8;              // packed k of the first element
+        const int seg = SPLIT ? kp0 / kpad : 0;
+        const int k0 = SPLIT ? kp0 - seg * kpad : kp0;
+        const int wtap = flip ? taps - 1 - tap : tap;
+        alignas(16) unsigned short v[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const int k = k0 + j;
+            unsigned short o = 0;
+            if (m < m_total && k < k_total) {
+                const TIn e = w[(int64_t)g * gstride + (int64_t)m * sm + (int64_t)k * sk + wtap];
+                if constexpr (SPLIT) {
+                    const float f = (float)e;
+                    const unsigned short h = bf16_bits(f);
+                    o = seg == 2 ? bf16_bits(f - bf16_val(h)) : h;
+                } else {
+                    o = __half_as_ushort(e);
+                }
+            }
+            v[j] = o;
+        }
+        const int64_t tile = (((int64_t)g * mt + mti) * kc + kci) * taps + tap;
+        unsigned char* dst = wp + tile * kATile + k8 * 2048 + (mrow / 8) * 128 + (mrow % 8) * 16;
+        *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(v);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ main kernel
+
+__device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, int c4, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+                 ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+template <int NCOLS>
+__device__ __forceinline__ void tmem_alloc_n(uint32_t* slot)
+{
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "n"(NCOLS) : "memory");
+}
+
+__global__ void __launch_bounds__(kThreads, 2) conv_igemm_kernel(const __grid_constant__ CUtensorMap tmx, const IgemmParams p)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ uint64_t full_bar[kMaxStages], empty_bar[kMaxStages], acc_bar;
+    __shared__ uint32_t tmem_slot;
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    int tile = blockIdx.x;
+    const int tx = tile % p.tiles_x; tile /= p.tiles_x;
+    const int ty = tile % p.tiles_y;
+    const int t = tile / p.tiles_y;
+    const int mti = blockIdx.y, inst = blockIdx.z;
+    const int ox0 = tx * p.wt, oy0 = ty * p.th;
+    const int taps2 = p.kh * p.kw;
+    const int kchunks = (p.kc + p.ks - 1) / p.ks;
+    const int iters = p.kt * kchunks;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < p.stages; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(&acc_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        if (p.tmem_cols <= 32) tmem_alloc_n<32>(&tmem_slot);
+        else if (p.tmem_cols <= 64) tmem_alloc_n<64>(&tmem_slot);
+        else if (p.tmem_cols <= 128) tmem_alloc_n<128>(&tmem_slot);
+        else tmem_alloc_n<256>(&tmem_slot);
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_d = tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            const unsigned char* wpg = p.wp + (((int64_t)(inst % p.wgroups) * p.mt + mti) * p.kc) * (int64_t)(p.kt * taps2) * kATile;
+            const int blk0 = inst * p.nblk;
+            int it = 0;
+            for (int kt = 0; kt < p.kt; kt++) {
+                for (int kcix = 0; kcix < kchunks; kcix++, it++) {
+                    const int s = it % p.stages;
+                    if (it >= p.stages) mbar_wait(&empty_bar[s], (uint32_t)((it / p.stages - 1) & 1));
+                    unsigned char* st = smem + (size_t)s * p.stage_bytes;
+                    const int k0 = kcix * p.ks;
+                    const int nks = min(p.ks, p.kc - k0);
+                    const uint32_t a_bytes = (uint32_t)(nks * taps2 * kATile);
+                    mbar_expect_tx(&full_bar[s], a_bytes + (uint32_t)(nks * p.b_bytes));
+                    // A: kt == 1 -> the nks steps' tiles are contiguous; kt > 1 -> ks == 1, the taps of this kt are contiguous
+                    bulk_copy_g2s(st, wpg + ((int64_t)k0 * p.kt + kt) * (int64_t)taps2 * kATile, a_bytes, &full_bar[s]);
+                    for (int j = 0; j < nks; j++) {
+                        const int kb = (k0 + j) * 2;
+                        const int sb = kb < p.kb_wrap ? kb : kb - p.kb_wrap;
+                        tma_load_5d(st + p.a_stage + (size_t)j * p.b_step, &tmx, 0, ox0 - p.pad_w, oy0 - p.pad_h, t + kt - p.pad_t, blk0 + sb,
+                                    &full_bar[s]);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // instruction descriptor: D = f32, A and B K-major, fp16 or bf16 operands, N >> 3, M >> 4
+            const uint32_t idesc = (1u << 4) | (p.bf16 ? ((1u << 7) | (1u << 10)) : 0u) | ((uint32_t)(p.ncols >> 3) << 17) |
+                                   ((uint32_t)(kBM >> 4) << 24);
+            const uint32_t blk_bytes = (uint32_t)p.b_bytes / 2;
+            int it = 0;
+            for (int kt = 0; kt < p.kt; kt++) {
+                for (int kcix = 0; kcix < kchunks; kcix++, it++) {
+                    const int s = it % p.stages;
+                    mbar_wait(&full_bar[s], (uint32_t)((it / p.stages) & 1));
+                    tc_fence_after();
+                    const uint32_t st = smem_u32(smem + (size_t)s * p.stage_bytes);
+                    const int nks = min(p.ks, p.kc - kcix * p.ks);
+                    for (int j = 0; j < nks; j++) {
+                        const uint32_t a0 = st + (uint32_t)(j * taps2) * kATile;
+                        const uint32_t b0 = st + (uint32_t)p.a_stage + (uint32_t)j * (uint32_t)p.b_step;
+                        for (int ky = 0; ky < p.kh; ky++) {
+                            for (int kx = 0; kx < p.kw; kx++) {
+                                const uint64_t adesc = make_desc(a0 + (uint32_t)(ky * p.kw + kx) * kATile, 2048, 128);
+                                const uint64_t bdesc = make_desc(b0 + (uint32_t)(ky * p.wtb + kx) * 16, blk_bytes, 128);
+                                umma_f16(tmem_d, adesc, bdesc, idesc, (it > 0 || j > 0 || ky > 0 || kx > 0) ? 1u : 0u);
+                            }
+                        }
+                    }
+                    umma_commit(&empty_bar[s]);
+                }
+            }
+            umma_commit(&acc_bar);
+        }
+    } else {
+        // ---- epilogue warps: TMEM lane quadrant = warp % 4
+        mbar_wait(&acc_bar, 0);
+        tc_fence_after();
+        const int q = warp % 4;
+        const int m = mti * kBM + q * 32 + lane;
+        const bool mok = m < p.cout;
+        const int64_t ch = (int64_t)inst * p.cout + m;
+        const float b = (p.bias != nullptr && mok) ? __ldg(p.bias + (int64_t)(inst % p.wgroups) * p.cout + m) : 0.f;
+        const int64_t plane = ch * p.y_cs + (int64_t)t * p.ho * p.wo;
+        for (int n0 = 0; n0 < p.ncols; n0 += 32) {
+            uint32_t acc[32];
+            tmem_ld32(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)n0, acc);
+            int r = n0 / p.wtb, c = n0 - r * p.wtb;
+#pragma unroll
+            for (int j = 0; j < 32; j++) {
+                const int oy = oy0 + r, ox = ox0 + c;
+                if (mok && c < p.wt && r < p.th && oy < p.ho && ox < p.wo) {
+                    float v = __uint_as_float(acc[j]);
+                    if (p.act) {
+                        v += b;
+                        if (p.act == 2) v = v < 0.f ? v * p.alpha : v;
+                        v *= p.gain;
+                        if (p.clamp >= 0.f) v = fminf(fmaxf(v, -p.clamp), p.clamp);
+                    }
+                    const int64_t o = plane + (int64_t)oy * p.wo + ox;
+                    if (p.out_f32) reinterpret_cast<float*>(p.y)[o] = v;
+                    else reinterpret_cast<__half*>(p.y)[o] = __float2half_rn(v);
+                }
+                if (++c == p.wtb) { c = 0; ++r; }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        if (p.tmem_cols <= 32) tmem_dealloc(tmem_d, 32);
+        else if (p.tmem_cols <= 64) tmem_dealloc(tmem_d, 64);
+        else if (p.tmem_cols <= 128) tmem_dealloc(tmem_d, 128);
+        else tmem_dealloc(tmem_d, 256);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn()
+{
+    static EncodeTiledFn fn = [] {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) f = nullptr;
+        return reinterpret_cast<EncodeTiledFn>(f);
+    }();
+    return fn;
+}
+
+inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+struct Geometry {
+    int cpad, cblk, nblk, kpacked, kc, mt;
+    int64_t act_bytes, w_bytes;
+};
+
+// K-side geometry for `ck` contraction channels and `cm` output channels per group
+Geometry geometry(int split, int64_t inst, int groups, int ck, int cm, int64_t thw, int taps)
+{
+    Geometry g;
+    g.cpad = round_up(ck, 16);
+    g.cblk = g.cpad / 8;
+    g.nblk = split ? 2 * g.cblk : g.cblk;
+    g.kpacked = split ? 3 * g.cpad : g.cpad;
+    g.kc = g.kpacked / 16;
+    g.mt = (cm + kBM - 1) / kBM;
+    g.act_bytes = inst * g.nblk * thw * 16;
+    g.w_bytes = (int64_t)groups * g.mt * g.kc * taps * kATile;
+    return g;
+}
+
+// shared driver of fprop and dgrad: `x` has `ck` channels per group, `y` gets `cm`; logical A[m][k][tap] = w[g*gs + m*sm + k*sk + tap']
+int run_igemm(const void* x, const void* w, void* y, int dtype, int n, int groups, int ck, int cm, int t, int h, int wd, int kt, int kh,
+              int kw, int pad_t, int pad_h, int pad_w, int64_t w_gs, int64_t w_sm, int64_t w_sk, int flip, const float* bias, int act,
+              float alpha, float gain, float clamp, void* workspace, int64_t workspace_bytes, cudaStream_t s)
+{
+    const int split = dtype == LVG_F32 ? 1 : 0;
+    const int taps = kt * kh * kw;
+    const int64_t inst = (int64_t)n * groups;
+    const int64_t thw = (int64_t)t * h * wd;
+    const Geometry g = geometry(split, inst, groups, ck, cm, thw, taps);
+    LVG_REQUIRE(workspace && workspace_bytes >= g.act_bytes + g.w_bytes + 256, "convnd: workspace too small");
+    LVG_REQUIRE(aligned16(workspace), "convnd: workspace must be 16-byte aligned");
+    LVG_REQUIRE(inst <= 65535 && g.mt <= 65535, "convnd: too many instances / channel tiles for one launch");
+    LVG_REQUIRE(inst * g.nblk < (1ll << 31), "convnd: too many channel blocks for a tensor map");
+    EncodeTiledFn enc = encode_fn();
+    LVG_REQUIRE(enc != nullptr, "convnd: cuTensorMapEncodeTiled is not available from this driver");
+
+    unsigned char* wp = reinterpret_cast<unsigned char*>(workspace);
+    unsigned char* x8 = wp + ((g.w_bytes + 127) / 128) * 128;
+
+    IgemmParams p;
+    memset(&p, 0, sizeof(p));
+    p.wp = wp; p.y = y; p.bias = bias; p.act = act; p.alpha = alpha; p.gain = gain; p.clamp = clamp;
+    p.out_f32 = split; p.bf16 = split;
+    p.wgroups = groups; p.cout = cm; p.mt = g.mt; p.kc = g.kc; p.nblk = g.nblk;
+    p.kb_wrap = split ? 2 * g.cblk : (1 << 30);
+    p.to = t + 2 * pad_t - kt + 1; p.ho = h + 2 * pad_h - kh + 1; p.wo = wd + 2 * pad_w - kw + 1;
+    LVG_REQUIRE(p.to >= 1 && p.ho >= 1 && p.wo >= 1, "convnd: empty output");
+    p.kt = kt; p.kh = kh; p.kw = kw; p.pad_t = pad_t; p.pad_h = pad_h; p.pad_w = pad_w;
+    // tile: as many whole rows as fit 256 accumulator columns; wide images are cut into column tiles
+    const int max_wt = 256 - (kw - 1);
+    p.tiles_x = (p.wo + max_wt - 1) / max_wt;
+    p.wt = (p.wo + p.tiles_x - 1) / p.tiles_x;
+    p.wtb = p.wt + kw - 1;
+    p.th = 256 / p.wtb;
+    if (p.th > p.ho) p.th = p.ho;
+    if (p.th < 1) p.th = 1;
+    p.tiles_y = (p.ho + p.th - 1) / p.th;
+    p.th = (p.ho + p.tiles_y - 1) / p.tiles_y;               // balance the row tiles
+    p.thb = p.th + kh - 1;
+    p.ncols = round_up(p.th * p.wtb, 16);
+    LVG_REQUIRE(p.th >= 1 && p.ncols <= 256 && p.ncols >= 16, "convnd: tile geometry");
+    p.tmem_cols = p.ncols <= 32 ? 32 : p.ncols <= 64 ? 64 : p.ncols <= 128 ? 128 : 256;
+    // TMA writes the two 8-channel blocks of a k-step densely: block 1 starts thb*wtb*16 bytes after block 0 (= LBO);
+    // the k-steps of a stage start at 128-byte multiples (TMA destination alignment)
+    p.b_bytes = 2 * p.thb * p.wtb * 16;
+    p.b_step = round_up(p.b_bytes, 128);
+    const int taps2 = kh * kw;
+    p.ks = (kt == 1) ? (taps2 == 1 ? 4 : (taps2 <= 3 ? 2 : 1)) : 1;
+    if (p.ks > g.kc) p.ks = g.kc;
+    p.a_stage = p.ks * taps2 * kATile;
+    p.stage_bytes = round_up(p.a_stage + p.ks * p.b_step + 512, 128);      // + slack: the last taps read a few pixels past the tile
+    p.stages = 2;
+    const int smem_budget = 100 * 1024;
+    while (p.stages < kMaxStages && (p.stages + 1) * p.stage_bytes <= smem_budget) p.stages++;
+    LVG_REQUIRE(p.stages * p.stage_bytes <= 200 * 1024, "convnd: stage does not fit shared memory (%d bytes)", p.stage_bytes);
+    p.y_cs = (int64_t)p.to * p.ho * p.wo;
+    LVG_REQUIRE((int64_t)p.tiles_x * p.tiles_y * p.to < (1ll << 31), "convnd: too many tiles");
+
+    // re-tile the operands
+    {
+        const int64_t total = inst * g.cblk * thw;
+        int64_t blocks = (total + 255) / 256;
+        const int64_t cap = (int64_t)num_sms() * 64;
+        if (blocks > cap) blocks = cap;
+        if (split) conv_pack_act_kernel<float, true><<<(unsigned)blocks, 256, 0, s>>>((const float*)x, (uint4*)x8, inst, ck, g.cblk, thw);
+        else conv_pack_act_kernel<__half, false><<<(unsigned)blocks, 256, 0, s>>>((const __half*)x, (uint4*)x8, inst, ck, g.cblk, thw);
+        LVG_LAUNCH_CHECK();
+        const int64_t wtotal = g.w_bytes / 16;
+        blocks = (wtotal + 255) / 256;
+        if (blocks > cap) blocks = cap;
+        if (split) conv_pack_w_kernel<float, true><<<(unsigned)blocks, 256, 0, s>>>((const float*)w, wp, groups, cm, ck, g.cpad, taps, w_gs, w_sm, w_sk, flip, g.mt, g.kc);
+        else conv_pack_w_kernel<__half, false><<<(unsigned)blocks, 256, 0, s>>>((const __half*)w, wp, groups, cm, ck, g.cpad, taps, w_gs, w_sm, w_sk, flip, g.mt, g.kc);
+        LVG_LAUNCH_CHECK();
+    }
+
+    // tensor map over X8: (8, W, H, T, instance * block)
+    CUtensorMap tm;
+    {
+        const cuuint64_t dims[5] = {8, (cuuint64_t)wd, (cuuint64_t)h, (cuuint64_t)t, (cuuint64_t)(inst * g.nblk)};
+        const cuuint64_t strides[4] = {16, (cuuint64_t)wd * 16, (cuuint64_t)h * wd * 16, (cuuint64_t)thw * 16};
+        const cuuint32_t box[5] = {8, (cuuint32_t)p.wtb, (cuuint32_t)p.thb, 1, 2};
+        const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+        LVG_REQUIRE(p.wtb <= 256 && p.thb <= 256, "convnd: TMA box too large");
+        const CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT16, 5, x8, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        LVG_REQUIRE(r == CUDA_SUCCESS, "convnd: cuTensorMapEncodeTiled failed (%d)", (int)r);
+    }
+    const size_t smem = (size_t)p.stages * p.stage_bytes + 128;
+    LVG_CUDA(cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((unsigned)(p.tiles_x * p.tiles_y * p.to), (unsigned)g.mt, (unsigned)inst);
+    conv_igemm_kernel<<<grid, kThreads, smem, s>>>(tm, p);
+    LVG_LAUNCH_CHECK();
+    return LVG_OK;
+}
+
+bool nd_supported(int dtype, int kt, int kh, int kw)
+{
+    return (dtype == LVG_F16 || dtype == LVG_F32) && kt >= 1 && kh >= 1 && kw >= 1 && kh * kw <= 9 && kt <= 7;
+}
+
+}  // namespace
+}  // namespace lvg
+
+using namespace lvg;
+
+extern "C" int64_t lvg_convnd_workspace(int dtype, int n, int groups, int cin, int cout, int t, int h, int wd, int kt, int kh, int kw,
+                                        int pad_t, int pad_h, int pad_w)
+{
+    if (!nd_supported(dtype, kt, kh, kw) || n < 1 || groups < 1) return -1;
+    const int split = dtype == LVG_F32;
+    const int taps = kt * kh * kw;
+    const int64_t inst = (int64_t)n * groups;
+    const int to = t + 2 * pad_t - kt + 1, ho = h + 2 * pad_h - kh + 1, wo = wd + 2 * pad_w - kw + 1;
+    if (to < 1 || ho < 1 || wo < 1) return -1;
+    const Geometry a = geometry(split, inst, groups, cin, cout, (int64_t)t * h * wd, taps);        // fprop
+    const Geometry b = geometry(split, inst, groups, cout, cin, (int64_t)to * ho * wo, taps);      // dgrad
+    const int64_t fa = a.act_bytes + a.w_bytes, fb = b.act_bytes + b.w_bytes;
+    return (fa > fb ? fa : fb) + 1024;
+}
+
+extern "C" int lvg_convnd_fprop(const void* x, const void* w, void* y, int dtype, int n, int groups, int cin, int cout, int t, int h, int wd,
+                                int kt, int kh, int kw, int pad_t, int pad_h, int pad_w, const float* bias, int act, float alpha, float gain,
+                                float clamp, void* workspace, int64_t workspace_bytes, void* stream)
+{
+    LVG_REQUIRE(x && w && y, "convnd_fprop: x, w, y must not be NULL");
+    if (!nd_supported(dtype, kt, kh, kw) || n < 1 || pad_t < 0 || pad_h < 0 || pad_w < 0) {
+        set_error("convnd_fprop: outside the tensor-core kernel's envelope");
+        return LVG_UNSUPPORTED;
+    }
+    const int taps = kt * kh * kw;
+    return run_igemm(x, w, y, dtype, n, groups, cin, cout, t, h, wd, kt, kh, kw, pad_t, pad_h, pad_w, (int64_t)cout * cin * taps,
+                     (int64_t)cin * taps, taps, 0, bias, act, alpha, gain, clamp, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int lvg_convnd_dgrad(const void* dy, const void* w, void* dx, int dtype, int n, int groups, int cin, int cout, int t, int h, int wd,
+                                int kt, int kh, int kw, int pad_t, int pad_h, int pad_w, void* workspace, int64_t workspace_bytes, void* stream)
+{
+    LVG_REQUIRE(dy && w && dx, "convnd_dgrad: dy, w, dx must not be NULL");
+    if (!nd_supported(dtype, kt, kh, kw) || n < 1 || pad_t < 0 || pad_h < 0 || pad_w < 0 || pad_t > kt - 1 || pad_h > kh - 1 || pad_w > kw - 1) {
+        set_error("convnd_dgrad: outside the tensor-core kernel's envelope");
+        return LVG_UNSUPPORTED;
+    }
+    // dx = correlation of dy (to x ho x wo, cout channels) with the channel-transposed, mirrored weights, padding k-1-pad
+    const int taps = kt * kh * kw;
+    const int to = t + 2 * pad_t - kt + 1, ho = h + 2 * pad_h - kh + 1, wo = wd + 2 * pad_w - kw + 1;
+    return run_igemm(dy, w, dx, dtype, n, groups, cout, cin, to, ho, wo, kt, kh, kw, kt - 1 - pad_t, kh - 1 - pad_h, kw - 1 - pad_w,
+                     (int64_t)cout * cin * taps, taps, (int64_t)cin * taps, 1, nullptr, 0, 0.f, 1.f, -1.f, workspace, workspace_bytes,
+                     (cudaStream_t)stream);
+}
+
+// =================================================================================================
+// Weight gradient:  dW[g][co][ci][kt][ky][kx] = sum over samples and output pixels of dy[co][pix] * x[ci][pix + tap]
+//
+// GEMM view per CTA (group g, 128-channel tile of co, NT-channel tile of ci, tap row (kt, ky)):
+//   D_kx[co][ci] += A[co][k] * B_kx[ci][k],   K = output pixels, the kw taps of the row as kw accumulators in TMEM.
+// Both operands come from the SAME channel-block-of-8 tensors the forward kernels use, now as MN-major operands: a pixel
+// is a 16-byte row (8 channels) and the pixel index runs linearly at 16 bytes over a stage tile of RH rows x PS columns,
+// PS = (segment width + kw - 1) rounded up to 16. The dy tile is loaded through a tensor map whose W extent is clipped to
+// the column segment, so TMA zero-fills its last PS - width columns -- those are the K positions where the x tile holds
+// the row's halo; with equal pitches on both sides a tap (kx) is a start-address shift of kx * 16 bytes and the tap row
+// (kt, ky) a shifted TMA box. One MMA covers 16 consecutive pixels of the linear index.
+// Few groups (discriminators, low-res networks): the stages are cut into `nsplit` ranges over the grid, fp32 partial
+// sums go to a workspace and conv_wgrad_reduce_kernel folds them. fp32 tensors: hi/lo bf16 halves of BOTH operands are
+// staged, three MMAs per k-step (hi*hi + lo*hi + hi*lo).
+
+namespace lvg {
+namespace {
+
+struct WgradV2Params {
+    void* dw;                    // final output when nsplit == 1, else fp32 partials [nsplit][...]
+    int out_f32;                 // element type of `dw` (partials are always fp32)
+    int bf16, split;             // operand format; split = hi/lo pairs staged
+    int n, groups, cin, cout;
+    int to, ho;                  // output rows / frames iterated
+    int kt, kh, kw, pad_t, pad_h, pad_w;
+    int nt;                      // ci per n-tile (multiple of 16)
+    int nblk_a, nblk_b;          // channel blocks per instance in dy8 / x8 (incl. the lo half in split mode)
+    int lo_a, lo_b;              // block offset of the lo half
+    int nseg, seg_w[2], seg_x0[2], ps[2];
+    int rh;                      // rows per stage
+    int nsplit;
+    int a_bytes, b_bytes, stage_bytes, stages;      // per stage: one A (B) operand image; a stage holds split+1 of each
+    int64_t split_stride;        // elements between fp32 partials
+};
+
+__global__ void __launch_bounds__(kThreads, 1) conv_wgrad_v2_kernel(const __grid_constant__ CUtensorMap tma0, const __grid_constant__ CUtensorMap tma1,
+                                                                     const __grid_constant__ CUtensorMap tmb, const WgradV2Params p)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ uint64_t full_bar[kMaxStages], empty_bar[kMaxStages], acc_bar;
+    __shared__ uint32_t tmem_slot;
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    int bx = blockIdx.x;
+    const int sp = bx % p.nsplit; bx /= p.nsplit;
+    const int ky = bx % p.kh; bx /= p.kh;
+    const int kt = bx % p.kt;
+    const int nti = bx / p.kt;
+    const int mti = blockIdx.y, g = blockIdx.z;
+    const int NT = p.nt;
+    const int nop = p.split ? 2 : 1;                              // operand images per stage and side
+
+    // stages of this CTA: (sample, frame, segment, row block), range [s0, s1)
+    const int rblocks = (p.ho + p.rh - 1) / p.rh;
+    const int per_plane = p.nseg * rblocks;
+    const int total = p.n * p.to * per_plane;
+    const int s0 = (int)((int64_t)total * sp / p.nsplit), s1 = (int)((int64_t)total * (sp + 1) / p.nsplit);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < p.stages; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(&acc_bar, 1);
+        fence_barrier_init();
+    }
+    // zero the slack behind the stage buffers (the kx-shifted reads of the last block run 32 bytes past its end; the dy
+    // values they meet are zero, and zero * garbage must not become NaN)
+    // (uninitialised shared memory may hold NaN patterns: clear all of it once)
+    for (int i = threadIdx.x; i < (p.stages * p.stage_bytes + 256) / 16; i += kThreads) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_d = tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int s = s0; s < s1; s++) {
+                const int it = s - s0, slot = it % p.stages;
+                if (it >= p.stages) mbar_wait(&empty_bar[slot], (uint32_t)((it / p.stages - 1) & 1));
+                int r = s;
+                const int rb = r % rblocks; r /= rblocks;
+                const int seg = r % p.nseg; r /= p.nseg;
+                const int t = r % p.to;
+                const int n = r / p.to;
+                const int inst = n * p.groups + g;
+                unsigned char* st = smem + (size_t)slot * p.stage_bytes;
+                mbar_expect_tx(&full_bar[slot], (uint32_t)(nop * (p.a_bytes + p.b_bytes)));
+                const int oy0 = rb * p.rh;
+                for (int o = 0; o < nop; o++) {
+                    tma_load_5d(st + (size_t)o * p.a_bytes, seg == 0 ? &tma0 : &tma1, 0, 0, oy0, t, inst * p.nblk_a + o * p.lo_a + mti * 16, &full_bar[slot]);
+                    tma_load_5d(st + (size_t)nop * p.a_bytes + (size_t)o * p.b_bytes, &tmb, 0, p.seg_x0[seg] - p.pad_w, oy0 + ky - p.pad_h,
+                                t + kt - p.pad_t, inst * p.nblk_b + o * p.lo_b + nti * (NT / 8), &full_bar[slot]);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // instruction descriptor: D = f32, A and B MN-major (bits 15, 16), N >> 3, M >> 4
+            const uint32_t idesc = (1u << 4) | (p.bf16 ? ((1u << 7) | (1u << 10)) : 0u) | (1u << 15) | (1u << 16) | ((uint32_t)(NT >> 3) << 17) |
+                                   ((uint32_t)(kBM >> 4) << 24);
+            bool first = true;
+            for (int s = s0; s < s1; s++) {
+                const int it = s - s0, slot = it % p.stages;
+                const int seg = (s / rblocks) % p.nseg;
+                const int rb = s % rblocks;
+                const int rows = min(p.rh, p.ho - rb * p.rh);
+                const int ksteps = rows * p.ps[seg] / 16;
+                const uint32_t blk = (uint32_t)(p.rh * p.ps[seg] * 16);          // bytes of one channel block of the stage tile
+                mbar_wait(&full_bar[slot], (uint32_t)((it / p.stages) & 1));
+                tc_fence_after();
+                const uint32_t a0 = smem_u32(smem + (size_t)slot * p.stage_bytes);
+                const uint32_t b0 = a0 + (uint32_t)(nop * p.a_bytes);
+                for (int term = 0; term < (p.split ? 3 : 1); term++) {
+                    const uint32_t at = a0 + (term == 1 ? (uint32_t)p.a_bytes : 0u);     // hi*hi, lo*hi, hi*lo
+                    const uint32_t bt = b0 + (term == 2 ? (uint32_t)p.b_bytes : 0u);
+                    for (int k = 0; k < ksteps; k++) {
+                        const uint64_t adesc = make_desc(at + (uint32_t)k * 256, 128, blk);
+                        for (int kx = 0; kx < p.kw; kx++) {
+                            const uint64_t bdesc = make_desc(bt + (uint32_t)k * 256 + (uint32_t)kx * 16, 128, blk);
+                            umma_f16(tmem_d + (uint32_t)(kx * NT), adesc, bdesc, idesc, (first && k == 0) ? 0u : 1u);
+                        }
+                    }
+                    first = false;
+                }
+                umma_commit(&empty_bar[slot]);
+            }
+            umma_commit(&acc_bar);
+        }
+    }
+    // ---- epilogue, 32 input channels at a time: TMEM -> shared [co][ci * kw + kx] (fp32) -> global rows of kw-runs
+    float* tile = reinterpret_cast<float*>(smem);
+    const int row_pitch = 32 * p.kw + 1;
+    if (warp >= 2) {
+        mbar_wait(&acc_bar, 0);
+        tc_fence_after();
+    }
+    __syncthreads();                       // every stage buffer is free from here on
+    {
+        const int taps = p.kt * p.kh * p.kw;
+        const int ci0 = nti * NT, co0 = mti * kBM;
+        const int tap0 = (kt * p.kh + ky) * p.kw;
+        const bool any = s1 > s0;
+        for (int c0 = 0; c0 < NT; c0 += 32) {
+            if (warp >= 2) {
+                const int q = warp % 4;
+                const int r = q * 32 + lane;
+                for (int kx = 0; kx < p.kw; kx++) {
+                    uint32_t acc[32];
+                    tmem_ld32(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(kx * NT + c0), acc);
+#pragma unroll
+                    for (int j = 0; j < 32; j++) tile[r * row_pitch + j * p.kw + kx] = any ? __uint_as_float(acc[j]) : 0.f;
+                }
+            }
+            __syncthreads();
+            const int ci_n = min(32, min(NT - c0, p.cin - ci0 - c0));
+            const int per_row = ci_n * p.kw;
+            if (per_row > 0) {
+                for (int r = warp; r < kBM; r += kThreads / 32) {
+                    const int co = co0 + r;
+                    if (co >= p.cout) break;
+                    const int64_t base = (((int64_t)g * p.cout + co) * p.cin + ci0 + c0) * taps + tap0;
+                    const float* src = tile + r * row_pitch;
+                    if (p.nsplit > 1) {
+                        float* dst = reinterpret_cast<float*>(p.dw) + (int64_t)sp * p.split_stride + base;
+                        for (int j = lane; j < per_row; j += 32) { const int ci = j / p.kw, kx = j - ci * p.kw; dst[ci * taps + kx] = src[j]; }
+                    } else if (p.out_f32) {
+                        float* dst = reinterpret_cast<float*>(p.dw) + base;
+                        for (int j = lane; j < per_row; j += 32) { const int ci = j / p.kw, kx = j - ci * p.kw; dst[ci * taps + kx] = src[j]; }
+                    } else {
+                        __half* dst = reinterpret_cast<__half*>(p.dw) + base;
+                        for (int j = lane; j < per_row; j += 32) { const int ci = j / p.kw, kx = j - ci * p.kw; dst[ci * taps + kx] = __float2half_rn(src[j]); }
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_d, 512);
+}
+
+template <class TOut>
+__global__ void __launch_bounds__(256) conv_wgrad_reduce_kernel(const float* __restrict__ part, TOut* __restrict__ out, int64_t n, int nsplit, int64_t stride)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        float s = 0.f;
+        for (int k = 0; k < nsplit; k++) s += part[(int64_t)k * stride + i];
+        if constexpr (sizeof(TOut) == 2) out[i] = __float2half_rn(s);
+        else out[i] = s;
+    }
+}
+
+int encode_map(CUtensorMap* tm, void* base, int w, int h, int t, int64_t blocks, int64_t pitch_w, int64_t pitch_hw, int64_t pitch_thw, int box_w,
+               int box_h, int box_blk)
+{
+    EncodeTiledFn enc = encode_fn();
+    LVG_REQUIRE(enc != nullptr, "convnd: cuTensorMapEncodeTiled is not available from this driver");
+    const cuuint64_t dims[5] = {8, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)t, (cuuint64_t)blocks};
+    const cuuint64_t strides[4] = {16, (cuuint64_t)pitch_w * 16, (cuuint64_t)pitch_hw * 16, (cuuint64_t)pitch_thw * 16};
+    const cuuint32_t box[5] = {8, (cuuint32_t)box_w, (cuuint32_t)box_h, 1, (cuuint32_t)box_blk};
+    const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    LVG_REQUIRE(box_w <= 256 && box_h <= 256 && box_blk <= 256, "convnd: TMA box too large");
+    const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT16, 5, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    LVG_REQUIRE(r == CUDA_SUCCESS, "convnd: cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return LVG_OK;
+}
+
+struct WgradPlan {
+    int split, cpad_a, cpad_b, nt, ntiles, mt, nsplit;
+    int nseg, seg_w[2], seg_x0[2], ps, rh, stages;
+    int a_stage, b_stage, stage_bytes;
+    size_t smem;
+    int64_t a_bytes, b_bytes, part_bytes, dw_elems;
+};
+
+WgradPlan wgrad_plan(int dtype, int n, int groups, int cin, int cout, int t, int h, int wd, int to, int ho, int wo, int kt, int kh, int kw)
+{
+    WgradPlan q;
+    q.split = dtype == LVG_F32;
+    q.cpad_a = round_up(cout, 128);          // whole m-tiles of 16 blocks
+    q.cpad_b = round_up(cin, 16);
+    int nt_cap = (512 / kw) / 16 * 16;
+    if (nt_cap > 256) nt_cap = 256;
+    if (q.split && nt_cap > 96) nt_cap = 96;
+    q.ntiles = (q.cpad_b + nt_cap - 1) / nt_cap;
+    q.nt = round_up((q.cpad_b + q.ntiles - 1) / q.ntiles, 16);
+    q.cpad_b = q.nt * q.ntiles;
+    q.mt = q.cpad_a / 128;
+    const int64_t inst = (int64_t)n * groups;
+    q.a_bytes = inst * (q.split ? 2 : 1) * (q.cpad_a / 8) * (int64_t)to * ho * wo * 16;
+    q.b_bytes = inst * (q.split ? 2 : 1) * (q.cpad_b / 8) * (int64_t)t * h * wd * 16;
+    q.dw_elems = (int64_t)groups * cout * cin * kt * kh * kw;
+    // column segments (a TMA box is at most 256 pixels wide) and the common tile pitch
+    q.nseg = (wo + kw - 1 > 256) ? 2 : 1;
+    const int w0 = q.nseg == 1 ? wo : (wo + 1) / 2;
+    q.seg_w[0] = w0; q.seg_x0[0] = 0; q.seg_w[1] = wo - w0; q.seg_x0[1] = w0;
+    q.ps = round_up(w0 + kw - 1, 16);
+    // rows per stage: about 80 KB of operands per stage
+    const int nop = q.split ? 2 : 1;
+    const int per_row = nop * (16 + q.nt / 8) * q.ps * 16;
+    q.rh = (80 * 1024) / per_row;
+    if (q.rh < 1) q.rh = 1;
+    if (q.rh > ho) q.rh = ho;
+    if (q.rh > 255) q.rh = 255;
+    q.a_stage = 16 * q.rh * q.ps * 16;
+    q.b_stage = (q.nt / 8) * q.rh * q.ps * 16;
+    q.stage_bytes = round_up(nop * (q.a_stage + q.b_stage), 128);
+    q.stages = 2;
+    while (q.stages < kMaxStages && (q.stages + 1) * q.stage_bytes <= 190 * 1024) q.stages++;
+    const size_t tile_bytes = (size_t)kBM * (32 * kw + 1) * 4;
+    q.smem = (size_t)q.stages * q.stage_bytes + 256;
+    if (tile_bytes > q.smem) q.smem = tile_bytes;
+    q.smem += 128;
+    // split the pixel range until the grid fills the machine about twice
+    const int64_t ctas = (int64_t)q.ntiles * kh * kt * q.mt * groups;
+    const int64_t stages = (int64_t)n * to * q.nseg * ((ho + q.rh - 1) / q.rh);
+    int64_t ns = (2 * 148 + ctas - 1) / ctas;
+    if (ns > stages) ns = stages;
+    if (ns > 64) ns = 64;
+    if (ns < 1) ns = 1;
+    q.nsplit = (int)ns;
+    q.part_bytes = q.nsplit > 1 ? q.nsplit * q.dw_elems * 4 : 0;
+    return q;
+}
+
+}  // namespace
+}  // namespace lvg
+
+extern "C" int64_t lvg_convnd_wgrad_workspace(int dtype, int n, int groups, int cin, int cout, int t, int h, int wd, int kt, int kh, int kw,
+                                              int pad_t, int pad_h, int pad_w)
+{
+    if (!nd_supported(dtype, kt, kh, kw) || n < 1 || groups < 1 || kw > 3) return -1;
+    const int to = t + 2 * pad_t - kt + 1, ho = h + 2 * pad_h - kh + 1, wo = wd + 2 * pad_w - kw + 1;
+    if (to < 1 || ho < 1 || wo < 1 || wo + kw - 1 > 2 * 240) return -1;
+    const WgradPlan q = wgrad_plan(dtype, n, groups, cin, cout, t, h, wd, to, ho, wo, kt, kh, kw);
+    return q.a_bytes + q.b_bytes + q.part_bytes + 1024;
+}
+
+extern "C" int lvg_convnd_wgrad(const void* x, const void* dy, void* dw, int dtype, int n, int groups, int cin, int cout, int t, int h, int wd,
+                                int kt, int kh, int kw, int pad_t, int pad_h, int pad_w, void* workspace, int64_t workspace_bytes, void* stream)
+{
+    LVG_REQUIRE(x && dy && dw, "convnd_wgrad: x, dy, dw must not be NULL");
+    const int to = t + 2 * pad_t - kt + 1, ho = h + 2 * pad_h - kh + 1, wo = wd + 2 * pad_w - kw + 1;
+    if (!nd_supported(dtype, kt, kh, kw) || n < 1 || kw > 3 || pad_t < 0 || pad_h < 0 || pad_w < 0 || to < 1 || ho < 1 || wo < 1 ||
+        wo + kw - 1 > 2 * 240) {
+        set_error("convnd_wgrad: outside the tensor-core kernel's envelope");
+        return LVG_UNSUPPORTED;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    const WgradPlan q = wgrad_plan(dtype, n, groups, cin, cout, t, h, wd, to, ho, wo, kt, kh, kw);
+    LVG_REQUIRE(workspace && workspace_bytes >= q.a_bytes + q.b_bytes + q.part_bytes + 768, "convnd_wgrad: workspace too small");
+    LVG_REQUIRE(aligned16(workspace), "convnd_wgrad: workspace must be 16-byte aligned");
+    LVG_REQUIRE(groups <= 65535 && q.mt <= 65535, "convnd_wgrad: too many groups / channel tiles");
+    const int64_t inst = (int64_t)n * groups;
+    unsigned char* dy8 = reinterpret_cast<unsigned char*>(workspace);
+    unsigned char* x8 = dy8 + ((q.a_bytes + 255) / 256) * 256;
+    float* part = reinterpret_cast<float*>(x8 + ((q.b_bytes + 255) / 256) * 256);
+    const int64_t thw_a = (int64_t)to * ho * wo, thw_b = (int64_t)t * h * wd;
+    {
+        const int64_t cap = (int64_t)num_sms() * 64;
+        int64_t total = inst * (q.cpad_a / 8) * thw_a, blocks = (total + 255) / 256;
+        if (blocks > cap) blocks = cap;
+        if (q.split) conv_pack_act_kernel<float, true><<<(unsigned)blocks, 256, 0, s>>>((const float*)dy, (uint4*)dy8, inst, cout, q.cpad_a / 8, thw_a);
+        else conv_pack_act_kernel<__half, false><<<(unsigned)blocks, 256, 0, s>>>((const __half*)dy, (uint4*)dy8, inst, cout, q.cpad_a / 8, thw_a);
+        LVG_LAUNCH_CHECK();
+        total = inst * (q.cpad_b / 8) * thw_b; blocks = (total + 255) / 256;
+        if (blocks > cap) blocks = cap;
+        if (q.split) conv_pack_act_kernel<float, true><<<(unsigned)blocks, 256, 0, s>>>((const float*)x, (uint4*)x8, inst, cin, q.cpad_b / 8, thw_b);
+        else conv_pack_act_kernel<__half, false><<<(unsigned)blocks, 256, 0, s>>>((const __half*)x, (uint4*)x8, inst, cin, q.cpad_b / 8, thw_b);
+        LVG_LAUNCH_CHECK();
+    }
+    WgradV2Params p;
+    memset(&p, 0, sizeof(p));
+    p.out_f32 = q.split; p.bf16 = q.split; p.split = q.split;
+    p.n = n; p.groups = groups; p.cin = cin; p.cout = cout; p.to = to; p.ho = ho;
+    p.kt = kt; p.kh = kh; p.kw = kw; p.pad_t = pad_t; p.pad_h = pad_h; p.pad_w = pad_w;
+    p.nt = q.nt;
+    p.nblk_a = (q.split ? 2 : 1) * (q.cpad_a / 8); p.nblk_b = (q.split ? 2 : 1) * (q.cpad_b / 8);
+    p.lo_a = q.cpad_a / 8; p.lo_b = q.cpad_b / 8;
+    p.nseg = q.nseg;
+    for (int j = 0; j < 2; j++) { p.seg_w[j] = q.seg_w[j]; p.seg_x0[j] = q.seg_x0[j]; p.ps[j] = q.ps; }
+    const int nop = q.split ? 2 : 1;
+    (void)nop;
+    p.rh = q.rh;
+    p.a_bytes = q.a_stage; p.b_bytes = q.b_stage; p.stage_bytes = q.stage_bytes; p.stages = q.stages;
+    const size_t smem = q.smem;
+    LVG_REQUIRE(smem <= 227 * 1024, "convnd_wgrad: stage does not fit shared memory (%zu bytes)", smem);
+    p.nsplit = q.nsplit;
+    p.split_stride = q.dw_elems;
+    p.dw = q.nsplit > 1 ? (void*)part : dw;
+    // NOTE the per-segment tile pitch: a stage tile of segment j is [block][rh][ps[j]][16 B] -- the box width IS the pitch
+    CUtensorMap tma0, tma1, tmb;
+    int rc = encode_map(&tma0, dy8, p.seg_w[0], ho, to, inst * p.nblk_a, wo, (int64_t)ho * wo, thw_a, p.ps[0], p.rh, 16);
+    if (rc) return rc;
+    if (p.nseg == 2) rc = encode_map(&tma1, dy8 + (size_t)p.seg_x0[1] * 16, p.seg_w[1], ho, to, inst * p.nblk_a, wo, (int64_t)ho * wo, thw_a, p.ps[1], p.rh, 16);
+    else tma1 = tma0;
+    if (rc) return rc;
+    rc = encode_map(&tmb, x8, wd, h, t, inst * p.nblk_b, wd, (int64_t)h * wd, thw_b, p.ps[0], p.rh, q.nt / 8);
+    if (rc) return rc;
+    LVG_CUDA(cudaFuncSetAttribute(conv_wgrad_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((unsigned)(q.ntiles * kt * kh * q.nsplit), (unsigned)q.mt, (unsigned)groups);
+    conv_wgrad_v2_kernel<<<grid, kThreads, smem, s>>>(tma0, tma1, tmb, p);
+    LVG_LAUNCH_CHECK();
+    if (q.nsplit > 1) {
+        int64_t blocks = (q.dw_elems + 255) / 256;
+        const int64_t cap = (int64_t)num_sms() * 32;
+        if (blocks > cap) blocks = cap;
+        if (q.split) conv_wgrad_reduce_kernel<float><<<(unsigned)blocks, 256, 0, s>>>(part, (float*)dw, q.dw_elems, q.nsplit, q.dw_elems);
+        else conv_wgrad_reduce_kernel<__half><<<(unsigned)blocks, 256, 0, s>>>(part, (__half*)dw, q.dw_elems, q.nsplit, q.dw_elems);
+        LVG_LAUNCH_CHECK();
+    }
+    return LVG_OK;
+}

@@ -60,6 +60,11 @@ _SIGNATURES = {
     'lvg_conv2d_fprop_workspace': (_c_i64, [_c_int] * 12),
     'lvg_conv2d_dgrad': (_c_int, [_c_void_p] * 3 + [_c_int] * 12 + [_c_void_p, _c_i64, _c_void_p]),
     'lvg_conv2d_wgrad': (_c_int, [_c_void_p] * 3 + [_c_int] * 12 + [_c_void_p]),
+    'lvg_convnd_workspace': (_c_i64, [_c_int] * 14),
+    'lvg_convnd_fprop': (_c_int, [_c_void_p] * 3 + [_c_int] * 14 + [_c_void_p, _c_int, _c_float, _c_float, _c_float, _c_void_p, _c_i64, _c_void_p]),
+    'lvg_convnd_dgrad': (_c_int, [_c_void_p] * 3 + [_c_int] * 14 + [_c_void_p, _c_i64, _c_void_p]),
+    'lvg_convnd_wgrad_workspace': (_c_i64, [_c_int] * 14),
+    'lvg_convnd_wgrad': (_c_int, [_c_void_p] * 3 + [_c_int] * 14 + [_c_void_p, _c_i64, _c_void_p]),
 }
 
 LVG_UNSUPPORTED = -1
@@ -551,7 +556,103 @@ class Conv2dPlugin:
         return dw
 
 
+class ConvNdPlugin:
+    """TMA-fed tcgen05 implicit-GEMM convolution for 1-D / 2-D / 3-D NC(T)HW tensors, fp16 or fp32 (bf16 hi/lo split),
+    stride 1: forward (optionally with the bias_act epilogue fused), input gradient, weight gradient. No reference
+    plugin: the reference hands these to cuDNN (conv2d_gradfix.py:37-45, generator_lres.py:119, discriminator_lres.py:121,172)."""
+
+    def __init__(self, lib):
+        self._lib = lib
+        self._ws = {}
+
+    @staticmethod
+    def _dims(x, w):
+        """-> (n, c, t, h, w), (kt, kh, kw), spatial rank"""
+        nd = x.ndim - 2
+        sp = list(x.shape[2:])
+        k = list(w.shape[2:])
+        while len(sp) < 3:
+            sp.insert(0, 1)
+            k.insert(0, 1)
+        return sp, k, nd
+
+    @staticmethod
+    def _pad3(padding, nd):
+        p = list(padding) if isinstance(padding, (list, tuple)) else [padding] * nd
+        return [0] * (3 - nd) + [int(v) for v in p]
+
+    def supported(self, x, w, stride, padding, dilation, groups):
+        if not (x.is_cuda and x.dtype in (torch.float16, torch.float32) and w.dtype == x.dtype and x.ndim == w.ndim and x.ndim in (3, 4, 5)):
+            return False
+        nd = x.ndim - 2
+        as_t = lambda v: tuple(v) if isinstance(v, (list, tuple)) else (v,) * nd       # noqa: E731
+        if as_t(stride) != (1,) * nd or as_t(dilation) != (1,) * nd:
+            return False
+        sp, k, _ = self._dims(x, w)
+        pad = self._pad3(padding, nd)
+        if k[1] * k[2] > 9 or k[0] > 7 or k[2] > 3 or min(pad) < 0 or any(p > kk - 1 for p, kk in zip(pad, k)):
+            return False
+        if x.shape[1] != w.shape[1] * groups or w.shape[0] % groups != 0 or x.shape[0] * groups > 65535 or x.numel() == 0:
+            return False
+        return all(s + 2 * p - kk + 1 >= 1 for s, p, kk in zip(sp, pad, k)) and sp[2] + 2 * pad[2] <= 480
+
+    def _workspace(self, device, need):
+        if need < 0:
+            raise RuntimeError('convnd: configuration outside the tensor-core kernel envelope')
+        buf = self._ws.get(device)
+        if buf is None or buf.numel() < need:
+            buf = torch.empty(max(int(need), 1 << 22), dtype=torch.uint8, device=device)
+            self._ws[device] = buf      # stream-ordered reuse: every call re-tiles its operands before it reads them
+        return buf
+
+    def _args(self, x_shape, w_shape, padding, groups, dtype):
+        nd = len(x_shape) - 2
+        sp = [1] * (3 - nd) + list(x_shape[2:])
+        k = [1] * (3 - nd) + list(w_shape[2:])
+        pad = self._pad3(padding, nd)
+        code = 1 if dtype == torch.float16 else 0
+        return [code, x_shape[0], groups, w_shape[1], w_shape[0] // groups] + sp + k + pad, sp, k, pad
+
+    def fprop(self, x, w, padding, groups, bias=None, act=0, alpha=0.2, gain=1.0, clamp=-1.0):
+        x, w = x.contiguous(), w.contiguous()
+        a, sp, k, pad = self._args(tuple(x.shape), tuple(w.shape), padding, groups, x.dtype)
+        out_sp = [s + 2 * p - kk + 1 for s, p, kk in zip(sp, pad, k)][3 - (x.ndim - 2):]
+        y = torch.empty([x.shape[0], w.shape[0]] + out_sp, dtype=x.dtype, device=x.device)
+        ws = self._workspace(x.device, self._lib.lvg_convnd_workspace(*a))
+        if bias is not None:
+            bias = bias.to(torch.float32).contiguous()
+        with _DeviceGuard(x):
+            rc = _check(self._lib.lvg_convnd_fprop(_ptr(x), _ptr(w), _ptr(y), *a, _ptr(bias), int(act), float(alpha), float(gain),
+                                                   float(clamp), _ptr(ws), ws.numel(), _stream(x)), 'convnd_fprop')
+        if rc == LVG_UNSUPPORTED:
+            raise RuntimeError('convnd_fprop: ' + self._lib.lvg_last_error().decode())
+        return y
+
+    def dgrad(self, dy, w, x_shape, padding, groups):
+        dy, w = dy.contiguous(), w.contiguous()
+        a, sp, k, pad = self._args(tuple(x_shape), tuple(w.shape), padding, groups, dy.dtype)
+        dx = torch.empty(list(x_shape), dtype=dy.dtype, device=dy.device)
+        ws = self._workspace(dy.device, self._lib.lvg_convnd_workspace(*a))
+        with _DeviceGuard(dy):
+            rc = _check(self._lib.lvg_convnd_dgrad(_ptr(dy), _ptr(w), _ptr(dx), *a, _ptr(ws), ws.numel(), _stream(dy)), 'convnd_dgrad')
+        if rc == LVG_UNSUPPORTED:
+            raise RuntimeError('convnd_dgrad: ' + self._lib.lvg_last_error().decode())
+        return dx
+
+    def wgrad(self, x, dy, w_shape, padding, groups):
+        x, dy = x.contiguous(), dy.contiguous()
+        a, sp, k, pad = self._args(tuple(x.shape), tuple(w_shape), padding, groups, x.dtype)
+        dw = torch.empty(list(w_shape), dtype=x.dtype, device=x.device)
+        ws = self._workspace(x.device, self._lib.lvg_convnd_wgrad_workspace(*a))
+        with _DeviceGuard(x):
+            rc = _check(self._lib.lvg_convnd_wgrad(_ptr(x), _ptr(dy), _ptr(dw), *a, _ptr(ws), ws.numel(), _stream(x)), 'convnd_wgrad')
+        if rc == LVG_UNSUPPORTED:
+            raise RuntimeError('convnd_wgrad: ' + self._lib.lvg_last_error().decode())
+        return dw
+
+
 _PLUGIN_CLASSES = {
+    'convnd_plugin': ConvNdPlugin,
     'conv2d_plugin': Conv2dPlugin,
     'bias_act_plugin': BiasActPlugin,
     'upfirdn2d_plugin': Upfirdn2dPlugin,

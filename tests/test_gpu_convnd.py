@@ -1,0 +1,109 @@
+"""The TMA-fed tcgen05 implicit-GEMM convolution engine (csrc/conv_igemm.cu) through the C ABI, against torch's own
+convolutions in float64 on the same inputs: 1-D / 2-D / 3-D, fp16 and fp32 (bf16 hi/lo split), forward with and
+without the fused bias_act epilogue, input gradient, weight gradient (with and without split-K, one and two column
+segments). Shapes follow the call sites: conv2d_gradfix.py:37-45 (generator_sres.py:63-65, conv2d_resample.py:29-41),
+generator_lres.py:119,578, discriminator_lres.py:121,172."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from torch_utils import custom_ops
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+
+
+@pytest.fixture(scope='module')
+def plug():
+    return custom_ops.get_plugin('convnd_plugin')
+
+
+def rnd(shape, seed, scale=1.0):
+    g = torch.Generator(device=DEV).manual_seed(seed)
+    return torch.randn(*shape, generator=g, device=DEV, dtype=torch.float64) * scale
+
+
+def conv_ref(x, w, padding, groups):
+    nd = x.ndim - 2
+    return (F.conv1d, F.conv2d, F.conv3d)[nd - 1](x, w, padding=padding, groups=groups)
+
+
+CASES = [
+    # name, x shape, w shape, padding, groups
+    ('2d modulated 3x3 pad2 ragged', (1, 4 * 24, 20, 26), (4 * 40, 24, 3, 3), (2, 2), 4),
+    ('2d 1x1', (3, 40, 17, 23), (24, 40, 1, 1), (0, 0), 1),
+    ('2d 3x3 pad1 batch', (3, 64, 33, 40), (130, 64, 3, 3), (1, 1), 1),
+    ('2d wide row 150', (1, 2 * 27, 10, 148), (2 * 72, 27, 3, 3), (2, 2), 2),
+    ('2d two column tiles 278', (1, 16, 7, 276), (24, 16, 3, 3), (2, 2), 1),
+    ('2d tiny 4x4', (2, 32, 4, 4), (32, 32, 3, 3), (1, 1), 1),
+    ('2d many k-steps', (1, 539, 12, 20), (130, 539, 3, 3), (2, 2), 1),
+    ('3d 3x3x3', (2, 32, 6, 9, 16), (48, 32, 3, 3, 3), (1, 1, 1), 1),
+    ('3d 1x3x3', (1, 24, 5, 18, 32), (20, 24, 1, 3, 3), (0, 1, 1), 1),
+    ('3d 5x3x3', (1, 16, 9, 8, 8), (24, 16, 5, 3, 3), (2, 1, 1), 1),
+    ('3d 1x1x1', (2, 48, 4, 5, 8), (136, 48, 1, 1, 1), (0, 0, 0), 1),
+    ('3d 3x3x3 3x4 image', (2, 40, 7, 3, 4), (40, 40, 3, 3, 3), (1, 1, 1), 1),
+    ('1d k3', (2, 64, 16), (32, 64, 3), (1,), 1),
+    ('1d k1', (3, 200, 16), (50, 200, 1), (0,), 1),
+]
+
+
+@pytest.mark.parametrize('dtype', [torch.float16, torch.float32], ids=['f16', 'f32split'])
+@pytest.mark.parametrize('name,xs,ws,pad,groups', CASES, ids=[c[0] for c in CASES])
+def test_convnd_forward_and_gradients(plug, name, xs, ws, pad, groups, dtype):
+    fan = math.prod(ws[1:])
+    x64, w64 = rnd(xs, 1), rnd(ws, 2, 1.0 / math.sqrt(fan))
+    x, w = x64.to(dtype), w64.to(dtype)
+    xr, wr = x.double().requires_grad_(True), w.double().requires_grad_(True)     # the reference sees the rounded operands
+    yr = conv_ref(xr, wr, pad, groups)
+    assert plug.supported(x, w, 1, pad, 1, groups)
+    y = plug.fprop(x, w, pad, groups)
+    assert y.shape == yr.shape and y.dtype == dtype
+    tol = 2e-3 if dtype == torch.float16 else 5e-5          # fp16: result rounding; split fp32: ~2^-16 per product
+    scale = float(yr.abs().max())
+    assert float((y.double() - yr).abs().max()) <= tol * scale, f'fprop {float((y.double() - yr).abs().max()) / scale:.3e}'
+    dy64 = rnd(tuple(yr.shape), 3)
+    dy = dy64.to(dtype)
+    gx, gw = torch.autograd.grad(yr, [xr, wr], dy.double())
+    dx = plug.dgrad(dy, w, tuple(x.shape), pad, groups)
+    assert float((dx.double() - gx).abs().max()) <= tol * float(gx.abs().max()), f'dgrad {float((dx.double() - gx).abs().max() / gx.abs().max()):.3e}'
+    dw = plug.wgrad(x, dy, tuple(w.shape), pad, groups)
+    assert dw.shape == w.shape and dw.dtype == dtype
+    assert float((dw.double() - gw).abs().max()) <= tol * float(gw.abs().max()), f'wgrad {float((dw.double() - gw).abs().max() / gw.abs().max()):.3e}'
+
+
+@pytest.mark.parametrize('dtype', [torch.float16, torch.float32])
+def test_convnd_fused_bias_act_epilogue(plug, dtype):
+    x, w, b = rnd((2, 24, 6, 9, 16), 4).to(dtype), rnd((40, 24, 3, 3, 3), 5, 0.05).to(dtype), rnd((40,), 6).float()
+    for act, alpha, gain, clamp in ((2, 0.2, math.sqrt(2), 0.8), (1, 0.0, 1.0, 256.0), (2, 0.2, 1.0, -1.0)):
+        y = plug.fprop(x, w, (1, 1, 1), 1, bias=b, act=act, alpha=alpha, gain=gain, clamp=clamp)
+        r = F.conv3d(x.double(), w.double(), padding=1) + b.double().view(1, -1, 1, 1, 1)
+        if act == 2:
+            r = F.leaky_relu(r, alpha)
+        r = r * gain
+        if clamp >= 0:
+            r = r.clamp(-clamp, clamp)
+        tol = 2e-3 if dtype == torch.float16 else 5e-5
+        assert float((y.double() - r).abs().max()) <= tol * float(r.abs().max())
+
+
+def test_convnd_wgrad_split_k_matches_single_pass(plug):
+    # one group, 16 samples: the pixel range is cut over the grid and the fp32 partial sums are folded by a second kernel
+    x, dy = rnd((16, 32, 24, 24), 7).half(), rnd((16, 48, 24, 24), 8).half()
+    dw = plug.wgrad(x, dy, (48, 32, 3, 3), (1, 1), 1)
+    xr = x.double()
+    wr = torch.zeros(48, 32, 3, 3, device=DEV, dtype=torch.float64, requires_grad=True)
+    gw, = torch.autograd.grad(F.conv2d(xr, wr, padding=1), [wr], dy.double())
+    assert float((dw.double() - gw).abs().max()) <= 2e-3 * float(gw.abs().max())
+
+
+def test_convnd_is_used_for_nan_free_padding(plug):
+    # zero * garbage must not leak NaN from uninitialised shared memory or workspace tails into the result
+    for _ in range(3):
+        x, w = rnd((1, 17, 5, 6), 9).half(), rnd((19, 17, 3, 3), 10, 0.1).half()
+        junk = torch.full((1 << 22,), float('nan'), device=DEV)
+        del junk
+        y = plug.fprop(x, w, (2, 2), 1)
+        dw = plug.wgrad(x, torch.ones_like(y), (19, 17, 3, 3), (2, 2), 1)
+        assert torch.isfinite(y).all() and torch.isfinite(dw).all()

@@ -32,7 +32,11 @@ def elementwise(got, want, rtol, what):
     g, w = got.detach().double(), want.detach().double()
     assert torch.isfinite(g).all(), what
     scale = float(w.abs().max())
-    bound = rtol * w.abs() + rtol * FLOOR * scale
+    # fp16 storage: intermediates are rounded at different points on the two sides (e.g. the reference rounds between its two
+    # separable passes, upfirdn2d.py:244-245), an absolute error of a few 1e-4 of the tensor's scale that does not shrink
+    # with the element -> a 10 % floor there
+    floor = FLOOR if got.dtype != torch.float16 else 10 * FLOOR
+    bound = rtol * w.abs() + rtol * floor * scale
     bad = (g - w).abs() > bound
     if bad.any():
         i = int(((g - w).abs() / bound).argmax())
