@@ -222,7 +222,8 @@ int lvg_conv2d_wgrad(const void* x, const void* dy, void* dw, int dtype,
  * networks (generator_lres.py:119,578; discriminator_lres.py:172) and the F.conv1d calls of the low-res discriminator
  * (discriminator_lres.py:108-127).
  *   x [N][G*Cin][T][H][W]   w [G*Cout][Cin][kt][kh][kw]   y [N][G*Cout][To][Ho][Wo]      (dense; 2-D: T = kt = 1)
- * stride 1, kh*kw <= 9, kt <= 7. dtype LVG_F16: fp16 operands, fp32 accumulation, fp16 result. dtype LVG_F32: operands
+ * kh*kw <= 9, kt <= 7; `stride` (1..4) applies to H and W (T: 1) -- a strided forward pass computes the stride-1 result and
+ * stores every stride-th row / column, its gradients spread dy over that lattice. dtype LVG_F16: fp16 operands, fp32 accumulation, fp16 result. dtype LVG_F32: operands
  * split into bf16 hi + lo halves, hi*hi + lo*hi + hi*lo accumulated in fp32 (fp32-grade result, relative error
  * ~2^-16; the reference runs these layers in strict fp32, train_lres.py:269). Optional fused epilogue on fprop:
  * act 0 = none, 1 = (y + bias[co]) * gain clamped, 2 = lrelu(y + bias[co], alpha) * gain clamped (bias_act semantics,
@@ -235,16 +236,16 @@ int lvg_conv2d_wgrad(const void* x, const void* dy, void* dw, int dtype,
 int64_t lvg_convnd_workspace(int dtype, int n, int groups, int cin, int cout, int t, int h, int wd,
                              int kt, int kh, int kw, int pad_t, int pad_h, int pad_w);
 int lvg_convnd_fprop(const void* x, const void* w, void* y, int dtype, int n, int groups, int cin, int cout,
-                     int t, int h, int wd, int kt, int kh, int kw, int pad_t, int pad_h, int pad_w,
+                     int t, int h, int wd, int kt, int kh, int kw, int pad_t, int pad_h, int pad_w, int stride,
                      const float* bias, int act, float alpha, float gain, float clamp,
                      void* workspace, int64_t workspace_bytes, void* stream);
 int lvg_convnd_dgrad(const void* dy, const void* w, void* dx, int dtype, int n, int groups, int cin, int cout,
-                     int t, int h, int wd, int kt, int kh, int kw, int pad_t, int pad_h, int pad_w,
+                     int t, int h, int wd, int kt, int kh, int kw, int pad_t, int pad_h, int pad_w, int stride,
                      void* workspace, int64_t workspace_bytes, void* stream);
 int64_t lvg_convnd_wgrad_workspace(int dtype, int n, int groups, int cin, int cout, int t, int h, int wd,
                                    int kt, int kh, int kw, int pad_t, int pad_h, int pad_w);
 int lvg_convnd_wgrad(const void* x, const void* dy, void* dw, int dtype, int n, int groups, int cin, int cout,
-                     int t, int h, int wd, int kt, int kh, int kw, int pad_t, int pad_h, int pad_w,
+                     int t, int h, int wd, int kt, int kh, int kw, int pad_t, int pad_h, int pad_w, int stride,
                      void* workspace, int64_t workspace_bytes, void* stream);
 
 /*

@@ -57,14 +57,18 @@ struct IgemmParams {
     int kb_wrap;                 // split mode: source block of packed block kb is kb < kb_wrap ? kb : kb - kb_wrap
     int to, ho, wo;              // output extent
     int kt, kh, kw, pad_t, pad_h, pad_w;
-    int th, wt, wtb, thb;        // tile rows / cols, box cols / rows
-    int ncols;                   // accumulator columns (multiple of 16, <= 256)
-    int tmem_cols;               // power of two >= ncols
-    int tiles_x, tiles_y;
+    int tt, th, wt, wtb, thb;    // tile frames / rows / cols, box cols / rows
+    int frame_px;                // thb * wtb: accumulator columns from one frame of the tile to the next
+    int ncols;                   // accumulator columns (multiple of 16, <= 512)
+    int n0;                      // columns of the first MMA of a tap (the second one takes ncols - n0; 0 = single MMA)
+    int nbuf;                    // accumulator buffers in TMEM: 2 when ncols <= 256 (epilogue of tile i overlaps tile i + 1)
+    int tiles_x, tiles_y, tiles_t;
+    int64_t total_tiles;         // tiles_x * tiles_y * tiles_t * mt * instances
     int ks;                      // k-steps per stage (> 1 only when kt == 1)
     int stages;
     int a_stage, b_step, b_bytes, stage_bytes;    // bytes: A per stage, B stride / payload per k-step, whole stage
-    int64_t y_cs;                // output channel stride (= to*ho*wo)
+    int64_t y_cs;                // output channel stride (= to*hos*wos)
+    int ostride, hos, wos;       // output decimation (strided convolution): only rows / columns divisible by ostride are stored
 };
 
 // ------------------------------------------------------------------------------------------------ re-tiling passes
@@ -74,10 +78,15 @@ __device__ __forceinline__ float bf16_val(unsigned short b) { return __uint_as_f
 
 // NC(T)HW -> X8. One thread = one pixel of one channel block: 8 strided reads (coalesced across the warp), one or two
 // 16-byte writes. SPLIT: fp32 in, bf16 hi blocks [0, cblk) and lo blocks [cblk, 2 cblk) out.
+// Dilation (gradients of strided convolutions): input pixel (t, i, j) of an ih x iw image lands at (t, i*dil, j*dil) of
+// the oh x ow output image, which the caller has zeroed.
+struct PackGeom { int64_t thw_in, thw_out; int ih, iw, oh, ow, dil; };
+
 template <class TIn, bool SPLIT>
 __global__ void __launch_bounds__(256) conv_pack_act_kernel(const TIn* __restrict__ x, uint4* __restrict__ y, int64_t inst, int c,
-                                                             int cblk, int64_t thw)
+                                                             int cblk, PackGeom gm)
 {
+    const int64_t thw = gm.thw_in;
     const int64_t total = inst * cblk * thw;
     const int nblk = SPLIT ? 2 * cblk : cblk;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -87,11 +96,19 @@ __global__ void __launch_bounds__(256) conv_pack_act_kernel(const TIn* __restric
         const int64_t in = r / cblk;
         const int c0 = blk * 8;
         const TIn* src = x + ((int64_t)in * c + c0) * thw + p;
+        int64_t po = p;
+        if (gm.dil > 1) {
+            const int j = (int)(p % gm.iw);
+            const int64_t q = p / gm.iw;
+            const int ii = (int)(q % gm.ih);
+            const int64_t t = q / gm.ih;
+            po = (t * gm.oh + (int64_t)ii * gm.dil) * gm.ow + (int64_t)j * gm.dil;
+        }
         if constexpr (!SPLIT) {
             alignas(16) unsigned short v[8];
 #pragma unroll
             for (int j = 0; j < 8; j++) v[j] = (c0 + j < c) ? __half_as_ushort(__ldg(reinterpret_cast<const __half*>(src) + (int64_t)j * thw)) : (unsigned short)0;
-            y[((int64_t)in * nblk + blk) * thw + p] = *reinterpret_cast<const uint4*>(v);
+            y[((int64_t)in * nblk + blk) * gm.thw_out + po] = *reinterpret_cast<const uint4*>(v);
         } else {
             alignas(16) unsigned short hi[8], lo[8];
 #pragma unroll
@@ -100,10 +117,26 @@ __global__ void __launch_bounds__(256) conv_pack_act_kernel(const TIn* __restric
                 hi[j] = bf16_bits(f);
                 lo[j] = bf16_bits(f - bf16_val(hi[j]));
             }
-            y[((int64_t)in * nblk + blk) * thw + p] = *reinterpret_cast<const uint4*>(hi);
-            y[((int64_t)in * nblk + cblk + blk) * thw + p] = *reinterpret_cast<const uint4*>(lo);
+            y[((int64_t)in * nblk + blk) * gm.thw_out + po] = *reinterpret_cast<const uint4*>(hi);
+            y[((int64_t)in * nblk + cblk + blk) * gm.thw_out + po] = *reinterpret_cast<const uint4*>(lo);
         }
     }
+}
+
+// launches the re-tiling of one activation tensor (zeroing the target first when it is dilated)
+int pack_act(const void* x, void* x8, int split, int64_t inst, int c, int cblk, int t, int ih, int iw, int oh, int ow, int dil, cudaStream_t s)
+{
+    PackGeom gm;
+    gm.thw_in = (int64_t)t * ih * iw; gm.thw_out = (int64_t)t * oh * ow; gm.ih = ih; gm.iw = iw; gm.oh = oh; gm.ow = ow; gm.dil = dil;
+    if (dil > 1) LVG_CUDA(cudaMemsetAsync(x8, 0, (size_t)(inst * (split ? 2 : 1) * cblk * gm.thw_out * 16), s));
+    const int64_t total = inst * cblk * gm.thw_in;
+    int64_t blocks = (total + 255) / 256;
+    const int64_t cap = (int64_t)num_sms() * 64;
+    if (blocks > cap) blocks = cap;
+    if (split) conv_pack_act_kernel<float, true><<<(unsigned)blocks, 256, 0, s>>>((const float*)x, (uint4*)x8, inst, c, cblk, gm);
+    else conv_pack_act_kernel<__half, false><<<(unsigned)blocks, 256, 0, s>>>((const __half*)x, (uint4*)x8, inst, c, cblk, gm);
+    LVG_LAUNCH_CHECK();
+    return LVG_OK;
 }
 
 // weights -> tile images.  Element (m, k, tap) of the logical A matrix of group g sits at
@@ -112,45 +145,60 @@ __global__ void __launch_bounds__(256) conv_pack_act_kernel(const TIn* __restric
 // Image of one 128 x 16 tile (K-major, no swizzle): byte offset(m, k) = (k/8)*2048 + (m/8)*128 + (m%8)*16 + (k%8)*2.
 // SPLIT: the packed K axis is three segments of kpad channels [hi | hi | lo], matching the activation blocks
 // [hi | lo | hi] visited by the main loop: hi*hi + lo*hi + hi*lo.
+// One CTA = one (group, m-tile, k-step): the 128 x 16 x taps source elements are read in memory order (coalesced) into
+// shared memory and leave as whole 16-byte image rows, consecutive threads writing consecutive rows.
 template <class TIn, bool SPLIT>
-__global__ void __launch_bounds__(256) conv_pack_w_kernel(const TIn* __restrict__ w, unsigned char* __restrict__ wp, int groups, int m_total,
-                                                           int k_total, int kpad, int taps, int64_t gstride, int64_t sm, int64_t sk, int flip,
-                                                           int mt, int kc)
+__global__ void __launch_bounds__(256) conv_pack_w_kernel(const TIn* __restrict__ w, unsigned char* __restrict__ wp, int m_total, int k_total,
+                                                           int kpad, int taps, int64_t gstride, int64_t sm, int64_t sk, int flip, int mt, int kc,
+                                                           int rows_per_pass)
 {
-    const int64_t total = (int64_t)groups * mt * kc * taps * (kATile / 16);
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        int64_t r = i;
-        const int tap = (int)(r % taps); r /= taps;
-        const int k8 = (int)(r % 2); r /= 2;
-        const int mrow = (int)(r % kBM); r /= kBM;
-        const int kci = (int)(r % kc); r /= kc;
-        const int mti = (int)(r % mt);
-        const int g = (int)(r / mt);
-        const int m = mti * kBM + mrow;
-        const int kp0 = kci * 16 + k8 * 8;              // packed k of the first element
-        const int seg = SPLIT ? kp0 / kpad : 0;
-        const int k0 = SPLIT ? kp0 - seg * kpad : kp0;
-        const int wtap = flip ? taps - 1 - tap : tap;
-        alignas(16) unsigned short v[8];
+    extern __shared__ float sw[];                    // [rows_per_pass][16 * taps + 1]
+    const int pitch = 16 * taps + 1;
+    const int kci = blockIdx.x % kc;
+    const int mti = (blockIdx.x / kc) % mt;
+    const int g = blockIdx.x / (kc * mt);
+    const int kp0 = kci * 16;                        // packed k of the chunk
+    const int seg = SPLIT ? kp0 / kpad : 0;
+    const int k0 = SPLIT ? kp0 - seg * kpad : kp0;
+    const TIn* wg = w + (int64_t)g * gstride;
+    unsigned char* dst0 = wp + ((((int64_t)g * mt + mti) * kc + kci) * taps) * kATile;
+    for (int r0 = 0; r0 < kBM; r0 += rows_per_pass) {
+        const int R = min(rows_per_pass, kBM - r0);
+        const int m0 = mti * kBM + r0;
+        const int n_el = R * 16 * taps;
+        if (sk < sm) {                               // rows of m: (k, tap) contiguous
+            for (int e = threadIdx.x; e < n_el; e += 256) {
+                const int tap = e % taps, k = (e / taps) % 16, m = e / (16 * taps);
+                float v = 0.f;
+                if (m0 + m < m_total && k0 + k < k_total) v = (float)wg[(int64_t)(m0 + m) * sm + (int64_t)(k0 + k) * sk + tap];
+                sw[m * pitch + k * taps + tap] = v;
+            }
+        } else {                                     // rows of k: (m, tap) contiguous
+            for (int e = threadIdx.x; e < n_el; e += 256) {
+                const int tap = e % taps, m = (e / taps) % R, k = e / (R * taps);
+                float v = 0.f;
+                if (m0 + m < m_total && k0 + k < k_total) v = (float)wg[(int64_t)(k0 + k) * sk + (int64_t)(m0 + m) * sm + tap];
+                sw[m * pitch + k * taps + tap] = v;
+            }
+        }
+        __syncthreads();
+        for (int o = threadIdx.x; o < taps * 2 * R; o += 256) {
+            const int mrow = o % R, k8 = (o / R) % 2, tap = o / (2 * R);
+            const int wtap = flip ? taps - 1 - tap : tap;
+            alignas(16) unsigned short v[8];
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
-            const int k = k0 + j;
-            unsigned short o = 0;
-            if (m < m_total && k < k_total) {
-                const TIn e = w[(int64_t)g * gstride + (int64_t)m * sm + (int64_t)k * sk + wtap];
+            for (int j = 0; j < 8; j++) {
+                const float f = sw[mrow * pitch + (k8 * 8 + j) * taps + wtap];
                 if constexpr (SPLIT) {
-                    const float f = (float)e;
                     const unsigned short h = bf16_bits(f);
-                    o = seg == 2 ? bf16_bits(f - bf16_val(h)) : h;
+                    v[j] = seg == 2 ? bf16_bits(f - bf16_val(h)) : h;
                 } else {
-                    o = __half_as_ushort(e);
+                    v[j] = __half_as_ushort(__float2half_rn(f));       // exact: the source is fp16
                 }
             }
-            v[j] = o;
+            *reinterpret_cast<uint4*>(dst0 + (size_t)tap * kATile + k8 * 2048 + (r0 + mrow) * 16) = *reinterpret_cast<const uint4*>(v);
         }
-        const int64_t tile = (((int64_t)g * mt + mti) * kc + kci) * taps + tap;
-        unsigned char* dst = wp + tile * kATile + k8 * 2048 + (mrow / 8) * 128 + (mrow % 8) * 16;
-        *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(v);
+        __syncthreads();
     }
 }
 
@@ -163,120 +211,138 @@ __device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* map, i
                  : "memory");
 }
 
-template <int NCOLS>
-__device__ __forceinline__ void tmem_alloc_n(uint32_t* slot)
+struct TileCoord { int ox0, oy0, t0, mti, inst; };
+
+__device__ __forceinline__ TileCoord decode_tile(const IgemmParams& p, int64_t L)
 {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "n"(NCOLS) : "memory");
+    TileCoord c;
+    int64_t r = L;
+    c.ox0 = (int)(r % p.tiles_x) * p.wt; r /= p.tiles_x;
+    c.oy0 = (int)(r % p.tiles_y) * p.th; r /= p.tiles_y;
+    c.t0 = (int)(r % p.tiles_t) * p.tt; r /= p.tiles_t;
+    c.mti = (int)(r % p.mt);
+    c.inst = (int)(r / p.mt);
+    return c;
 }
 
-__global__ void __launch_bounds__(kThreads, 2) conv_igemm_kernel(const __grid_constant__ CUtensorMap tmx, const IgemmParams p)
+// Persistent: CTA b works on tiles b, b + gridDim.x, ... (pixel tile fastest, so that concurrently running CTAs share the
+// weight tiles of one (instance, m-tile) in L2). The operand ring runs across tile boundaries; with <= 256 accumulator
+// columns two TMEM buffers alternate, so the epilogue of tile i overlaps the main loop of tile i + 1.
+__global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_constant__ CUtensorMap tmx, const IgemmParams p)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ uint64_t full_bar[kMaxStages], empty_bar[kMaxStages], acc_bar;
+    __shared__ uint64_t full_bar[kMaxStages], empty_bar[kMaxStages], acc_full[2], acc_empty[2];
     __shared__ uint32_t tmem_slot;
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
 
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-    int tile = blockIdx.x;
-    const int tx = tile % p.tiles_x; tile /= p.tiles_x;
-    const int ty = tile % p.tiles_y;
-    const int t = tile / p.tiles_y;
-    const int mti = blockIdx.y, inst = blockIdx.z;
-    const int ox0 = tx * p.wt, oy0 = ty * p.th;
     const int taps2 = p.kh * p.kw;
     const int kchunks = (p.kc + p.ks - 1) / p.ks;
-    const int iters = p.kt * kchunks;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.stages; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        mbar_init(&acc_bar, 1);
+        for (int b = 0; b < 2; b++) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 4); }
         fence_barrier_init();
     }
     if (warp == 1) {
-        if (p.tmem_cols <= 32) tmem_alloc_n<32>(&tmem_slot);
-        else if (p.tmem_cols <= 64) tmem_alloc_n<64>(&tmem_slot);
-        else if (p.tmem_cols <= 128) tmem_alloc_n<128>(&tmem_slot);
-        else tmem_alloc_n<256>(&tmem_slot);
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_slot)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_d = tmem_slot;
+    const uint32_t tmem_base = tmem_slot;
 
     if (warp == 0) {
         if (lane == 0) {
-            const unsigned char* wpg = p.wp + (((int64_t)(inst % p.wgroups) * p.mt + mti) * p.kc) * (int64_t)(p.kt * taps2) * kATile;
-            const int blk0 = inst * p.nblk;
             int it = 0;
-            for (int kt = 0; kt < p.kt; kt++) {
-                for (int kcix = 0; kcix < kchunks; kcix++, it++) {
-                    const int s = it % p.stages;
-                    if (it >= p.stages) mbar_wait(&empty_bar[s], (uint32_t)((it / p.stages - 1) & 1));
-                    unsigned char* st = smem + (size_t)s * p.stage_bytes;
-                    const int k0 = kcix * p.ks;
-                    const int nks = min(p.ks, p.kc - k0);
-                    const uint32_t a_bytes = (uint32_t)(nks * taps2 * kATile);
-                    mbar_expect_tx(&full_bar[s], a_bytes + (uint32_t)(nks * p.b_bytes));
-                    // A: kt == 1 -> the nks steps' tiles are contiguous; kt > 1 -> ks == 1, the taps of this kt are contiguous
-                    bulk_copy_g2s(st, wpg + ((int64_t)k0 * p.kt + kt) * (int64_t)taps2 * kATile, a_bytes, &full_bar[s]);
-                    for (int j = 0; j < nks; j++) {
-                        const int kb = (k0 + j) * 2;
-                        const int sb = kb < p.kb_wrap ? kb : kb - p.kb_wrap;
-                        tma_load_5d(st + p.a_stage + (size_t)j * p.b_step, &tmx, 0, ox0 - p.pad_w, oy0 - p.pad_h, t + kt - p.pad_t, blk0 + sb,
-                                    &full_bar[s]);
+            for (int64_t L = blockIdx.x; L < p.total_tiles; L += gridDim.x) {
+                const TileCoord c = decode_tile(p, L);
+                const unsigned char* wpg = p.wp + (((int64_t)(c.inst % p.wgroups) * p.mt + c.mti) * p.kc) * (int64_t)(p.kt * taps2) * kATile;
+                const int blk0 = c.inst * p.nblk;
+                for (int kt = 0; kt < p.kt; kt++) {
+                    for (int kcix = 0; kcix < kchunks; kcix++, it++) {
+                        const int s = it % p.stages;
+                        if (it >= p.stages) mbar_wait(&empty_bar[s], (uint32_t)((it / p.stages - 1) & 1));
+                        unsigned char* st = smem + (size_t)s * p.stage_bytes;
+                        const int k0 = kcix * p.ks;
+                        const int nks = min(p.ks, p.kc - k0);
+                        const uint32_t a_bytes = (uint32_t)(nks * taps2 * kATile);
+                        mbar_expect_tx(&full_bar[s], a_bytes + (uint32_t)(nks * p.b_bytes));
+                        // A: kt == 1 -> the nks steps' tiles are contiguous; kt > 1 -> ks == 1, the taps of this kt are contiguous
+                        bulk_copy_g2s(st, wpg + ((int64_t)k0 * p.kt + kt) * (int64_t)taps2 * kATile, a_bytes, &full_bar[s]);
+                        for (int j = 0; j < nks; j++) {
+                            const int kb = (k0 + j) * 2;
+                            const int sb = kb < p.kb_wrap ? kb : kb - p.kb_wrap;
+                            tma_load_5d(st + p.a_stage + (size_t)j * p.b_step, &tmx, 0, c.ox0 - p.pad_w, c.oy0 - p.pad_h, c.t0 + kt - p.pad_t,
+                                        blk0 + sb, &full_bar[s]);
+                        }
                     }
                 }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            // instruction descriptor: D = f32, A and B K-major, fp16 or bf16 operands, N >> 3, M >> 4
-            const uint32_t idesc = (1u << 4) | (p.bf16 ? ((1u << 7) | (1u << 10)) : 0u) | ((uint32_t)(p.ncols >> 3) << 17) |
-                                   ((uint32_t)(kBM >> 4) << 24);
+            // instruction descriptors: D = f32, A and B K-major, fp16 or bf16 operands, N >> 3, M >> 4
+            const uint32_t ibase = (1u << 4) | (p.bf16 ? ((1u << 7) | (1u << 10)) : 0u) | ((uint32_t)(kBM >> 4) << 24);
+            const int na = p.n0 > 0 ? p.n0 : p.ncols, nb = p.n0 > 0 ? p.ncols - p.n0 : 0;
+            const uint32_t idesc_a = ibase | ((uint32_t)(na >> 3) << 17), idesc_b = ibase | ((uint32_t)(nb >> 3) << 17);
             const uint32_t blk_bytes = (uint32_t)p.b_bytes / 2;
-            int it = 0;
-            for (int kt = 0; kt < p.kt; kt++) {
-                for (int kcix = 0; kcix < kchunks; kcix++, it++) {
-                    const int s = it % p.stages;
-                    mbar_wait(&full_bar[s], (uint32_t)((it / p.stages) & 1));
-                    tc_fence_after();
-                    const uint32_t st = smem_u32(smem + (size_t)s * p.stage_bytes);
-                    const int nks = min(p.ks, p.kc - kcix * p.ks);
-                    for (int j = 0; j < nks; j++) {
-                        const uint32_t a0 = st + (uint32_t)(j * taps2) * kATile;
-                        const uint32_t b0 = st + (uint32_t)p.a_stage + (uint32_t)j * (uint32_t)p.b_step;
-                        for (int ky = 0; ky < p.kh; ky++) {
-                            for (int kx = 0; kx < p.kw; kx++) {
-                                const uint64_t adesc = make_desc(a0 + (uint32_t)(ky * p.kw + kx) * kATile, 2048, 128);
-                                const uint64_t bdesc = make_desc(b0 + (uint32_t)(ky * p.wtb + kx) * 16, blk_bytes, 128);
-                                umma_f16(tmem_d, adesc, bdesc, idesc, (it > 0 || j > 0 || ky > 0 || kx > 0) ? 1u : 0u);
+            int it = 0, i = 0;
+            for (int64_t L = blockIdx.x; L < p.total_tiles; L += gridDim.x, i++) {
+                const int buf = i % p.nbuf;
+                if (i >= p.nbuf) mbar_wait(&acc_empty[buf], (uint32_t)((i / p.nbuf - 1) & 1));
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + (uint32_t)buf * 256;
+                bool first = true;
+                for (int kt = 0; kt < p.kt; kt++) {
+                    for (int kcix = 0; kcix < kchunks; kcix++, it++) {
+                        const int s = it % p.stages;
+                        mbar_wait(&full_bar[s], (uint32_t)((it / p.stages) & 1));
+                        tc_fence_after();
+                        const uint32_t st = smem_u32(smem + (size_t)s * p.stage_bytes);
+                        const int nks = min(p.ks, p.kc - kcix * p.ks);
+                        for (int j = 0; j < nks; j++) {
+                            const uint32_t a0 = st + (uint32_t)(j * taps2) * kATile;
+                            const uint32_t b0 = st + (uint32_t)p.a_stage + (uint32_t)j * (uint32_t)p.b_step;
+                            for (int ky = 0; ky < p.kh; ky++) {
+                                for (int kx = 0; kx < p.kw; kx++) {
+                                    const uint64_t adesc = make_desc(a0 + (uint32_t)(ky * p.kw + kx) * kATile, 2048, 128);
+                                    const uint32_t bs = b0 + (uint32_t)(ky * p.wtb + kx) * 16;
+                                    umma_f16(tmem_d, adesc, make_desc(bs, blk_bytes, 128), idesc_a, first ? 0u : 1u);
+                                    if (nb > 0) umma_f16(tmem_d + (uint32_t)na, adesc, make_desc(bs + (uint32_t)na * 16, blk_bytes, 128), idesc_b, first ? 0u : 1u);
+                                    first = false;
+                                }
                             }
                         }
+                        umma_commit(&empty_bar[s]);
                     }
-                    umma_commit(&empty_bar[s]);
                 }
+                umma_commit(&acc_full[buf]);
             }
-            umma_commit(&acc_bar);
         }
     } else {
-        // ---- epilogue warps: TMEM lane quadrant = warp % 4
-        mbar_wait(&acc_bar, 0);
-        tc_fence_after();
+        // ---- epilogue warps: TMEM lane quadrant = warp % 4; each warp owns 32 output channels of the tile and a private
+        // 32 x 33 transposition buffer so that a store instruction covers 32 consecutive pixels of one channel
         const int q = warp % 4;
-        const int m = mti * kBM + q * 32 + lane;
-        const bool mok = m < p.cout;
-        const int64_t ch = (int64_t)inst * p.cout + m;
-        const float b = (p.bias != nullptr && mok) ? __ldg(p.bias + (int64_t)(inst % p.wgroups) * p.cout + m) : 0.f;
-        const int64_t plane = ch * p.y_cs + (int64_t)t * p.ho * p.wo;
-        for (int n0 = 0; n0 < p.ncols; n0 += 32) {
-            uint32_t acc[32];
-            tmem_ld32(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)n0, acc);
-            int r = n0 / p.wtb, c = n0 - r * p.wtb;
+        float* sT = reinterpret_cast<float*>(smem + (size_t)p.stages * p.stage_bytes + 512) + (warp - 2) * (32 * 33);
+        int i = 0;
+        for (int64_t L = blockIdx.x; L < p.total_tiles; L += gridDim.x, i++) {
+            const TileCoord c = decode_tile(p, L);
+            const int buf = i % p.nbuf;
+            mbar_wait(&acc_full[buf], (uint32_t)((i / p.nbuf) & 1));
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_base + (uint32_t)buf * 256;
+            const int m_lane = c.mti * kBM + q * 32 + lane;         // this lane's channel while the values are in registers
+            const float b = (p.bias != nullptr && m_lane < p.cout) ? __ldg(p.bias + (int64_t)(c.inst % p.wgroups) * p.cout + m_lane) : 0.f;
+            const int m0 = c.mti * kBM + q * 32;
+            const int rows_ok = min(32, p.cout - m0);               // channels of this warp that exist
+            const int64_t ch0 = ((int64_t)c.inst * p.cout + m0) * p.y_cs;
+            for (int n0 = 0; n0 < p.ncols; n0 += 32) {
+                uint32_t acc[32];
+                tmem_ld32(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)n0, acc);
 #pragma unroll
-            for (int j = 0; j < 32; j++) {
-                const int oy = oy0 + r, ox = ox0 + c;
-                if (mok && c < p.wt && r < p.th && oy < p.ho && ox < p.wo) {
+                for (int j = 0; j < 32; j++) {
                     float v = __uint_as_float(acc[j]);
                     if (p.act) {
                         v += b;
@@ -284,22 +350,41 @@ __global__ void __launch_bounds__(kThreads, 2) conv_igemm_kernel(const __grid_co
                         v *= p.gain;
                         if (p.clamp >= 0.f) v = fminf(fmaxf(v, -p.clamp), p.clamp);
                     }
-                    const int64_t o = plane + (int64_t)oy * p.wo + ox;
-                    if (p.out_f32) reinterpret_cast<float*>(p.y)[o] = v;
-                    else reinterpret_cast<__half*>(p.y)[o] = __float2half_rn(v);
+                    sT[j * 33 + lane] = v;
                 }
-                if (++c == p.wtb) { c = 0; ++r; }
+                __syncwarp();
+                // lane = accumulator column n0 + lane -> (frame, row, col) of the tile
+                const int n = n0 + lane;
+                const int f = n / p.frame_px, rem = n - f * p.frame_px;
+                const int r = rem / p.wtb, cc = rem - r * p.wtb;
+                const int ot = c.t0 + f, oy = c.oy0 + r, ox = c.ox0 + cc;
+                bool ok = n < p.ncols && f < p.tt && r < p.th && cc < p.wt && ot < p.to && oy < p.ho && ox < p.wo;
+                int64_t off;
+                if (p.ostride == 1) {
+                    off = ch0 + ((int64_t)ot * p.ho + oy) * p.wo + ox;
+                } else {
+                    ok = ok && (oy % p.ostride == 0) && (ox % p.ostride == 0);
+                    off = ch0 + ((int64_t)ot * p.hos + oy / p.ostride) * p.wos + ox / p.ostride;
+                }
+                if (ok) {
+                    if (p.out_f32) {
+                        float* y = reinterpret_cast<float*>(p.y) + off;
+                        for (int row = 0; row < rows_ok; row++) y[(int64_t)row * p.y_cs] = sT[lane * 33 + row];
+                    } else {
+                        __half* y = reinterpret_cast<__half*>(p.y) + off;
+                        for (int row = 0; row < rows_ok; row++) y[(int64_t)row * p.y_cs] = __float2half_rn(sT[lane * 33 + row]);
+                    }
+                }
+                __syncwarp();
             }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[buf]);
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) {
-        if (p.tmem_cols <= 32) tmem_dealloc(tmem_d, 32);
-        else if (p.tmem_cols <= 64) tmem_dealloc(tmem_d, 64);
-        else if (p.tmem_cols <= 128) tmem_dealloc(tmem_d, 128);
-        else tmem_dealloc(tmem_d, 256);
-    }
+    if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -342,9 +427,12 @@ Geometry geometry(int split, int64_t inst, int groups, int ck, int cm, int64_t t
 }
 
 // shared driver of fprop and dgrad: `x` has `ck` channels per group, `y` gets `cm`; logical A[m][k][tap] = w[g*gs + m*sm + k*sk + tap']
+// `dil` > 1: x is given as an xin_h x xin_w image that is placed on every dil-th pixel of the h x wd grid (input gradient of
+// a strided convolution); `ostride` > 1: only every ostride-th output row / column is stored (strided forward convolution).
 int run_igemm(const void* x, const void* w, void* y, int dtype, int n, int groups, int ck, int cm, int t, int h, int wd, int kt, int kh,
               int kw, int pad_t, int pad_h, int pad_w, int64_t w_gs, int64_t w_sm, int64_t w_sk, int flip, const float* bias, int act,
-              float alpha, float gain, float clamp, void* workspace, int64_t workspace_bytes, cudaStream_t s)
+              float alpha, float gain, float clamp, int xin_h, int xin_w, int dil, int ostride, void* workspace, int64_t workspace_bytes,
+              cudaStream_t s)
 {
     const int split = dtype == LVG_F32 ? 1 : 0;
     const int taps = kt * kh * kw;
@@ -353,7 +441,6 @@ int run_igemm(const void* x, const void* w, void* y, int dtype, int n, int group
     const Geometry g = geometry(split, inst, groups, ck, cm, thw, taps);
     LVG_REQUIRE(workspace && workspace_bytes >= g.act_bytes + g.w_bytes + 256, "convnd: workspace too small");
     LVG_REQUIRE(aligned16(workspace), "convnd: workspace must be 16-byte aligned");
-    LVG_REQUIRE(inst <= 65535 && g.mt <= 65535, "convnd: too many instances / channel tiles for one launch");
     LVG_REQUIRE(inst * g.nblk < (1ll << 31), "convnd: too many channel blocks for a tensor map");
     EncodeTiledFn enc = encode_fn();
     LVG_REQUIRE(enc != nullptr, "convnd: cuTensorMapEncodeTiled is not available from this driver");
@@ -370,50 +457,73 @@ int run_igemm(const void* x, const void* w, void* y, int dtype, int n, int group
     p.to = t + 2 * pad_t - kt + 1; p.ho = h + 2 * pad_h - kh + 1; p.wo = wd + 2 * pad_w - kw + 1;
     LVG_REQUIRE(p.to >= 1 && p.ho >= 1 && p.wo >= 1, "convnd: empty output");
     p.kt = kt; p.kh = kh; p.kw = kw; p.pad_t = pad_t; p.pad_h = pad_h; p.pad_w = pad_w;
-    // tile: as many whole rows as fit 256 accumulator columns; wide images are cut into column tiles
+    // tile: whole rows (and, for small frames, several frames) up to 512 accumulator columns; wide images are cut into
+    // column tiles. A tile of <= 256 columns leaves room for two accumulator buffers (epilogue overlap).
+    // (short K loops are epilogue-bound: they take <= 256 columns and alternate two accumulator buffers)
+    const int col_budget = (g.kc * kt <= 12) ? 256 : 512;
     const int max_wt = 256 - (kw - 1);
     p.tiles_x = (p.wo + max_wt - 1) / max_wt;
     p.wt = (p.wo + p.tiles_x - 1) / p.tiles_x;
     p.wtb = p.wt + kw - 1;
-    p.th = 256 / p.wtb;
+    p.th = col_budget / p.wtb;
     if (p.th > p.ho) p.th = p.ho;
     if (p.th < 1) p.th = 1;
     p.tiles_y = (p.ho + p.th - 1) / p.th;
     p.th = (p.ho + p.tiles_y - 1) / p.tiles_y;               // balance the row tiles
+    p.ostride = ostride;
+    p.hos = (p.ho - 1) / ostride + 1; p.wos = (p.wo - 1) / ostride + 1;
+    if (ostride > 1) {                                         // tile origins on the output lattice
+        if (p.tiles_x > 1) { p.wt = round_up(p.wt, ostride); p.wtb = p.wt + kw - 1; p.tiles_x = (p.wo + p.wt - 1) / p.wt; if (p.th * p.wtb > col_budget) p.th = col_budget / p.wtb; }
+        if (p.th < p.ho) { p.th = p.th / ostride * ostride; if (p.th < ostride) p.th = ostride; }
+        p.tiles_y = (p.ho + p.th - 1) / p.th;
+        LVG_REQUIRE(p.th * p.wtb <= 512, "convnd: strided tile does not fit");
+    }
     p.thb = p.th + kh - 1;
-    p.ncols = round_up(p.th * p.wtb, 16);
-    LVG_REQUIRE(p.th >= 1 && p.ncols <= 256 && p.ncols >= 16, "convnd: tile geometry");
-    p.tmem_cols = p.ncols <= 32 ? 32 : p.ncols <= 64 ? 64 : p.ncols <= 128 ? 128 : 256;
-    // TMA writes the two 8-channel blocks of a k-step densely: block 1 starts thb*wtb*16 bytes after block 0 (= LBO);
+    p.frame_px = p.thb * p.wtb;
+    p.tt = 1;
+    if (p.tiles_y == 1 && p.tiles_x == 1) {                    // whole frames: take as many as fit
+        while (p.tt < p.to && p.tt * p.frame_px + p.th * p.wtb <= col_budget && p.tt < 64) p.tt++;
+    }
+    p.tiles_t = (p.to + p.tt - 1) / p.tt;
+    p.tt = (p.to + p.tiles_t - 1) / p.tiles_t;
+    p.ncols = round_up((p.tt - 1) * p.frame_px + p.th * p.wtb, 16);
+    LVG_REQUIRE(p.th >= 1 && p.ncols <= 512 && p.ncols >= 16, "convnd: tile geometry");
+    p.nbuf = p.ncols <= 256 ? 2 : 1;
+    p.n0 = p.ncols <= 256 ? 0 : round_up(p.ncols / 2, 16);
+    // TMA writes the two 8-channel blocks of a k-step densely: block 1 starts tt*thb*wtb*16 bytes after block 0 (= LBO);
     // the k-steps of a stage start at 128-byte multiples (TMA destination alignment)
-    p.b_bytes = 2 * p.thb * p.wtb * 16;
+    p.b_bytes = 2 * p.tt * p.frame_px * 16;
     p.b_step = round_up(p.b_bytes, 128);
     const int taps2 = kh * kw;
     p.ks = (kt == 1) ? (taps2 == 1 ? 4 : (taps2 <= 3 ? 2 : 1)) : 1;
     if (p.ks > g.kc) p.ks = g.kc;
     p.a_stage = p.ks * taps2 * kATile;
     p.stage_bytes = round_up(p.a_stage + p.ks * p.b_step + 512, 128);      // + slack: the last taps read a few pixels past the tile
+    const int epi_bytes = 4 * 32 * 33 * 4 + 512;
     p.stages = 2;
-    const int smem_budget = 100 * 1024;
+    const int smem_budget = 200 * 1024 - epi_bytes;
     while (p.stages < kMaxStages && (p.stages + 1) * p.stage_bytes <= smem_budget) p.stages++;
-    LVG_REQUIRE(p.stages * p.stage_bytes <= 200 * 1024, "convnd: stage does not fit shared memory (%d bytes)", p.stage_bytes);
-    p.y_cs = (int64_t)p.to * p.ho * p.wo;
-    LVG_REQUIRE((int64_t)p.tiles_x * p.tiles_y * p.to < (1ll << 31), "convnd: too many tiles");
+    LVG_REQUIRE(p.stages * p.stage_bytes <= smem_budget + 16 * 1024, "convnd: stage does not fit shared memory (%d bytes)", p.stage_bytes);
+    p.y_cs = (int64_t)p.to * p.hos * p.wos;
+    p.total_tiles = (int64_t)p.tiles_x * p.tiles_y * p.tiles_t * g.mt * inst;
 
     // re-tile the operands
     {
-        const int64_t total = inst * g.cblk * thw;
-        int64_t blocks = (total + 255) / 256;
-        const int64_t cap = (int64_t)num_sms() * 64;
-        if (blocks > cap) blocks = cap;
-        if (split) conv_pack_act_kernel<float, true><<<(unsigned)blocks, 256, 0, s>>>((const float*)x, (uint4*)x8, inst, ck, g.cblk, thw);
-        else conv_pack_act_kernel<__half, false><<<(unsigned)blocks, 256, 0, s>>>((const __half*)x, (uint4*)x8, inst, ck, g.cblk, thw);
-        LVG_LAUNCH_CHECK();
-        const int64_t wtotal = g.w_bytes / 16;
-        blocks = (wtotal + 255) / 256;
-        if (blocks > cap) blocks = cap;
-        if (split) conv_pack_w_kernel<float, true><<<(unsigned)blocks, 256, 0, s>>>((const float*)w, wp, groups, cm, ck, g.cpad, taps, w_gs, w_sm, w_sk, flip, g.mt, g.kc);
-        else conv_pack_w_kernel<__half, false><<<(unsigned)blocks, 256, 0, s>>>((const __half*)w, wp, groups, cm, ck, g.cpad, taps, w_gs, w_sm, w_sk, flip, g.mt, g.kc);
+        const int rc = pack_act(x, x8, split, inst, ck, g.cblk, t, xin_h, xin_w, h, wd, dil, s);
+        if (rc) return rc;
+        const int64_t wblocks = (int64_t)groups * g.mt * g.kc;
+        LVG_REQUIRE(wblocks < (1ll << 31), "convnd: too many weight tiles");
+        int rpp = (int)((96 * 1024) / ((16 * taps + 1) * sizeof(float))) / 8 * 8;       // rows per pass: <= 96 KB of staging
+        if (rpp > kBM) rpp = kBM;
+        if (rpp < 8) rpp = 8;
+        const size_t wsm = (size_t)rpp * (16 * taps + 1) * sizeof(float);
+        if (split) {
+            LVG_CUDA(cudaFuncSetAttribute(conv_pack_w_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsm));
+            conv_pack_w_kernel<float, true><<<(unsigned)wblocks, 256, wsm, s>>>((const float*)w, wp, cm, ck, g.cpad, taps, w_gs, w_sm, w_sk, flip, g.mt, g.kc, rpp);
+        } else {
+            LVG_CUDA(cudaFuncSetAttribute(conv_pack_w_kernel<__half, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsm));
+            conv_pack_w_kernel<__half, false><<<(unsigned)wblocks, 256, wsm, s>>>((const __half*)w, wp, cm, ck, g.cpad, taps, w_gs, w_sm, w_sk, flip, g.mt, g.kc, rpp);
+        }
         LVG_LAUNCH_CHECK();
     }
 
@@ -422,17 +532,17 @@ int run_igemm(const void* x, const void* w, void* y, int dtype, int n, int group
     {
         const cuuint64_t dims[5] = {8, (cuuint64_t)wd, (cuuint64_t)h, (cuuint64_t)t, (cuuint64_t)(inst * g.nblk)};
         const cuuint64_t strides[4] = {16, (cuuint64_t)wd * 16, (cuuint64_t)h * wd * 16, (cuuint64_t)thw * 16};
-        const cuuint32_t box[5] = {8, (cuuint32_t)p.wtb, (cuuint32_t)p.thb, 1, 2};
+        const cuuint32_t box[5] = {8, (cuuint32_t)p.wtb, (cuuint32_t)p.thb, (cuuint32_t)p.tt, 2};
         const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-        LVG_REQUIRE(p.wtb <= 256 && p.thb <= 256, "convnd: TMA box too large");
+        LVG_REQUIRE(p.wtb <= 256 && p.thb <= 256 && p.tt <= 256, "convnd: TMA box too large");
         const CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT16, 5, x8, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         LVG_REQUIRE(r == CUDA_SUCCESS, "convnd: cuTensorMapEncodeTiled failed (%d)", (int)r);
     }
-    const size_t smem = (size_t)p.stages * p.stage_bytes + 128;
+    const size_t smem = (size_t)p.stages * p.stage_bytes + epi_bytes + 128;
     LVG_CUDA(cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid((unsigned)(p.tiles_x * p.tiles_y * p.to), (unsigned)g.mt, (unsigned)inst);
-    conv_igemm_kernel<<<grid, kThreads, smem, s>>>(tm, p);
+    int64_t ctas = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
+    conv_igemm_kernel<<<(unsigned)ctas, kThreads, smem, s>>>(tm, p);
     LVG_LAUNCH_CHECK();
     return LVG_OK;
 }
@@ -463,33 +573,37 @@ extern "C" int64_t lvg_convnd_workspace(int dtype, int n, int groups, int cin, i
 }
 
 extern "C" int lvg_convnd_fprop(const void* x, const void* w, void* y, int dtype, int n, int groups, int cin, int cout, int t, int h, int wd,
-                                int kt, int kh, int kw, int pad_t, int pad_h, int pad_w, const float* bias, int act, float alpha, float gain,
-                                float clamp, void* workspace, int64_t workspace_bytes, void* stream)
+                                int kt, int kh, int kw, int pad_t, int pad_h, int pad_w, int stride, const float* bias, int act, float alpha,
+                                float gain, float clamp, void* workspace, int64_t workspace_bytes, void* stream)
 {
     LVG_REQUIRE(x && w && y, "convnd_fprop: x, w, y must not be NULL");
-    if (!nd_supported(dtype, kt, kh, kw) || n < 1 || pad_t < 0 || pad_h < 0 || pad_w < 0) {
+    if (!nd_supported(dtype, kt, kh, kw) || n < 1 || pad_t < 0 || pad_h < 0 || pad_w < 0 || stride < 1 || stride > 4) {
         set_error("convnd_fprop: outside the tensor-core kernel's envelope");
         return LVG_UNSUPPORTED;
     }
     const int taps = kt * kh * kw;
     return run_igemm(x, w, y, dtype, n, groups, cin, cout, t, h, wd, kt, kh, kw, pad_t, pad_h, pad_w, (int64_t)cout * cin * taps,
-                     (int64_t)cin * taps, taps, 0, bias, act, alpha, gain, clamp, workspace, workspace_bytes, (cudaStream_t)stream);
+                     (int64_t)cin * taps, taps, 0, bias, act, alpha, gain, clamp, h, wd, 1, stride, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 extern "C" int lvg_convnd_dgrad(const void* dy, const void* w, void* dx, int dtype, int n, int groups, int cin, int cout, int t, int h, int wd,
-                                int kt, int kh, int kw, int pad_t, int pad_h, int pad_w, void* workspace, int64_t workspace_bytes, void* stream)
+                                int kt, int kh, int kw, int pad_t, int pad_h, int pad_w, int stride, void* workspace, int64_t workspace_bytes,
+                                void* stream)
 {
     LVG_REQUIRE(dy && w && dx, "convnd_dgrad: dy, w, dx must not be NULL");
-    if (!nd_supported(dtype, kt, kh, kw) || n < 1 || pad_t < 0 || pad_h < 0 || pad_w < 0 || pad_t > kt - 1 || pad_h > kh - 1 || pad_w > kw - 1) {
+    if (!nd_supported(dtype, kt, kh, kw) || n < 1 || pad_t < 0 || pad_h < 0 || pad_w < 0 || pad_t > kt - 1 || pad_h > kh - 1 || pad_w > kw - 1 ||
+        stride < 1 || stride > 4) {
         set_error("convnd_dgrad: outside the tensor-core kernel's envelope");
         return LVG_UNSUPPORTED;
     }
-    // dx = correlation of dy (to x ho x wo, cout channels) with the channel-transposed, mirrored weights, padding k-1-pad
+    // dx = correlation of dy (to x ho x wo, cout channels; for a strided convolution: dy spread over every stride-th pixel of
+    // that grid) with the channel-transposed, mirrored weights, padding k-1-pad
     const int taps = kt * kh * kw;
     const int to = t + 2 * pad_t - kt + 1, ho = h + 2 * pad_h - kh + 1, wo = wd + 2 * pad_w - kw + 1;
+    const int hos = (ho - 1) / stride + 1, wos = (wo - 1) / stride + 1;
     return run_igemm(dy, w, dx, dtype, n, groups, cout, cin, to, ho, wo, kt, kh, kw, kt - 1 - pad_t, kh - 1 - pad_h, kw - 1 - pad_w,
-                     (int64_t)cout * cin * taps, taps, (int64_t)cin * taps, 1, nullptr, 0, 0.f, 1.f, -1.f, workspace, workspace_bytes,
-                     (cudaStream_t)stream);
+                     (int64_t)cout * cin * taps, taps, (int64_t)cin * taps, 1, nullptr, 0, 0.f, 1.f, -1.f, hos, wos, stride, 1, workspace,
+                     workspace_bytes, (cudaStream_t)stream);
 }
 
 // =================================================================================================
@@ -777,12 +891,13 @@ extern "C" int64_t lvg_convnd_wgrad_workspace(int dtype, int n, int groups, int 
 }
 
 extern "C" int lvg_convnd_wgrad(const void* x, const void* dy, void* dw, int dtype, int n, int groups, int cin, int cout, int t, int h, int wd,
-                                int kt, int kh, int kw, int pad_t, int pad_h, int pad_w, void* workspace, int64_t workspace_bytes, void* stream)
+                                int kt, int kh, int kw, int pad_t, int pad_h, int pad_w, int stride, void* workspace, int64_t workspace_bytes,
+                                void* stream)
 {
     LVG_REQUIRE(x && dy && dw, "convnd_wgrad: x, dy, dw must not be NULL");
     const int to = t + 2 * pad_t - kt + 1, ho = h + 2 * pad_h - kh + 1, wo = wd + 2 * pad_w - kw + 1;
     if (!nd_supported(dtype, kt, kh, kw) || n < 1 || kw > 3 || pad_t < 0 || pad_h < 0 || pad_w < 0 || to < 1 || ho < 1 || wo < 1 ||
-        wo + kw - 1 > 2 * 240) {
+        wo + kw - 1 > 2 * 240 || stride < 1 || stride > 4) {
         set_error("convnd_wgrad: outside the tensor-core kernel's envelope");
         return LVG_UNSUPPORTED;
     }
@@ -797,17 +912,11 @@ extern "C" int lvg_convnd_wgrad(const void* x, const void* dy, void* dw, int dty
     float* part = reinterpret_cast<float*>(x8 + ((q.b_bytes + 255) / 256) * 256);
     const int64_t thw_a = (int64_t)to * ho * wo, thw_b = (int64_t)t * h * wd;
     {
-        const int64_t cap = (int64_t)num_sms() * 64;
-        int64_t total = inst * (q.cpad_a / 8) * thw_a, blocks = (total + 255) / 256;
-        if (blocks > cap) blocks = cap;
-        if (q.split) conv_pack_act_kernel<float, true><<<(unsigned)blocks, 256, 0, s>>>((const float*)dy, (uint4*)dy8, inst, cout, q.cpad_a / 8, thw_a);
-        else conv_pack_act_kernel<__half, false><<<(unsigned)blocks, 256, 0, s>>>((const __half*)dy, (uint4*)dy8, inst, cout, q.cpad_a / 8, thw_a);
-        LVG_LAUNCH_CHECK();
-        total = inst * (q.cpad_b / 8) * thw_b; blocks = (total + 255) / 256;
-        if (blocks > cap) blocks = cap;
-        if (q.split) conv_pack_act_kernel<float, true><<<(unsigned)blocks, 256, 0, s>>>((const float*)x, (uint4*)x8, inst, cin, q.cpad_b / 8, thw_b);
-        else conv_pack_act_kernel<__half, false><<<(unsigned)blocks, 256, 0, s>>>((const __half*)x, (uint4*)x8, inst, cin, q.cpad_b / 8, thw_b);
-        LVG_LAUNCH_CHECK();
+        // dy of a strided convolution is spread over every stride-th pixel of the stride-1 output grid (zeros between)
+        int rc = pack_act(dy, dy8, q.split, inst, cout, q.cpad_a / 8, to, (ho - 1) / stride + 1, (wo - 1) / stride + 1, ho, wo, stride, s);
+        if (rc) return rc;
+        rc = pack_act(x, x8, q.split, inst, cin, q.cpad_b / 8, t, h, wd, h, wd, 1, s);
+        if (rc) return rc;
     }
     WgradV2Params p;
     memset(&p, 0, sizeof(p));

@@ -61,10 +61,10 @@ _SIGNATURES = {
     'lvg_conv2d_dgrad': (_c_int, [_c_void_p] * 3 + [_c_int] * 12 + [_c_void_p, _c_i64, _c_void_p]),
     'lvg_conv2d_wgrad': (_c_int, [_c_void_p] * 3 + [_c_int] * 12 + [_c_void_p]),
     'lvg_convnd_workspace': (_c_i64, [_c_int] * 14),
-    'lvg_convnd_fprop': (_c_int, [_c_void_p] * 3 + [_c_int] * 14 + [_c_void_p, _c_int, _c_float, _c_float, _c_float, _c_void_p, _c_i64, _c_void_p]),
-    'lvg_convnd_dgrad': (_c_int, [_c_void_p] * 3 + [_c_int] * 14 + [_c_void_p, _c_i64, _c_void_p]),
+    'lvg_convnd_fprop': (_c_int, [_c_void_p] * 3 + [_c_int] * 15 + [_c_void_p, _c_int, _c_float, _c_float, _c_float, _c_void_p, _c_i64, _c_void_p]),
+    'lvg_convnd_dgrad': (_c_int, [_c_void_p] * 3 + [_c_int] * 15 + [_c_void_p, _c_i64, _c_void_p]),
     'lvg_convnd_wgrad_workspace': (_c_i64, [_c_int] * 14),
-    'lvg_convnd_wgrad': (_c_int, [_c_void_p] * 3 + [_c_int] * 14 + [_c_void_p, _c_i64, _c_void_p]),
+    'lvg_convnd_wgrad': (_c_int, [_c_void_p] * 3 + [_c_int] * 15 + [_c_void_p, _c_i64, _c_void_p]),
 }
 
 LVG_UNSUPPORTED = -1
@@ -586,7 +586,8 @@ class ConvNdPlugin:
             return False
         nd = x.ndim - 2
         as_t = lambda v: tuple(v) if isinstance(v, (list, tuple)) else (v,) * nd       # noqa: E731
-        if as_t(stride) != (1,) * nd or as_t(dilation) != (1,) * nd:
+        st = as_t(stride)
+        if as_t(dilation) != (1,) * nd or len(set(st[-2:])) != 1 or not (1 <= st[-1] <= 4) or (nd == 3 and st[0] != 1) or (nd == 1 and st[0] != 1):
             return False
         sp, k, _ = self._dims(x, w)
         pad = self._pad3(padding, nd)
@@ -613,39 +614,40 @@ class ConvNdPlugin:
         code = 1 if dtype == torch.float16 else 0
         return [code, x_shape[0], groups, w_shape[1], w_shape[0] // groups] + sp + k + pad, sp, k, pad
 
-    def fprop(self, x, w, padding, groups, bias=None, act=0, alpha=0.2, gain=1.0, clamp=-1.0):
+    def fprop(self, x, w, padding, groups, bias=None, act=0, alpha=0.2, gain=1.0, clamp=-1.0, stride=1):
         x, w = x.contiguous(), w.contiguous()
         a, sp, k, pad = self._args(tuple(x.shape), tuple(w.shape), padding, groups, x.dtype)
-        out_sp = [s + 2 * p - kk + 1 for s, p, kk in zip(sp, pad, k)][3 - (x.ndim - 2):]
+        st3 = [1, stride, stride] if x.ndim >= 4 else [1, 1, 1]
+        out_sp = [(s + 2 * p - kk) // q + 1 for s, p, kk, q in zip(sp, pad, k, st3)][3 - (x.ndim - 2):]
         y = torch.empty([x.shape[0], w.shape[0]] + out_sp, dtype=x.dtype, device=x.device)
         ws = self._workspace(x.device, self._lib.lvg_convnd_workspace(*a))
         if bias is not None:
             bias = bias.to(torch.float32).contiguous()
         with _DeviceGuard(x):
-            rc = _check(self._lib.lvg_convnd_fprop(_ptr(x), _ptr(w), _ptr(y), *a, _ptr(bias), int(act), float(alpha), float(gain),
+            rc = _check(self._lib.lvg_convnd_fprop(_ptr(x), _ptr(w), _ptr(y), *a, int(stride), _ptr(bias), int(act), float(alpha), float(gain),
                                                    float(clamp), _ptr(ws), ws.numel(), _stream(x)), 'convnd_fprop')
         if rc == LVG_UNSUPPORTED:
             raise RuntimeError('convnd_fprop: ' + self._lib.lvg_last_error().decode())
         return y
 
-    def dgrad(self, dy, w, x_shape, padding, groups):
+    def dgrad(self, dy, w, x_shape, padding, groups, stride=1):
         dy, w = dy.contiguous(), w.contiguous()
         a, sp, k, pad = self._args(tuple(x_shape), tuple(w.shape), padding, groups, dy.dtype)
         dx = torch.empty(list(x_shape), dtype=dy.dtype, device=dy.device)
         ws = self._workspace(dy.device, self._lib.lvg_convnd_workspace(*a))
         with _DeviceGuard(dy):
-            rc = _check(self._lib.lvg_convnd_dgrad(_ptr(dy), _ptr(w), _ptr(dx), *a, _ptr(ws), ws.numel(), _stream(dy)), 'convnd_dgrad')
+            rc = _check(self._lib.lvg_convnd_dgrad(_ptr(dy), _ptr(w), _ptr(dx), *a, int(stride), _ptr(ws), ws.numel(), _stream(dy)), 'convnd_dgrad')
         if rc == LVG_UNSUPPORTED:
             raise RuntimeError('convnd_dgrad: ' + self._lib.lvg_last_error().decode())
         return dx
 
-    def wgrad(self, x, dy, w_shape, padding, groups):
+    def wgrad(self, x, dy, w_shape, padding, groups, stride=1):
         x, dy = x.contiguous(), dy.contiguous()
         a, sp, k, pad = self._args(tuple(x.shape), tuple(w_shape), padding, groups, x.dtype)
         dw = torch.empty(list(w_shape), dtype=x.dtype, device=x.device)
         ws = self._workspace(x.device, self._lib.lvg_convnd_wgrad_workspace(*a))
         with _DeviceGuard(x):
-            rc = _check(self._lib.lvg_convnd_wgrad(_ptr(x), _ptr(dy), _ptr(dw), *a, _ptr(ws), ws.numel(), _stream(x)), 'convnd_wgrad')
+            rc = _check(self._lib.lvg_convnd_wgrad(_ptr(x), _ptr(dy), _ptr(dw), *a, int(stride), _ptr(ws), ws.numel(), _stream(x)), 'convnd_wgrad')
         if rc == LVG_UNSUPPORTED:
             raise RuntimeError('convnd_wgrad: ' + self._lib.lvg_last_error().decode())
         return dw

@@ -61,7 +61,7 @@ def test_convnd_forward_and_gradients(plug, name, xs, ws, pad, groups, dtype):
     y = plug.fprop(x, w, pad, groups)
     assert y.shape == yr.shape and y.dtype == dtype
     tol = 2e-3 if dtype == torch.float16 else 5e-5          # fp16: result rounding; split fp32: ~2^-16 per product
-    scale = float(yr.abs().max())
+    scale = float(yr.detach().abs().max())
     assert float((y.double() - yr).abs().max()) <= tol * scale, f'fprop {float((y.double() - yr).abs().max()) / scale:.3e}'
     dy64 = rnd(tuple(yr.shape), 3)
     dy = dy64.to(dtype)
@@ -86,6 +86,35 @@ def test_convnd_fused_bias_act_epilogue(plug, dtype):
             r = r.clamp(-clamp, clamp)
         tol = 2e-3 if dtype == torch.float16 else 5e-5
         assert float((y.double() - r).abs().max()) <= tol * float(r.abs().max())
+
+
+STRIDED = [
+    ('3x3 s2 pad0 (conv2d_resample down path)', (2, 32, 35, 42), (48, 32, 3, 3), 0, 2, 1),
+    ('3x3 s2 pad1 even', (3, 24, 32, 32), (40, 24, 3, 3), 1, 2, 1),
+    ('1x1 s2', (2, 64, 31, 17), (24, 64, 1, 1), 0, 2, 1),
+    ('3x3 s2 wide, row tiles', (1, 16, 40, 300), (16, 16, 3, 3), 1, 2, 1),
+    ('3x3 s2 grouped', (1, 3 * 16, 21, 22), (3 * 24, 16, 3, 3), 1, 2, 3),
+]
+
+
+@pytest.mark.parametrize('dtype', [torch.float16, torch.float32], ids=['f16', 'f32split'])
+@pytest.mark.parametrize('name,xs,ws,pad,stride,groups', STRIDED, ids=[c[0] for c in STRIDED])
+def test_convnd_strided(plug, name, xs, ws, pad, stride, groups, dtype):
+    fan = math.prod(ws[1:])
+    x, w = rnd(xs, 11).to(dtype), rnd(ws, 12, 1.0 / math.sqrt(fan)).to(dtype)
+    xr, wr = x.double().requires_grad_(True), w.double().requires_grad_(True)
+    yr = F.conv2d(xr, wr, stride=stride, padding=pad, groups=groups)
+    assert plug.supported(x, w, stride, pad, 1, groups)
+    tol = 2e-3 if dtype == torch.float16 else 5e-5
+    y = plug.fprop(x, w, (pad, pad), groups, stride=stride)
+    assert y.shape == yr.shape
+    assert float((y.double() - yr).abs().max()) <= tol * float(yr.detach().abs().max()), 'fprop'
+    dy = rnd(tuple(yr.shape), 13).to(dtype)
+    gx, gw = torch.autograd.grad(yr, [xr, wr], dy.double())
+    dx = plug.dgrad(dy, w, tuple(x.shape), (pad, pad), groups, stride=stride)
+    assert float((dx.double() - gx).abs().max()) <= tol * float(gx.abs().max()), 'dgrad'
+    dw = plug.wgrad(x, dy, tuple(w.shape), (pad, pad), groups, stride=stride)
+    assert float((dw.double() - gw).abs().max()) <= tol * float(gw.abs().max()), 'wgrad'
 
 
 def test_convnd_wgrad_split_k_matches_single_pass(plug):
