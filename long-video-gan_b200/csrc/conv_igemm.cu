@@ -145,15 +145,18 @@ int pack_act(const void* x, void* x8, int split, int64_t inst, int c, int cblk, 
 // Image of one 128 x 16 tile (K-major, no swizzle): byte offset(m, k) = (k/8)*2048 + (m/8)*128 + (m%8)*16 + (k%8)*2.
 // SPLIT: the packed K axis is three segments of kpad channels [hi | hi | lo], matching the activation blocks
 // [hi | lo | hi] visited by the main loop: hi*hi + lo*hi + hi*lo.
-// One CTA = one (group, m-tile, k-step): the 128 x 16 x taps source elements are read in memory order (coalesced) into
-// shared memory and leave as whole 16-byte image rows, consecutive threads writing consecutive rows.
+// One CTA = one (group, m-tile, k-step). The 128 x 16 x taps source elements form contiguous RUNS in memory (fprop: one
+// run of 16*taps elements per output channel; dgrad: one run of 128*taps elements per k): a warp copies a run into shared
+// memory with aligned 4-byte loads (no per-element index arithmetic), then every thread assembles one 16-byte image row
+// from 8 shared-memory reads and consecutive threads write consecutive rows (512 contiguous bytes per warp).
 template <class TIn, bool SPLIT>
 __global__ void __launch_bounds__(256) conv_pack_w_kernel(const TIn* __restrict__ w, unsigned char* __restrict__ wp, int m_total, int k_total,
                                                            int kpad, int taps, int64_t gstride, int64_t sm, int64_t sk, int flip, int mt, int kc,
                                                            int rows_per_pass)
 {
-    extern __shared__ float sw[];                    // [rows_per_pass][16 * taps + 1]
-    const int pitch = 16 * taps + 1;
+    extern __shared__ uint32_t sw32[];               // [runs][pitch] words, then the runs' element offsets
+    constexpr int ES = (int)sizeof(TIn);
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
     const int kci = blockIdx.x % kc;
     const int mti = (blockIdx.x / kc) % mt;
     const int g = blockIdx.x / (kc * mt);
@@ -161,39 +164,61 @@ __global__ void __launch_bounds__(256) conv_pack_w_kernel(const TIn* __restrict_
     const int seg = SPLIT ? kp0 / kpad : 0;
     const int k0 = SPLIT ? kp0 - seg * kpad : kp0;
     const TIn* wg = w + (int64_t)g * gstride;
+    const bool mrows = sk < sm;                      // fprop layout: runs along (k, tap) per m; else runs along (m, tap) per k
+    const int R = rows_per_pass;
+    const int run_el = mrows ? 16 * taps : R * taps;
+    const int pitch = ((run_el * ES + 2 + 3) / 4) | 1;
+    const int max_runs = mrows ? R : 16;
+    int* s_off = reinterpret_cast<int*>(sw32 + (size_t)max_runs * pitch);
     unsigned char* dst0 = wp + ((((int64_t)g * mt + mti) * kc + kci) * taps) * kATile;
-    for (int r0 = 0; r0 < kBM; r0 += rows_per_pass) {
-        const int R = min(rows_per_pass, kBM - r0);
+    const int kvalid = max(0, min(16, k_total - k0));
+    for (int r0 = 0; r0 < kBM; r0 += R) {
+        const int Rn = min(R, kBM - r0);
         const int m0 = mti * kBM + r0;
-        const int n_el = R * 16 * taps;
-        if (sk < sm) {                               // rows of m: (k, tap) contiguous
-            for (int e = threadIdx.x; e < n_el; e += 256) {
-                const int tap = e % taps, k = (e / taps) % 16, m = e / (16 * taps);
-                float v = 0.f;
-                if (m0 + m < m_total && k0 + k < k_total) v = (float)wg[(int64_t)(m0 + m) * sm + (int64_t)(k0 + k) * sk + tap];
-                sw[m * pitch + k * taps + tap] = v;
+        const int mvalid = max(0, min(Rn, m_total - m0));
+        const int nruns = mrows ? mvalid : kvalid;
+        const int len = mrows ? kvalid * taps : mvalid * taps;             // valid elements of a run
+        for (int run = warp; run < nruns; run += 8) {
+            const int64_t e0 = mrows ? (int64_t)(m0 + run) * sm + (int64_t)k0 * sk : (int64_t)(k0 + run) * sk + (int64_t)m0 * sm;
+            const unsigned char* gb = reinterpret_cast<const unsigned char*>(wg + e0);
+            const int a = (int)(reinterpret_cast<uintptr_t>(gb) & 3);       // 0, or 2 for an odd fp16 element offset
+            const uint32_t* gw = reinterpret_cast<const uint32_t*>(gb - a);
+            const int nbytes = len * ES + a;
+            const int nwords = (nbytes + 3) / 4;
+            for (int wi = lane; wi < nwords; wi += 32) {
+                uint32_t v;
+                if (wi == 0 && a != 0) v = (uint32_t)__ldg(reinterpret_cast<const unsigned short*>(gb)) << 16;                       // do not touch bytes before the run
+                else if (wi == nwords - 1 && (nbytes & 3) != 0) v = (uint32_t)__ldg(reinterpret_cast<const unsigned short*>(gw + wi));   // ... or after it
+                else v = __ldg(gw + wi);
+                sw32[run * pitch + wi] = v;
             }
-        } else {                                     // rows of k: (m, tap) contiguous
-            for (int e = threadIdx.x; e < n_el; e += 256) {
-                const int tap = e % taps, m = (e / taps) % R, k = e / (R * taps);
-                float v = 0.f;
-                if (m0 + m < m_total && k0 + k < k_total) v = (float)wg[(int64_t)(k0 + k) * sk + (int64_t)(m0 + m) * sm + tap];
-                sw[m * pitch + k * taps + tap] = v;
-            }
+            if (lane == 0) s_off[run] = a / ES;
         }
         __syncthreads();
-        for (int o = threadIdx.x; o < taps * 2 * R; o += 256) {
-            const int mrow = o % R, k8 = (o / R) % 2, tap = o / (2 * R);
+        const bool pow2 = Rn == kBM;
+        for (int o = threadIdx.x; o < taps * 2 * Rn; o += 256) {
+            int mrow, k8, tap;
+            if (pow2) { mrow = o & (kBM - 1); k8 = (o >> 7) & 1; tap = o >> 8; }
+            else { mrow = o % Rn; k8 = (o / Rn) % 2; tap = o / (2 * Rn); }
             const int wtap = flip ? taps - 1 - tap : tap;
             alignas(16) unsigned short v[8];
 #pragma unroll
             for (int j = 0; j < 8; j++) {
-                const float f = sw[mrow * pitch + (k8 * 8 + j) * taps + wtap];
+                const int k = k8 * 8 + j;
+                const int run = mrows ? mrow : k;
+                const int idx = mrows ? k * taps + wtap : mrow * taps + wtap;
+                float f = 0.f;
+                unsigned short hbits = 0;
+                if (mrow < mvalid && k < kvalid) {
+                    if constexpr (ES == 2) hbits = reinterpret_cast<const unsigned short*>(sw32 + run * pitch)[s_off[run] + idx];
+                    else f = __uint_as_float(sw32[run * pitch + idx]);
+                }
                 if constexpr (SPLIT) {
+                    if constexpr (ES == 2) f = __half2float(__ushort_as_half(hbits));
                     const unsigned short h = bf16_bits(f);
                     v[j] = seg == 2 ? bf16_bits(f - bf16_val(h)) : h;
                 } else {
-                    v[j] = __half_as_ushort(__float2half_rn(f));       // exact: the source is fp16
+                    v[j] = ES == 2 ? hbits : __half_as_ushort(__float2half_rn(f));
                 }
             }
             *reinterpret_cast<uint4*>(dst0 + (size_t)tap * kATile + k8 * 2048 + (r0 + mrow) * 16) = *reinterpret_cast<const uint4*>(v);
@@ -208,6 +233,15 @@ __device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* map, i
 {
     asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
                  ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// X8 seen as 8-byte elements: (2*W, H, T, instance*block). A pixel of a block is two elements, so a box row is one
+// contiguous run of 16*width bytes (with a 16-byte innermost dimension TMA moves one pixel per request).
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+                 ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
                  : "memory");
 }
 
@@ -274,7 +308,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
                         for (int j = 0; j < nks; j++) {
                             const int kb = (k0 + j) * 2;
                             const int sb = kb < p.kb_wrap ? kb : kb - p.kb_wrap;
-                            tma_load_5d(st + p.a_stage + (size_t)j * p.b_step, &tmx, 0, c.ox0 - p.pad_w, c.oy0 - p.pad_h, c.t0 + kt - p.pad_t,
+                            tma_load_4d(st + p.a_stage + (size_t)j * p.b_step, &tmx, 2 * (c.ox0 - p.pad_w), c.oy0 - p.pad_h, c.t0 + kt - p.pad_t,
                                         blk0 + sb, &full_bar[s]);
                         }
                     }
@@ -404,6 +438,24 @@ EncodeTiledFn encode_fn()
     return fn;
 }
 
+// tensor map over a channel-block-of-8 tensor [blocks][t][h (pitch_hw / pitch_w rows)][w][8 x 2 bytes], seen as 8-byte
+// elements: (2 w, h, t, blocks); box = box_w pixels x box_h rows x box_t frames x box_blk blocks
+int encode_map(CUtensorMap* tm, void* base, int w, int h, int t, int64_t blocks, int64_t pitch_w, int64_t pitch_hw, int64_t pitch_thw, int box_w,
+               int box_h, int box_t, int box_blk)
+{
+    EncodeTiledFn enc = encode_fn();
+    LVG_REQUIRE(enc != nullptr, "convnd: cuTensorMapEncodeTiled is not available from this driver");
+    const cuuint64_t dims[4] = {(cuuint64_t)w * 2, (cuuint64_t)h, (cuuint64_t)t, (cuuint64_t)blocks};
+    const cuuint64_t strides[3] = {(cuuint64_t)pitch_w * 16, (cuuint64_t)pitch_hw * 16, (cuuint64_t)pitch_thw * 16};
+    const cuuint32_t box[4] = {(cuuint32_t)box_w * 2, (cuuint32_t)box_h, (cuuint32_t)box_t, (cuuint32_t)box_blk};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    LVG_REQUIRE(box_w <= 128 && box_h <= 256 && box_t <= 256 && box_blk <= 256, "convnd: TMA box too large");
+    const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT64, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    LVG_REQUIRE(r == CUDA_SUCCESS, "convnd: cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return LVG_OK;
+}
+
 inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
 
 struct Geometry {
@@ -461,7 +513,7 @@ int run_igemm(const void* x, const void* w, void* y, int dtype, int n, int group
     // column tiles. A tile of <= 256 columns leaves room for two accumulator buffers (epilogue overlap).
     // (short K loops are epilogue-bound: they take <= 256 columns and alternate two accumulator buffers)
     const int col_budget = (g.kc * kt <= 12) ? 256 : 512;
-    const int max_wt = 256 - (kw - 1);
+    const int max_wt = 128 - (kw - 1);                        // a TMA box row is at most 256 8-byte elements
     p.tiles_x = (p.wo + max_wt - 1) / max_wt;
     p.wt = (p.wo + p.tiles_x - 1) / p.tiles_x;
     p.wtb = p.wt + kw - 1;
@@ -513,10 +565,16 @@ int run_igemm(const void* x, const void* w, void* y, int dtype, int n, int group
         if (rc) return rc;
         const int64_t wblocks = (int64_t)groups * g.mt * g.kc;
         LVG_REQUIRE(wblocks < (1ll << 31), "convnd: too many weight tiles");
-        int rpp = (int)((96 * 1024) / ((16 * taps + 1) * sizeof(float))) / 8 * 8;       // rows per pass: <= 96 KB of staging
+        // rows of m per pass: <= ~64 KB of staging (16 * rows * taps elements either way)
+        const int es = split ? 4 : 2;
+        int rpp = (int)((64 * 1024) / (16 * taps * es + 16)) / 8 * 8;
         if (rpp > kBM) rpp = kBM;
         if (rpp < 8) rpp = 8;
-        const size_t wsm = (size_t)rpp * (16 * taps + 1) * sizeof(float);
+        const bool mrows = w_sk < w_sm;
+        const int run_el = mrows ? 16 * taps : rpp * taps;
+        const int pitch = ((run_el * es + 2 + 3) / 4) | 1;
+        const int max_runs = mrows ? rpp : 16;
+        const size_t wsm = ((size_t)max_runs * pitch + max_runs + 4) * 4;
         if (split) {
             LVG_CUDA(cudaFuncSetAttribute(conv_pack_w_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsm));
             conv_pack_w_kernel<float, true><<<(unsigned)wblocks, 256, wsm, s>>>((const float*)w, wp, cm, ck, g.cpad, taps, w_gs, w_sm, w_sk, flip, g.mt, g.kc, rpp);
@@ -527,17 +585,11 @@ int run_igemm(const void* x, const void* w, void* y, int dtype, int n, int group
         LVG_LAUNCH_CHECK();
     }
 
-    // tensor map over X8: (8, W, H, T, instance * block)
+    // tensor map over X8 as 8-byte elements: (2 W, H, T, instance * block)
     CUtensorMap tm;
     {
-        const cuuint64_t dims[5] = {8, (cuuint64_t)wd, (cuuint64_t)h, (cuuint64_t)t, (cuuint64_t)(inst * g.nblk)};
-        const cuuint64_t strides[4] = {16, (cuuint64_t)wd * 16, (cuuint64_t)h * wd * 16, (cuuint64_t)thw * 16};
-        const cuuint32_t box[5] = {8, (cuuint32_t)p.wtb, (cuuint32_t)p.thb, (cuuint32_t)p.tt, 2};
-        const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-        LVG_REQUIRE(p.wtb <= 256 && p.thb <= 256 && p.tt <= 256, "convnd: TMA box too large");
-        const CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT16, 5, x8, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        LVG_REQUIRE(r == CUDA_SUCCESS, "convnd: cuTensorMapEncodeTiled failed (%d)", (int)r);
+        const int rc = encode_map(&tm, x8, wd, h, t, inst * g.nblk, wd, (int64_t)h * wd, thw, p.wtb, p.thb, p.tt, 2);
+        if (rc) return rc;
     }
     const size_t smem = (size_t)p.stages * p.stage_bytes + epi_bytes + 128;
     LVG_CUDA(cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -634,15 +686,16 @@ struct WgradV2Params {
     int nt;                      // ci per n-tile (multiple of 16)
     int nblk_a, nblk_b;          // channel blocks per instance in dy8 / x8 (incl. the lo half in split mode)
     int lo_a, lo_b;              // block offset of the lo half
-    int nseg, seg_w[2], seg_x0[2], ps[2];
+    int nseg, seg_w[4], seg_x0[4], ps[4];
     int rh;                      // rows per stage
     int nsplit;
     int a_bytes, b_bytes, stage_bytes, stages;      // per stage: one A (B) operand image; a stage holds split+1 of each
     int64_t split_stride;        // elements between fp32 partials
 };
 
-__global__ void __launch_bounds__(kThreads, 1) conv_wgrad_v2_kernel(const __grid_constant__ CUtensorMap tma0, const __grid_constant__ CUtensorMap tma1,
-                                                                     const __grid_constant__ CUtensorMap tmb, const WgradV2Params p)
+struct WgradMaps { CUtensorMap a[4]; CUtensorMap b; };     // dy8 clipped to each column segment; x8
+
+__global__ void __launch_bounds__(kThreads, 1) conv_wgrad_v2_kernel(const __grid_constant__ WgradMaps maps, const WgradV2Params p)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t full_bar[kMaxStages], empty_bar[kMaxStages], acc_bar;
@@ -699,8 +752,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_v2_kernel(const __grid
                 mbar_expect_tx(&full_bar[slot], (uint32_t)(nop * (p.a_bytes + p.b_bytes)));
                 const int oy0 = rb * p.rh;
                 for (int o = 0; o < nop; o++) {
-                    tma_load_5d(st + (size_t)o * p.a_bytes, seg == 0 ? &tma0 : &tma1, 0, 0, oy0, t, inst * p.nblk_a + o * p.lo_a + mti * 16, &full_bar[slot]);
-                    tma_load_5d(st + (size_t)nop * p.a_bytes + (size_t)o * p.b_bytes, &tmb, 0, p.seg_x0[seg] - p.pad_w, oy0 + ky - p.pad_h,
+                    tma_load_4d(st + (size_t)o * p.a_bytes, &maps.a[seg], 0, oy0, t, inst * p.nblk_a + o * p.lo_a + mti * 16, &full_bar[slot]);
+                    tma_load_4d(st + (size_t)nop * p.a_bytes + (size_t)o * p.b_bytes, &maps.b, 2 * (p.seg_x0[seg] - p.pad_w), oy0 + ky - p.pad_h,
                                 t + kt - p.pad_t, inst * p.nblk_b + o * p.lo_b + nti * (NT / 8), &full_bar[slot]);
                 }
             }
@@ -716,7 +769,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_v2_kernel(const __grid
                 const int seg = (s / rblocks) % p.nseg;
                 const int rb = s % rblocks;
                 const int rows = min(p.rh, p.ho - rb * p.rh);
-                const int ksteps = rows * p.ps[seg] / 16;
+                const int ksteps = (rows * p.ps[seg] + 15) / 16;                 // (a trailing half step reads the zero-filled next row)
                 const uint32_t blk = (uint32_t)(p.rh * p.ps[seg] * 16);          // bytes of one channel block of the stage tile
                 mbar_wait(&full_bar[slot], (uint32_t)((it / p.stages) & 1));
                 tc_fence_after();
@@ -803,25 +856,9 @@ __global__ void __launch_bounds__(256) conv_wgrad_reduce_kernel(const float* __r
     }
 }
 
-int encode_map(CUtensorMap* tm, void* base, int w, int h, int t, int64_t blocks, int64_t pitch_w, int64_t pitch_hw, int64_t pitch_thw, int box_w,
-               int box_h, int box_blk)
-{
-    EncodeTiledFn enc = encode_fn();
-    LVG_REQUIRE(enc != nullptr, "convnd: cuTensorMapEncodeTiled is not available from this driver");
-    const cuuint64_t dims[5] = {8, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)t, (cuuint64_t)blocks};
-    const cuuint64_t strides[4] = {16, (cuuint64_t)pitch_w * 16, (cuuint64_t)pitch_hw * 16, (cuuint64_t)pitch_thw * 16};
-    const cuuint32_t box[5] = {8, (cuuint32_t)box_w, (cuuint32_t)box_h, 1, (cuuint32_t)box_blk};
-    const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    LVG_REQUIRE(box_w <= 256 && box_h <= 256 && box_blk <= 256, "convnd: TMA box too large");
-    const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT16, 5, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    LVG_REQUIRE(r == CUDA_SUCCESS, "convnd: cuTensorMapEncodeTiled failed (%d)", (int)r);
-    return LVG_OK;
-}
-
 struct WgradPlan {
     int split, cpad_a, cpad_b, nt, ntiles, mt, nsplit;
-    int nseg, seg_w[2], seg_x0[2], ps, rh, stages;
+    int nseg, seg_w[4], seg_x0[4], ps, rh, stages;
     int a_stage, b_stage, stage_bytes;
     size_t smem;
     int64_t a_bytes, b_bytes, part_bytes, dw_elems;
@@ -836,6 +873,17 @@ WgradPlan wgrad_plan(int dtype, int n, int groups, int cin, int cout, int t, int
     int nt_cap = (512 / kw) / 16 * 16;
     if (nt_cap > 256) nt_cap = 256;
     if (q.split && nt_cap > 96) nt_cap = 96;
+    // column segments (a TMA box row is at most 128 pixels incl. the kw - 1 halo) and the common tile pitch
+    q.nseg = (wo + 128 - kw) / (129 - kw);
+    if (q.nseg < 1) q.nseg = 1;
+    const int w0 = (wo + q.nseg - 1) / q.nseg;
+    for (int j = 0; j < 4; j++) { q.seg_x0[j] = j * w0; q.seg_w[j] = j < q.nseg ? (wo - j * w0 < w0 ? wo - j * w0 : w0) : 0; }
+    q.ps = round_up(w0 + kw - 1, 8);                           // rows x pitch must be a multiple of 16 pixels (one MMA K step)
+    {   // the smallest stage (1 or 2 rows) must leave room for two stages
+        const int min_rows = q.ps % 16 != 0 ? 2 : 1;
+        const int nop0 = q.split ? 2 : 1;
+        while (nt_cap > 16 && 2 * nop0 * (16 + nt_cap / 8) * min_rows * q.ps * 16 > 200 * 1024) nt_cap -= 16;
+    }
     q.ntiles = (q.cpad_b + nt_cap - 1) / nt_cap;
     q.nt = round_up((q.cpad_b + q.ntiles - 1) / q.ntiles, 16);
     q.cpad_b = q.nt * q.ntiles;
@@ -844,18 +892,14 @@ WgradPlan wgrad_plan(int dtype, int n, int groups, int cin, int cout, int t, int
     q.a_bytes = inst * (q.split ? 2 : 1) * (q.cpad_a / 8) * (int64_t)to * ho * wo * 16;
     q.b_bytes = inst * (q.split ? 2 : 1) * (q.cpad_b / 8) * (int64_t)t * h * wd * 16;
     q.dw_elems = (int64_t)groups * cout * cin * kt * kh * kw;
-    // column segments (a TMA box is at most 256 pixels wide) and the common tile pitch
-    q.nseg = (wo + kw - 1 > 256) ? 2 : 1;
-    const int w0 = q.nseg == 1 ? wo : (wo + 1) / 2;
-    q.seg_w[0] = w0; q.seg_x0[0] = 0; q.seg_w[1] = wo - w0; q.seg_x0[1] = w0;
-    q.ps = round_up(w0 + kw - 1, 16);
     // rows per stage: about 80 KB of operands per stage
     const int nop = q.split ? 2 : 1;
     const int per_row = nop * (16 + q.nt / 8) * q.ps * 16;
     q.rh = (80 * 1024) / per_row;
     if (q.rh < 1) q.rh = 1;
     if (q.rh > ho) q.rh = ho;
-    if (q.rh > 255) q.rh = 255;
+    if (q.rh > 254) q.rh = 254;
+    if (q.ps % 16 != 0) q.rh = q.rh >= 2 ? q.rh / 2 * 2 : 2;   // even row count (rows past the image are zero-filled)
     q.a_stage = 16 * q.rh * q.ps * 16;
     q.b_stage = (q.nt / 8) * q.rh * q.ps * 16;
     q.stage_bytes = round_up(nop * (q.a_stage + q.b_stage), 128);
@@ -885,7 +929,7 @@ extern "C" int64_t lvg_convnd_wgrad_workspace(int dtype, int n, int groups, int 
 {
     if (!nd_supported(dtype, kt, kh, kw) || n < 1 || groups < 1 || kw > 3) return -1;
     const int to = t + 2 * pad_t - kt + 1, ho = h + 2 * pad_h - kh + 1, wo = wd + 2 * pad_w - kw + 1;
-    if (to < 1 || ho < 1 || wo < 1 || wo + kw - 1 > 2 * 240) return -1;
+    if (to < 1 || ho < 1 || wo < 1 || wo > 4 * (128 - kw + 1)) return -1;
     const WgradPlan q = wgrad_plan(dtype, n, groups, cin, cout, t, h, wd, to, ho, wo, kt, kh, kw);
     return q.a_bytes + q.b_bytes + q.part_bytes + 1024;
 }
@@ -897,7 +941,7 @@ extern "C" int lvg_convnd_wgrad(const void* x, const void* dy, void* dw, int dty
     LVG_REQUIRE(x && dy && dw, "convnd_wgrad: x, dy, dw must not be NULL");
     const int to = t + 2 * pad_t - kt + 1, ho = h + 2 * pad_h - kh + 1, wo = wd + 2 * pad_w - kw + 1;
     if (!nd_supported(dtype, kt, kh, kw) || n < 1 || kw > 3 || pad_t < 0 || pad_h < 0 || pad_w < 0 || to < 1 || ho < 1 || wo < 1 ||
-        wo + kw - 1 > 2 * 240 || stride < 1 || stride > 4) {
+        wo > 4 * (128 - kw + 1) || stride < 1 || stride > 4) {
         set_error("convnd_wgrad: outside the tensor-core kernel's envelope");
         return LVG_UNSUPPORTED;
     }
@@ -927,7 +971,7 @@ extern "C" int lvg_convnd_wgrad(const void* x, const void* dy, void* dw, int dty
     p.nblk_a = (q.split ? 2 : 1) * (q.cpad_a / 8); p.nblk_b = (q.split ? 2 : 1) * (q.cpad_b / 8);
     p.lo_a = q.cpad_a / 8; p.lo_b = q.cpad_b / 8;
     p.nseg = q.nseg;
-    for (int j = 0; j < 2; j++) { p.seg_w[j] = q.seg_w[j]; p.seg_x0[j] = q.seg_x0[j]; p.ps[j] = q.ps; }
+    for (int j = 0; j < 4; j++) { p.seg_w[j] = q.seg_w[j]; p.seg_x0[j] = q.seg_x0[j]; p.ps[j] = q.ps; }
     const int nop = q.split ? 2 : 1;
     (void)nop;
     p.rh = q.rh;
@@ -938,17 +982,20 @@ extern "C" int lvg_convnd_wgrad(const void* x, const void* dy, void* dw, int dty
     p.split_stride = q.dw_elems;
     p.dw = q.nsplit > 1 ? (void*)part : dw;
     // NOTE the per-segment tile pitch: a stage tile of segment j is [block][rh][ps[j]][16 B] -- the box width IS the pitch
-    CUtensorMap tma0, tma1, tmb;
-    int rc = encode_map(&tma0, dy8, p.seg_w[0], ho, to, inst * p.nblk_a, wo, (int64_t)ho * wo, thw_a, p.ps[0], p.rh, 16);
-    if (rc) return rc;
-    if (p.nseg == 2) rc = encode_map(&tma1, dy8 + (size_t)p.seg_x0[1] * 16, p.seg_w[1], ho, to, inst * p.nblk_a, wo, (int64_t)ho * wo, thw_a, p.ps[1], p.rh, 16);
-    else tma1 = tma0;
-    if (rc) return rc;
-    rc = encode_map(&tmb, x8, wd, h, t, inst * p.nblk_b, wd, (int64_t)h * wd, thw_b, p.ps[0], p.rh, q.nt / 8);
-    if (rc) return rc;
+    WgradMaps maps;
+    memset(&maps, 0, sizeof(maps));
+    for (int j = 0; j < p.nseg; j++) {
+        const int rc = encode_map(&maps.a[j], dy8 + (size_t)p.seg_x0[j] * 16, p.seg_w[j], ho, to, inst * p.nblk_a, wo, (int64_t)ho * wo, thw_a,
+                                  p.ps[j], p.rh, 1, 16);
+        if (rc) return rc;
+    }
+    {
+        const int rc = encode_map(&maps.b, x8, wd, h, t, inst * p.nblk_b, wd, (int64_t)h * wd, thw_b, p.ps[0], p.rh, 1, q.nt / 8);
+        if (rc) return rc;
+    }
     LVG_CUDA(cudaFuncSetAttribute(conv_wgrad_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((unsigned)(q.ntiles * kt * kh * q.nsplit), (unsigned)q.mt, (unsigned)groups);
-    conv_wgrad_v2_kernel<<<grid, kThreads, smem, s>>>(tma0, tma1, tmb, p);
+    conv_wgrad_v2_kernel<<<grid, kThreads, smem, s>>>(maps, p);
     LVG_LAUNCH_CHECK();
     if (q.nsplit > 1) {
         int64_t blocks = (q.dw_elems + 255) / 256;

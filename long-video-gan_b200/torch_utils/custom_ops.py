@@ -595,7 +595,7 @@ class ConvNdPlugin:
             return False
         if x.shape[1] != w.shape[1] * groups or w.shape[0] % groups != 0 or x.shape[0] * groups > 65535 or x.numel() == 0:
             return False
-        return all(s + 2 * p - kk + 1 >= 1 for s, p, kk in zip(sp, pad, k)) and sp[2] + 2 * pad[2] <= 480
+        return all(s + 2 * p - kk + 1 >= 1 for s, p, kk in zip(sp, pad, k))
 
     def _workspace(self, device, need):
         if need < 0:

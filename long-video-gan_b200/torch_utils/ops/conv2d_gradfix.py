@@ -51,11 +51,20 @@ def _auto_install():
     if os.environ.get('LVG_NATIVE_CONV', '1') != '0' and torch.cuda.is_available():
         try:
             install_native(True)
-        except RuntimeError:
+        except (RuntimeError, OSError, AttributeError):
             pass
 
 
+def _engine():
+    """'nd' (default): the TMA-fed engine of csrc/conv_igemm.cu for every dtype / stride it covers; 'r1': the round-1
+    kernels (fp16, stride 1) first."""
+    return os.environ.get('LVG_CONV_ENGINE', 'nd')
+
+
 def conv2d(input, weight, bias=None, stride=1, padding=0, dilation=1, groups=1):
+    if input.device.type == 'cuda' and _engine() == 'nd' and os.environ.get('LVG_NATIVE_CONV', '1') != '0':
+        from . import conv_nd
+        return conv_nd.conv2d(input, weight, bias, stride, padding, dilation, groups)
     if _native is None and input.device.type == 'cuda' and not _auto_install.done:
         _auto_install.done = True
         _auto_install()
@@ -144,5 +153,8 @@ class _Conv2dWgrad(torch.autograd.Function):
 
 
 def conv_transpose2d(input, weight, bias=None, stride=1, padding=0, output_padding=0, groups=1, dilation=1):
+    if input.device.type == 'cuda' and os.environ.get('LVG_NATIVE_CONV', '1') != '0':
+        from . import conv_nd
+        return conv_nd.conv_transpose2d(input, weight, bias, stride, padding, output_padding, groups, dilation)
     return torch.nn.functional.conv_transpose2d(input=input, weight=weight, bias=bias, stride=stride, padding=padding,
                                                 output_padding=output_padding, groups=groups, dilation=dilation)
