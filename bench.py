@@ -44,12 +44,18 @@ WORKLOADS = {
 }
 GRAD_ELEMS = {'lres': (83_200_000, 46_400_000), 'sres': (27_200_000, 24_000_000)}   # G, D parameter counts
 HOT_OPS = ('bias_act', 'upfirdn2d', 'filtered_lrelu', 'conv2d_resample', 'conv2d')
+CONV_OPS = ('conv3d', 'conv1d')      # F.conv3d / F.conv1d of the low-res networks: replayed with --scope full
 
 
-def load_trace(name):
+SCOPE = {'ops': HOT_OPS, 'full': HOT_OPS + CONV_OPS}
+_scope = 'full'
+
+
+def load_trace(name, scope=None):
     fname, gkey, dkey, batch, frames = WORKLOADS[name]
+    keep = SCOPE[scope or _scope]
     tr = json.load(open(os.path.join(ROOT, 'workloads', fname)))
-    return [c for c in tr[gkey] if c['op'] in HOT_OPS], [c for c in tr[dkey] if c['op'] in HOT_OPS], batch, frames
+    return [c for c in tr[gkey] if c['op'] in keep], [c for c in tr[dkey] if c['op'] in keep], batch, frames
 
 
 def make_filter(shape, gen):
@@ -81,9 +87,9 @@ def run_backward(y, leaves, dy):
 class Replay:
     def __init__(self, calls, batch, device, dtype_policy, ops=None):
         if ops is None:
-            from torch_utils.ops import bias_act, upfirdn2d, filtered_lrelu, conv2d_resample, conv2d_gradfix
+            from torch_utils.ops import bias_act, upfirdn2d, filtered_lrelu, conv2d_resample, conv2d_gradfix, conv_nd
             ops = dict(bias_act=bias_act, upfirdn2d=upfirdn2d, filtered_lrelu=filtered_lrelu, conv2d_resample=conv2d_resample,
-                       conv2d=conv2d_gradfix)
+                       conv2d=conv2d_gradfix, conv3d=conv_nd.conv3d, conv1d=conv_nd.conv1d)
         self.ops = ops
         self.last_y = None
         self.device = device
@@ -103,7 +109,10 @@ class Replay:
                 continue
             x = self._buf('x', scaled(c['x'], batch), dt)
             item = dict(c=c, x=x, dtype=dt)
-            if c['op'] == 'bias_act':
+            if c['op'] in CONV_OPS:
+                item['w'] = (torch.randn(*c['w'], device=device) / np.sqrt(np.prod(c['w'][1:]))).to(dt)
+                item['nograd'] = c['groups'] > 1          # BlurredNoise.blur: fixed filters on a noise input (generator_lres.py:378-387)
+            elif c['op'] == 'bias_act':
                 item['b'] = torch.randn(c['x'][c['dim']], device=device, dtype=dt) if c['b'] else None
             elif c['op'] == 'upfirdn2d':
                 item['f'] = None if c['f'] is None else make_filter(c['f'], gen).to(device)
@@ -123,6 +132,8 @@ class Replay:
                 it['bytes_fwd'] = (it['x'].numel() + y.numel()) * y.element_size()
                 # bias_act: relu / lrelu keep 2-bit codes for the backward pass (x + y + n/4 forward with grad, dy + dx + n/4
                 # backward); other activations re-read y in the backward pass (dy + y + dx)
+                if it['c']['op'] in CONV_OPS + ('conv2d',) or (it['c']['op'] == 'conv2d_resample'):
+                    it['flops_fwd'] = 2.0 * y.numel() * float(np.prod(it['w'].shape[1:]))
                 coded = it['c']['op'] == 'bias_act' and it['c']['act'] in ('relu', 'lrelu')
                 it['bytes_fwd_grad'] = it['bytes_fwd'] + (y.numel() // 4 if coded else 0)
                 it['bytes_bwd'] = it['bytes_fwd'] + (y.numel() // 4 if coded else (y.numel() * y.element_size() if it['c']['op'] == 'bias_act' else 0))
@@ -147,6 +158,8 @@ class Replay:
                                                              clamp=c['clamp'], flip_filter=c['flip_filter'])
         if c['op'] == 'conv2d':
             return self.ops['conv2d'].conv2d(x, it['w'], padding=c['padding'], groups=it['groups'])
+        if c['op'] in CONV_OPS:
+            return self.ops[c['op']](x, it['w'], None, c['stride'], c['padding'], 1, c['groups'])
         return self.ops['conv2d_resample'].conv2d_resample(x, it['w'], f=it['f'], up=c['up'], down=c['down'], padding=c['padding'],
                                                            groups=c['groups'], flip_weight=c['flip_weight'], flip_filter=c['flip_filter'])
 
@@ -157,6 +170,10 @@ class Replay:
 
     def forward_backward(self, timer=None, lo=0, hi=None):
         for it in self.items[lo:hi]:
+            if it.get('nograd'):
+                with torch.no_grad():
+                    self.last_y = self._fwd(it, it['x'])
+                continue
             x = it['x'].detach().requires_grad_(True)
             leaves = [x]
             b = it.get('b')
@@ -169,14 +186,15 @@ class Replay:
             if saved_w is not None:
                 it['w'] = saved_w.detach().requires_grad_(True)
                 leaves.append(it['w'])
-            if timer is not None and it['c']['op'] == timer.op:
+            if timer is not None and it['c']['op'] in timer.ops:
+                flops = it.get('flops_fwd')
                 timer.start()
                 y = self._fwd(it, x)
-                timer.stop(it['bytes_fwd_grad'])
+                timer.stop(it['bytes_fwd_grad'] if flops is None else flops)
                 if y.requires_grad:
                     timer.start()
                     run_backward(y, leaves, it['dy'])
-                    timer.stop(it['bytes_bwd'])
+                    timer.stop(it['bytes_bwd'] if flops is None else 2.0 * flops)
             else:
                 y = self._fwd(it, x)
                 if y.requires_grad:
@@ -191,7 +209,7 @@ class KernelTimer:
     """CUDA-event timing of individual calls inside the timed region (events on the current stream)."""
 
     def __init__(self, op='bias_act'):
-        self.op = op            # which replayed op gets the event pairs (the step's dominant kernel)
+        self.ops = (op,) if isinstance(op, str) else tuple(op)      # which replayed ops get the event pairs (the step's dominant kernel)
         self.pairs = []
         self._cur = None
 
@@ -257,11 +275,28 @@ class ClockSampler:
                 'samples': len(self.samples)}
 
 
-def measured_peak():
+def measured_peak(kind='hbm'):
     try:
-        return json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))['hbm_gbs'], 'measured (MEASURED_PEAKS.json hbm_gbs)'
+        mp = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+        if kind == 'hbm':
+            return mp['hbm_gbs'], 'measured (MEASURED_PEAKS.json hbm_gbs)'
+        return mp['bf16_tflops_sustained'], 'measured (MEASURED_PEAKS.json bf16_tflops_sustained: the kernel is timed inside a long step)'
     except Exception:
-        return 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)'
+        return (6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)') if kind == 'hbm' else (1400.0, 'fallback (B200_PROFILING.md ~1.4 PFLOP/s sustained)')
+
+
+def metric_name(scope):
+    return ('frames/sec (G+D train step: every convolution and torch_utils.ops call of the forward/backward passes, replayed)' if scope == 'full'
+            else 'frames/sec (G+D train step, hot-path operator trace)')
+
+
+def reference_ops(ref):
+    """The reference's side of the replay: its own ops modules; its convolutions are torch.nn.functional (cuDNN / CPU), fp32 with
+    TF32 off as train_lres.py:269-270 sets it."""
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    return dict(bias_act=ref.bias_act, upfirdn2d=ref.upfirdn2d, filtered_lrelu=ref.filtered_lrelu, conv2d_resample=ref.conv2d_resample,
+                conv2d=ref.conv2d_gradfix, conv3d=torch.nn.functional.conv3d, conv1d=torch.nn.functional.conv1d)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -285,8 +320,7 @@ def cpu_sample_reference(workload, budget_s=20.0):
         return None
     threads = _host_threads()
     ref = ref_cuda.load()
-    ops = dict(bias_act=ref.bias_act, upfirdn2d=ref.upfirdn2d, filtered_lrelu=ref.filtered_lrelu,
-               conv2d_resample=ref.conv2d_resample, conv2d=ref.conv2d_gradfix)
+    ops = reference_ops(ref)
     g_calls, d_calls, batch, frames = load_trace(workload)
     # groups = (network, op): sampled calls of a group extrapolate to the group's bytes (cost per byte differs by op);
     # calls are visited largest first within a fixed round-robin over the groups: a short budget samples every group and
@@ -295,9 +329,17 @@ def cpu_sample_reference(workload, budget_s=20.0):
     for net, calls in (('G', g_calls), ('D', d_calls)):
         for c in calls:
             groups.setdefault((net, c['op']), []).append(c)
+    def weight(c):          # what a call's cost scales with inside its group: elements; multiply-adds for the convolutions
+        if c['op'] in CONV_OPS:
+            k = c['w'][2:]
+            pad = c['padding'] if isinstance(c['padding'], (list, tuple)) else [c['padding']] * len(k)
+            out = int(np.prod([s + 2 * p - kk + 1 for s, p, kk in zip(c['x'][2:], pad, k)]))
+            return float(c['x'][0] * c['w'][0] * out) * float(np.prod(c['w'][1:]))
+        return float(np.prod(c['x']))
+
     for k in groups:
-        groups[k].sort(key=lambda c: -int(np.prod(c['x'])))
-    stat = {k: dict(tf=0.0, tb=0.0, done=0, total=sum(int(np.prod(c['x'])) for c in v)) for k, v in groups.items()}
+        groups[k].sort(key=lambda c: -weight(c))
+    stat = {k: dict(tf=0.0, tb=0.0, done=0, total=sum(weight(c) for c in v)) for k, v in groups.items()}
     order, depth = [], 0
     while True:
         row = [(k, v[depth]) for k, v in groups.items() if depth < len(v)]
@@ -329,7 +371,7 @@ def cpu_sample_reference(workload, budget_s=20.0):
         st = stat[key]
         st['tf'] += t1 - t0
         st['tb'] += t2 - t1
-        st['done'] += int(np.prod(c['x']))
+        st['done'] += weight(c)
         n_done += 1
     if any(st['done'] == 0 for st in stat.values()):
         return None
@@ -343,7 +385,7 @@ def cpu_sample_reference(workload, budget_s=20.0):
     used = time.perf_counter() - t_start
     desc = (f"reference's own _ref ops (oracle/_ref/src, torch {torch.__version__} CPU, {threads} threads): forward+backward of {n_done} of "
             f"{len(order)} hot-path op calls of one G+D pass at batch 1 (of {batch}), {used:.1f} s, covering "
-            f"{100.0 * sum(done_bytes.values()) / max(1, sum(all_bytes.values())):.0f} % of the pass's elements (rest extrapolated per (network, op) group by elements); "
+            f"{100.0 * sum(done_bytes.values()) / max(1, sum(all_bytes.values())):.0f} % of the pass's work (rest extrapolated per (network, op) group: by elements, by multiply-adds for convolutions); "
             f"step = G 2 fwd + 1 bwd, D 3 fwd + 3 bwd")
     return fps, desc, threads, 'reference'
 
@@ -357,7 +399,7 @@ def cpu_sample_port(workload, budget_s=20.0):
     g_calls, d_calls, batch, frames = load_trace(workload)
     gen = torch.Generator().manual_seed(0)
     rng = np.random.default_rng(0)
-    calls = [c for c in g_calls + d_calls if c['op'] not in ('conv2d_resample', 'conv2d')]
+    calls = [c for c in g_calls + d_calls if c['op'] not in ('conv2d_resample', 'conv2d') + CONV_OPS]
     prepared = []
     for c in calls:
         item = {'c': c, 'x': rng.standard_normal(c['x'], dtype=np.float32)}
@@ -455,10 +497,12 @@ class GradExchange:
 
 # ---------------------------------------------------------------------------------------------
 
-def run_ours(args, workload, steps, rank, world, local_rank, device, with_cpu, with_refcuda):
+def run_ours(args, workload, scope, steps, rank, world, local_rank, device, with_cpu, with_refcuda):
     """One workload through this repository's ops on the GPU -> the JSON fields of its line."""
+    global _scope
     import torch.distributed as dist
     from torch_utils import custom_ops
+    _scope = scope
     g_calls, d_calls, batch, frames = load_trace(workload)
     policy = 'mixed' if workload == 'sres' else 'fp32'
     G = Replay(g_calls, batch, device, policy)
@@ -478,13 +522,14 @@ def run_ours(args, workload, steps, rank, world, local_rank, device, with_cpu, w
     if workload == 'lres':
         host_video = torch.empty((batch, 3, frames, 36, 64), dtype=torch.float32).uniform_(-1, 1).pin_memory()
         dev_video = torch.empty_like(host_video, device=device)
-        w_in = torch.randn(entry['x'].shape[1], 3, 1, 1, 1, device=device) / 3 ** 0.5
-        assert tuple(entry['x'].shape) == (batch, w_in.shape[0], frames, 64, 64), entry['x'].shape
+        direct = entry['x'].shape[1] == 3        # --scope full: the first replayed D op IS that first conv3d on the padded video
+        w_in = None if direct else torch.randn(entry['x'].shape[1], 3, 1, 1, 1, device=device) / 3 ** 0.5
+        assert tuple(entry['x'].shape) == (batch, entry['x'].shape[1], frames, 64, 64), entry['x'].shape
 
         def ingest():
             dev_video.copy_(host_video, non_blocking=True)
             v = torch.nn.functional.pad(dev_video, (0, 0, 14, 14))
-            entry['x'].copy_(torch.nn.functional.conv3d(v, w_in))
+            entry['x'].copy_(v if direct else torch.nn.functional.conv3d(v, w_in))
     else:
         host_video = torch.empty(tuple(entry['x'].shape), dtype=torch.float32).uniform_(-1, 1).pin_memory()
         stage = torch.empty_like(host_video, device=device)
@@ -560,7 +605,7 @@ def run_ours(args, workload, steps, rank, world, local_rank, device, with_cpu, w
     for _ in range(warm):
         step()
     torch.cuda.synchronize()
-    dominant_op = 'bias_act' if workload == 'lres' else 'filtered_lrelu'
+    dominant_op = ('conv3d' if scope == 'full' else 'bias_act') if workload == 'lres' else 'filtered_lrelu'
     launches_per_step = None
     if args.launch == 'graph':
         # Capture the two halves of the step (the gradient exchange stays outside: eager autograd + NCCL between the replays).
@@ -609,8 +654,9 @@ def run_ours(args, workload, steps, rank, world, local_rank, device, with_cpu, w
     value = frames_per_step * steps / (ms_total / 1000.0)
     e2e_value = frames_per_step * steps / (ms_e2e / 1000.0)
     k_ms, k_bytes, k_n = timer.summary()
-    peak, peak_src = measured_peak()
-    achieved = k_bytes / (k_ms / 1000.0) / 1e9 if k_ms > 0 else 0.0
+    tensor_bound = dominant_op == 'conv3d'
+    peak, peak_src = measured_peak('tensor' if tensor_bound else 'hbm')
+    achieved = k_bytes / (k_ms / 1000.0) / (1e12 if tensor_bound else 1e9) if k_ms > 0 else 0.0
     if graphs:
         k_share = k_ms / (ms_total / steps) if ms_total else None
         k_how = (f'CUDA events around every {dominant_op} call of one extra eager step (stream pre-filled by a spin kernel so that the '
@@ -620,7 +666,7 @@ def run_ours(args, workload, steps, rank, world, local_rank, device, with_cpu, w
         k_how = f'CUDA events around every {dominant_op} call inside the timed region'
 
     traffic, traffic_note = None, None
-    if workload == 'lres':
+    if workload == 'lres' and not tensor_bound:
         try:    # DRAM bytes of the dominant kernel from the committed ncu --set full capture (bench.py never runs under ncu)
             tr = json.load(open(os.path.join(ROOT, 'profiles', 'r01_traffic.json')))
             f, b = tr['bias_act_fwd'], tr['bias_act_bwd_fused_db']
@@ -631,23 +677,27 @@ def run_ours(args, workload, steps, rank, world, local_rank, device, with_cpu, w
             pass
     res = config = None
     if rank == 0:
-        config = {'workload': f'{workload}: train_{workload} op trace (torch_utils.ops calls of G+D update), per-GPU batch {batch}, '
+        what = ('convolutions + torch_utils.ops calls of G+D update' if scope == 'full' else 'torch_utils.ops calls of G+D update')
+        config = {'workload': f'{workload}: train_{workload} op trace ({what}), per-GPU batch {batch}, '
                               f'{frames} frames/sample, {"64x36" if workload == "lres" else "256x144 from 64x36"}',
                   'global_batch': batch * world, 'parallelism': f'dp{world}',
                   'l2': 'inputs and outputs of the replayed calls exceed L2 (largest tensors 0.75 GB); buffers shared per shape',
                   'launch': ('cuda_graph (step captured once, replayed' + ('; between the graph segments: real autograd backward over real Parameters -> lvg_dist.FlatGradSync(overlap=True) hooks -> bucketed NCCL all-reduces overlapping the rest of the pass)' if world > 1 else ')')) if args.launch == 'graph'
                             else 'eager (every call launched from Python)'}
-        res = {'value': value, 'unit': 'frames/s', 'n_gpus': world, 'steps': steps, 'warmup': warm,
+        res = {'metric': metric_name(scope), 'value': value, 'unit': 'frames/s', 'n_gpus': world, 'steps': steps, 'warmup': warm,
                'ms_per_step': ms_total / steps,
                'dtype': 'f32' if policy == 'fp32' else 'f16/f32 mixed (fp16 layers as the reference config)',
                'config': config, 'gpu_launches': int(launches),
                'e2e': {'value': e2e_value, 'unit': 'frames/s', 'h2d_bytes_per_step': host_video.numel() * 4, 'd2h_bytes_per_step': 4,
                        'eager_value': frames_per_step * steps / (ms_e2e_eager / 1000.0),
                        'path': 'pinned host video -> device -> first replayed discriminator op; first element of the last discriminator output -> host'},
-               'roofline': {'bound': 'hbm', 'kernel': 'bias_act (vector kernel: forward writing 2-bit sign/clamp codes + backward from the codes with fused dx/db)' if dominant_op == 'bias_act' else
-                            'filtered_lrelu (fused up-FIR / lrelu / down-FIR; FP32-issue-bound, its HBM figure is shown for reference)',
+               'roofline': {'bound': 'tensor' if tensor_bound else 'hbm',
+                            'kernel': {'bias_act': 'bias_act (vector kernel: forward writing 2-bit sign/clamp codes + backward from the codes with fused dx/db)',
+                                       'filtered_lrelu': 'filtered_lrelu (fused up-FIR / lrelu / down-FIR; FP32-issue-bound, its HBM figure is shown for reference)',
+                                       'conv3d': 'conv_igemm_kernel / conv_wgrad_v2_kernel (TMA-fed tcgen05 implicit GEMM; fp32 layers as bf16 hi/lo split: 3 tensor-core '
+                                                 'products per algorithmic product, so the tensor pipe executes 3x the achieved figure) incl. its operand re-tiling passes'}[dominant_op],
                             'achieved': achieved,
-                            'peak': peak, 'peak_source': peak_src, 'unit': 'GB/s', 'frac': achieved / peak if peak else None,
+                            'peak': peak, 'peak_source': peak_src, 'unit': 'TFLOP/s' if tensor_bound else 'GB/s', 'frac': achieved / peak if peak else None,
                             'launches_timed': k_n, 'share_of_step': k_share, 'traffic': traffic, 'traffic_note': traffic_note, 'timing': k_how},
                'clocks': clocks}
     # the same trace through the REFERENCE'S OWN CUDA ops on this GPU (oracle/_ref: its plugins built unmodified for sm_100a,
@@ -660,8 +710,7 @@ def run_ours(args, workload, steps, rank, world, local_rank, device, with_cpu, w
                 graphs.clear()
                 torch.cuda.empty_cache()
                 ref = ref_cuda.load()
-                rops = dict(bias_act=ref.bias_act, upfirdn2d=ref.upfirdn2d, filtered_lrelu=ref.filtered_lrelu,
-                            conv2d_resample=ref.conv2d_resample, conv2d=ref.conv2d_gradfix)
+                rops = reference_ops(ref)
                 RG, RD = Replay(g_calls, batch, device, policy, ops=rops), Replay(d_calls, batch, device, policy, ops=rops)
 
                 def rstep():
@@ -699,6 +748,9 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--workload', default='both', choices=sorted(WORKLOADS) + ['both'],
                     help="both (default): the line's value is the lres step (BASELINE configs[1]); the sres step (configs[2]) is measured in the same run and reported under the key sres")
+    ap.add_argument('--scope', default='full', choices=['full', 'ops'],
+                    help='full (default): the F.conv3d / F.conv1d calls of the low-res networks are part of the replayed step (on the tensor-core engine); '
+                         'ops: only the torch_utils.ops calls (the round-1 metric; also reported under ops_only in the default run)')
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--cpu-budget', type=float, default=12.0)
     ap.add_argument('--no-cpu', action='store_true')
@@ -710,8 +762,10 @@ def main():
     rank = int(os.environ.get('RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))
     local_rank = int(os.environ.get('LOCAL_RANK', 0))
+    global _scope
     primary = 'lres' if args.workload == 'both' else args.workload
-    metric = 'frames/sec (G+D train step, hot-path operator trace)'
+    _scope = args.scope
+    metric = metric_name(args.scope)
 
     if args.impl == 'reference':
         # the reference's own CPU implementation of the path on the box's host cores (rank 0 only; all host threads)
@@ -745,11 +799,14 @@ def main():
     from torch_utils import custom_ops
     custom_ops.load_library()
 
-    res = run_ours(args, primary, args.steps, rank, world, local_rank, device, with_cpu=not args.no_cpu, with_refcuda=not args.no_ref_cuda)
-    sres = None
+    res = run_ours(args, primary, args.scope, args.steps, rank, world, local_rank, device, with_cpu=not args.no_cpu, with_refcuda=not args.no_ref_cuda)
+    sres = ops_only = None
     if args.workload == 'both':
         torch.cuda.empty_cache()
-        sres = run_ours(args, 'sres', max(2, min(args.steps, 5)), rank, world, local_rank, device, with_cpu=False,
+        if args.scope == 'full':
+            ops_only = run_ours(args, primary, 'ops', args.steps, rank, world, local_rank, device, with_cpu=False, with_refcuda=not args.no_ref_cuda)
+            torch.cuda.empty_cache()
+        sres = run_ours(args, 'sres', 'ops', max(2, min(args.steps, 5)), rank, world, local_rank, device, with_cpu=False,
                         with_refcuda=not args.no_ref_cuda)
     if rank == 0:
         out = {'metric': metric, 'value': res['value'], 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps, 'warmup': res['warmup'],
@@ -758,6 +815,8 @@ def main():
         for k in ('config', 'gpu_launches', 'e2e', 'roofline', 'clocks', 'ref_cuda', 'cpu_baseline'):
             if k in res:
                 out[k] = res[k]
+        if ops_only is not None:
+            out['ops_only'] = {k: ops_only[k] for k in ('metric', 'value', 'unit', 'steps', 'ms_per_step', 'gpu_launches', 'e2e', 'roofline', 'ref_cuda') if k in ops_only}
         if sres is not None:
             out['sres'] = {k: sres[k] for k in ('value', 'unit', 'steps', 'warmup', 'ms_per_step', 'dtype', 'config', 'gpu_launches', 'e2e',
                                                 'roofline', 'ref_cuda') if k in sres}

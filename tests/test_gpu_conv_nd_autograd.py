@@ -1,0 +1,86 @@
+"""torch_utils/ops/conv_nd.py on the GPU: conv1d / conv2d / conv3d / conv_transpose2d through autograd (first order, and
+the R1-style second order) on the tensor-core engine against torch's fp64 autograd of the same graph; the functional
+proxy running conv3d / conv1d blocks shaped like the low-res networks' (generator_lres.py:83-125, discriminator_lres.py:108-213)."""
+import math
+import types
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from torch_utils.ops import conv_nd, conv2d_gradfix, bias_act
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+
+
+def rnd(shape, seed, scale=1.0):
+    g = torch.Generator(device=DEV).manual_seed(seed)
+    return torch.randn(*shape, generator=g, device=DEV, dtype=torch.float64) * scale
+
+
+CASES = [
+    ('conv3d', (2, 24, 6, 9, 16), (40, 24, 3, 3, 3), dict(padding=(1, 1, 1))),
+    ('conv3d', (1, 16, 5, 18, 32), (16, 16, 1, 3, 3), dict(padding=(0, 1, 1))),
+    ('conv3d', (1, 16, 9, 8, 8), (24, 16, 5, 3, 3), dict(padding=(2, 1, 1))),
+    ('conv1d', (2, 64, 16), (48, 64, 3), dict(padding=1)),
+    ('conv2d', (1, 3 * 24, 20, 26), (3 * 40, 24, 3, 3), dict(padding=2, groups=3)),
+    ('conv2d', (2, 32, 33, 40), (48, 32, 3, 3), dict(padding=0, stride=2)),
+]
+
+
+@pytest.mark.parametrize('dtype', [torch.float16, torch.float32], ids=['f16', 'f32'])
+@pytest.mark.parametrize('fn,xs,ws,kw', CASES, ids=[f'{c[0]}-{i}' for i, c in enumerate(CASES)])
+def test_autograd_first_and_second_order(fn, xs, ws, kw, dtype):
+    x0, w0 = rnd(xs, 1).to(dtype), rnd(ws, 2, 1 / math.sqrt(math.prod(ws[1:]))).to(dtype)
+    res = []
+    for native in (True, False):
+        dt = dtype if native else torch.float64
+        x, w = x0.to(dt).requires_grad_(True), w0.to(dt).requires_grad_(True)
+        y = getattr(conv_nd if native else F, fn)(x, w, None, **kw)
+        v = rnd(tuple(y.shape), 3).to(dt)
+        gx, gw = torch.autograd.grad((y * v).sum(), [x, w], create_graph=True)
+        ggw, = torch.autograd.grad(gx.square().sum(), [w])            # R1: d |dL/dx|^2 / dw
+        res.append([t.detach().double() for t in (y, gx, gw, ggw)])
+    tol = 4e-3 if dtype == torch.float16 else 1e-4
+    for name, a, r in zip(('y', 'dx', 'dw', 'd(|dx|^2)/dw'), *res):
+        err = float((a - r).abs().max() / r.abs().max())
+        assert err <= tol * (4 if name.startswith('d(') else 1), f'{name}: {err:.3e}'
+
+
+@pytest.mark.parametrize('dtype', [torch.float16, torch.float32], ids=['f16', 'f32'])
+def test_conv_transpose2d(dtype):
+    x, w = rnd((2, 32, 9, 11), 4).to(dtype), rnd((32, 24, 3, 3), 5, 0.1).to(dtype)
+    for kw in (dict(stride=2, padding=1, output_padding=1), dict(stride=1, padding=1), dict(stride=2, padding=0)):
+        xg, wg = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
+        y = conv2d_gradfix.conv_transpose2d(xg, wg, **kw)
+        r = F.conv_transpose2d(x.double().requires_grad_(True), w.double(), **kw)
+        tol = 3e-3 if dtype == torch.float16 else 1e-4
+        assert y.shape == r.shape and float((y.double() - r).abs().max()) <= tol * float(r.abs().max())
+        gx, gw = torch.autograd.grad(y.float().square().sum(), [xg, wg])
+        xr, wr = x.double().requires_grad_(True), w.double().requires_grad_(True)
+        rx, rw = torch.autograd.grad(F.conv_transpose2d(xr, wr, **kw).square().sum(), [xr, wr])
+        assert float((gx.double() - rx).abs().max()) <= 3 * tol * float(rx.abs().max())
+        assert float((gw.double() - rw).abs().max()) <= 3 * tol * float(rw.abs().max())
+
+
+def test_functional_proxy_runs_a_lowres_style_block():
+    # a model file's view: F.conv3d -> bias_act -> F.conv3d(1x1x1), then a conv1d stack -- through the proxy
+    mod = types.ModuleType('fake_lres_model')
+    mod.F = F
+    conv_nd.install_functional(mod)
+    x = rnd((2, 32, 8, 9, 16), 6).float().requires_grad_(True)
+    w1, w2 = rnd((48, 32, 3, 3, 3), 7, 0.03).float().requires_grad_(True), rnd((16, 48, 1, 1, 1), 8, 0.1).float().requires_grad_(True)
+    b1 = rnd((48,), 9).float().requires_grad_(True)
+
+    def block(Fm):
+        h = Fm.conv3d(x, w1, padding=(1, 1, 1))
+        h = bias_act.bias_act(h, b1, act='lrelu', clamp=256)
+        return Fm.conv3d(h, w2)
+    y = block(mod.F)
+    r = block(F)
+    assert float((y - r).abs().max()) <= 1e-4 * float(r.abs().max())
+    g = torch.autograd.grad(y.square().sum(), [x, w1, w2, b1])
+    gr = torch.autograd.grad(r.square().sum(), [x, w1, w2, b1])
+    for a, b in zip(g, gr):
+        assert float((a - b).abs().max()) <= 2e-4 * float(b.abs().max())
