@@ -879,6 +879,10 @@ WgradPlan wgrad_plan(int dtype, int n, int groups, int cin, int cout, int t, int
     const int w0 = (wo + q.nseg - 1) / q.nseg;
     for (int j = 0; j < 4; j++) { q.seg_x0[j] = j * w0; q.seg_w[j] = j < q.nseg ? (wo - j * w0 < w0 ? wo - j * w0 : w0) : 0; }
     q.ps = round_up(w0 + kw - 1, 8);                           // rows x pitch must be a multiple of 16 pixels (one MMA K step)
+    {   // a pitch of 8 mod 16 needs row pairs: take it only when two stages of two rows fit with a useful n-tile
+        const int nop0 = q.split ? 2 : 1;
+        if (q.ps % 16 != 0 && 2 * nop0 * (16 + 64 / 8) * 2 * q.ps * 16 > 200 * 1024) q.ps = round_up(q.ps, 16);
+    }
     {   // the smallest stage (1 or 2 rows) must leave room for two stages
         const int min_rows = q.ps % 16 != 0 ? 2 : 1;
         const int nop0 = q.split ? 2 : 1;

@@ -88,13 +88,22 @@ def test_conv2d_double_backward_matches_torch():
     assert_close(gw, gwr, 2e-2, 'second order')
 
 
-def test_unsupported_shapes_use_the_library_path():
-    x = torch.randn(1, 8, 16, 16, device=DEV)                       # fp32: outside the envelope
+def test_envelopes_of_the_two_engines():
+    x = torch.randn(1, 8, 16, 16, device=DEV)
     w = torch.randn(8, 8, 3, 3, device=DEV)
-    assert not conv2d_gradfix._native.supported(x, w, (1, 1), (1, 1), (1, 1), 1)
-    assert torch.equal(conv2d_gradfix.conv2d(x, w, padding=1), F.conv2d(x, w, padding=1))
     xh, wh = x.half(), w.half()
-    assert not conv2d_gradfix._native.supported(xh, wh, (2, 2), (1, 1), (1, 1), 1)    # strided
+    # round-1 kernels: fp16, stride 1 only
+    assert not conv2d_gradfix._native.supported(x, w, (1, 1), (1, 1), (1, 1), 1)
+    assert not conv2d_gradfix._native.supported(xh, wh, (2, 2), (1, 1), (1, 1), 1)
+    # the TMA-fed engine (default route of conv2d_gradfix.conv2d) also takes fp32 (bf16 hi/lo split) and strides ...
+    torch.backends.cudnn.allow_tf32 = False
+    y = conv2d_gradfix.conv2d(x, w, padding=1)
+    r = F.conv2d(x.double(), w.double(), padding=1)
+    assert not torch.equal(y, F.conv2d(x, w, padding=1)) and float((y.double() - r).abs().max()) <= 1e-4 * float(r.abs().max())
+    ys = conv2d_gradfix.conv2d(xh, wh, stride=2, padding=1)
+    assert float((ys.double() - F.conv2d(xh.double(), wh.double(), stride=2, padding=1)).abs().max()) <= 3e-3 * float(r.abs().max())
+    # ... and leaves dilation to the library, bit for bit
+    assert torch.equal(conv2d_gradfix.conv2d(x, w, padding=2, dilation=2), F.conv2d(x, w, padding=2, dilation=2))
 
 
 _CV = golden('conv')
