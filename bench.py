@@ -377,9 +377,9 @@ def cpu_sample_reference(workload, budget_s=20.0):
         st['tb'] += t2 - t1
         st['done'] += weight(c)
         n_done += 1
-    for key, v in groups.items():          # a group the budget did not reach: its cheapest call, so that every group has a rate
+    for key, v in groups.items():          # a group the budget did not reach: its median call, so that every group has a rate
         if stat[key]['done'] == 0:
-            c = v[-1]
+            c = v[len(v) // 2]
             rp = Replay([c], 1, torch.device('cpu'), 'fp32', ops=ops)
             it = rp.items[0]
             x = it['x'].detach().requires_grad_(True)

@@ -872,7 +872,7 @@ WgradPlan wgrad_plan(int dtype, int n, int groups, int cin, int cout, int t, int
     q.cpad_b = round_up(cin, 16);
     int nt_cap = (512 / kw) / 16 * 16;
     if (nt_cap > 256) nt_cap = 256;
-    if (q.split && nt_cap > 96) nt_cap = 96;
+    if (q.split && nt_cap > 128) nt_cap = 128;
     // column segments (a TMA box row is at most 128 pixels incl. the kw - 1 halo) and the common tile pitch
     q.nseg = (wo + 128 - kw) / (129 - kw);
     if (q.nseg < 1) q.nseg = 1;

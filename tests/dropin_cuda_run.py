@@ -21,10 +21,16 @@ if os.environ.get('LVG_REF_PLUGINS') == '1':
     ref_cuda.patch_custom_ops(_co)
 from model import generator_lres, discriminator_lres, generator_sres, discriminator_sres   # noqa: E402
 
+if os.environ.get('LVG_REF_PLUGINS') != '1':
+    # this repository's ops resolved: also hand the model files' F.conv3d / F.conv1d to the tensor-core engine (the files stay as they are)
+    from torch_utils.ops import conv_nd
+    patched = conv_nd.install_functional(generator_lres, discriminator_lres)
+    assert len(patched) == 2
 torch.backends.cudnn.allow_tf32 = False          # train_lres.py:269-270, train_sres.py
 torch.backends.cuda.matmul.allow_tf32 = False
 dev = torch.device('cuda')
-out = {'where': {'bias_act': _ba.__file__, 'plugin': type(_ba._plugin).__name__ if _ba._init() else None}}
+out = {'where': {'bias_act': _ba.__file__, 'plugin': type(_ba._plugin).__name__ if _ba._init() else None,
+                 'conv3d': type(generator_lres.F).__name__}}
 
 
 def grads(net):
@@ -53,8 +59,9 @@ out['lres_D_r1_gx'] = gx.detach().cpu()
 out['lres_D_grad'] = grads(D).cpu()
 del D, x, logits, gx
 
+FP16_RES = 0 if os.environ.get('LVG_FP32') == '1' else 4      # LVG_FP32=1: every layer in fp32 (the yardstick of the fp16 runs)
 torch.manual_seed(3)
-S = generator_sres.VideoGenerator(hr_height=144, hr_width=256, lr_height=36, lr_width=64, temporal_context=4, num_fp16_res=4,
+S = generator_sres.VideoGenerator(hr_height=144, hr_width=256, lr_height=36, lr_width=64, temporal_context=4, num_fp16_res=FP16_RES,
                                   fourfeats=False).to(dev)
 lr = (torch.rand(2, 3, 2 + 8, 36, 64, generator=torch.Generator().manual_seed(13)) * 2 - 1).to(dev)
 hr = S(lr)
@@ -66,8 +73,9 @@ del S
 
 torch.manual_seed(4)
 SD = discriminator_sres.VideoDiscriminator(channels=3, seq_length=2, lr_height=36, lr_width=64, hr_height=144, hr_width=256,
-                                           num_fp16_res=4).to(dev)
-hrv = hr.detach().float().clamp(-1, 1).requires_grad_(True)
+                                           num_fp16_res=FP16_RES).to(dev)
+# (an input of its own, so that the discriminator comparison does not inherit the generator's rounding)
+hrv = (torch.rand(2, 3, 2, 144, 256, generator=torch.Generator().manual_seed(15)) * 2 - 1).to(dev).requires_grad_(True)
 logits = SD(lr[:, :, 4:-4], hrv)
 out['sres_D'] = logits.detach().float().cpu()
 (torch.nn.functional.softplus(logits.float()).mean() * 4096.0).backward()   # scaled: the fp16 blocks' gradients stay normal numbers
