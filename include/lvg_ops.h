@@ -249,6 +249,17 @@ int lvg_convnd_wgrad(const void* x, const void* dy, void* dw, int dtype, int n, 
                      void* workspace, int64_t workspace_bytes, void* stream);
 
 /*
+ * Depthwise long FIR along the last axis (cross-correlation, no padding), fp32:
+ *   y[n][g][t] = sum_k w[g][k] * x[n][g][t + k],   x [n][groups][lin], w [groups][k], y [n][groups][lin - k + 1]
+ * -- BlurredNoise.blur of the low-res generator: F.conv1d(noise, blur_filters [128, 1, 5000], groups = 128)
+ * (model/generator_lres.py:378-387). Leading zero taps of each filter are skipped. `workspace`:
+ * lvg_fir1d_depthwise_workspace(groups) bytes. Forward only (the input is noise, the filters are buffers).
+ */
+int64_t lvg_fir1d_depthwise_workspace(int groups);
+int lvg_fir1d_depthwise(const float* x, const float* w, float* y, int n, int groups, int lin, int k,
+                        void* workspace, int64_t workspace_bytes, void* stream);
+
+/*
  * Post-processing of an all-reduced flat gradient buffer, in place and in one pass:
  *   g = g * scale;  NaN -> 0, +inf -> +limit, -inf -> -limit  (finite values untouched)
  * -- the `/ world_size * gain` + `nan_to_num(nan=0, posinf=1e5, neginf=-1e5)` tail of

@@ -70,8 +70,10 @@ struct Geom {
     static constexpr int A_SIZE = (TIH * P_IN > UXY_ROWS * P_UXY) ? TIH * P_IN : UXY_ROWS * P_UXY;
     static constexpr int B_SIZE = (TIH * P_UX > UXY_ROWS * P_DX) ? TIH * P_UX : UXY_ROWS * P_DX;
     static constexpr int CODE_BYTES = fir::round_up(TUHA * TUWA, 16);
-    static constexpr size_t smem_bytes(bool codes) {
-        return (size_t)(A_SIZE + B_SIZE + FU + FD) * sizeof(float) + (codes ? CODE_BYTES : 0);
+    static constexpr int SIGN_PITCH = TUWA / 4 + 2;                   // sign bytes per staged row (read mode)
+    static constexpr int SIGN_BYTES = fir::round_up(TUHA * SIGN_PITCH, 16);
+    static constexpr size_t smem_bytes(int mode) {
+        return (size_t)(A_SIZE + B_SIZE + FU + FD) * sizeof(float) + (mode == SIGN_WRITE ? CODE_BYTES : mode == SIGN_READ ? SIGN_BYTES : 0);
     }
 };
 
@@ -112,6 +114,22 @@ __global__ void __launch_bounds__(kThreads, (TOH <= 24 ? 3 : 2)) filtered_lrelu_
     const int tuw_e = (tow_e - 1) * DOWN + FD, tuh_e = (toh_e - 1) * DOWN + FD;
     const int nqx_e = (tuw_e + dxo + UP - 1) / UP, nqy_e = (tuh_e + dyo + UP - 1) / UP;
     const int tiw_e = fir::round_up(nqx_e, kR) + G::KU, tih_e = fir::round_up(nqy_e, kR) + G::KU;
+
+    // ---- stage 0 (read mode): this tile's slab of the sign tensor -> shared memory with coalesced byte loads, issued first
+    // so that their latency hides behind stages 1-2 (per-sample global byte loads in stage 3 cost 40 % of the kernel:
+    // long-scoreboard stalls). Bytes outside the tensor read as 0 = "unchanged", the operator's rule for such samples.
+    const int sgn_bx0 = (U0 - dxo + p.sx) >> 2;            // first staged byte column (floor division also for negatives)
+    if (MODE == SIGN_READ) {
+        const uint8_t* sgn = p.si + plane * (int64_t)p.s_h * p.s_wb;
+        const int gy0 = V0 - dyo + p.sy;
+        for (int i = threadIdx.x; i < G::TUHA * G::SIGN_PITCH; i += kThreads) {
+            const int row = i / G::SIGN_PITCH, bb = i - row * G::SIGN_PITCH;
+            const int gy = gy0 + row, gb = sgn_bx0 + bb;
+            uint8_t v = 0;
+            if ((unsigned)gy < (unsigned)p.s_h && (unsigned)gb < (unsigned)p.s_wb) v = __ldg(sgn + (int64_t)gy * p.s_wb + gb);
+            s_code[i] = v;
+        }
+    }
 
     // ---- stage 1: input tile (+ bias inside the image, zero outside) -> A
     // One warp per tile row, lanes along the row; the loop nest has compile-time trip counts and is fully
@@ -168,17 +186,15 @@ __global__ void __launch_bounds__(kThreads, (TOH <= 24 ? 3 : 2)) filtered_lrelu_
         const float slope = p.slope, clamp = p.clamp;
         const bool shrink = slope <= 1.f;                  // lrelu(v) = max(v, v*slope) for slope <= 1, min(...) otherwise
         const int Uax = U0 - dxo, Vay = V0 - dyo;          // global up-sampled coords of aligned sample (0, 0)
-        const uint8_t* sgn = (MODE == SIGN_READ) ? p.si + plane * (int64_t)p.s_h * p.s_wb : nullptr;
-        const int s_w = p.s_wb * 4;
         const int cols = nqx_e * UP;
+        const int qx0 = Uax + p.sx;
+        (void)Vay;
         auto activate = [&](float v, int row, int col, unsigned& code) {
             if (MODE == SIGN_READ) {
-                const int qx = Uax + col + p.sx, qy = Vay + row + p.sy;
-                if ((unsigned)qx < (unsigned)s_w && (unsigned)qy < (unsigned)p.s_h) {
-                    const unsigned s = sgn[(int64_t)qy * p.s_wb + (qx >> 2)] >> ((qx & 3) << 1);
-                    if (s & 1u) v *= slope;
-                    if (s & 2u) v = 0.f;
-                }
+                const int qx = qx0 + col;
+                const unsigned s = (unsigned)s_code[row * G::SIGN_PITCH + ((qx >> 2) - sgn_bx0)] >> ((qx & 3) << 1);
+                v = (s & 1u) ? v * slope : v;
+                v = (s & 2u) ? 0.f : v;
             } else if (MODE == SIGN_WRITE) {
                 // branch-free: selects only (the sign code is 2 if clamped, else 1 if negative)
                 const bool neg = v < 0.f;
@@ -302,7 +318,7 @@ int launch_cfg(FlParams& p, int mode, cudaStream_t s)
     p.tiles_y = (p.oh + TOH - 1) / TOH;
     const int64_t blocks = (int64_t)p.n * p.c * p.tiles_x * p.tiles_y;
     LVG_REQUIRE(blocks <= INT32_MAX, "filtered_lrelu: grid too large");
-    const size_t smem = G::smem_bytes(mode == SIGN_WRITE);
+    const size_t smem = G::smem_bytes(mode);
     void (*k)(FlParams) = nullptr;
     if (mode == SIGN_WRITE)     k = filtered_lrelu_kernel<T, UP, FU, DOWN, FD, TOW, TOH, SIGN_WRITE>;
     else if (mode == SIGN_READ) k = filtered_lrelu_kernel<T, UP, FU, DOWN, FD, TOW, TOH, SIGN_READ>;

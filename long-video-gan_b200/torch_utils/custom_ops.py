@@ -60,6 +60,8 @@ _SIGNATURES = {
     'lvg_conv2d_fprop_workspace': (_c_i64, [_c_int] * 12),
     'lvg_conv2d_dgrad': (_c_int, [_c_void_p] * 3 + [_c_int] * 12 + [_c_void_p, _c_i64, _c_void_p]),
     'lvg_conv2d_wgrad': (_c_int, [_c_void_p] * 3 + [_c_int] * 12 + [_c_void_p]),
+    'lvg_fir1d_depthwise_workspace': (_c_i64, [_c_int]),
+    'lvg_fir1d_depthwise': (_c_int, [_c_void_p] * 3 + [_c_int] * 4 + [_c_void_p, _c_i64, _c_void_p]),
     'lvg_convnd_workspace': (_c_i64, [_c_int] * 14),
     'lvg_convnd_fprop': (_c_int, [_c_void_p] * 3 + [_c_int] * 15 + [_c_void_p, _c_int, _c_float, _c_float, _c_float, _c_void_p, _c_i64, _c_void_p]),
     'lvg_convnd_dgrad': (_c_int, [_c_void_p] * 3 + [_c_int] * 15 + [_c_void_p, _c_i64, _c_void_p]),
@@ -640,6 +642,17 @@ class ConvNdPlugin:
         if rc == LVG_UNSUPPORTED:
             raise RuntimeError('convnd_dgrad: ' + self._lib.lvg_last_error().decode())
         return dx
+
+    def fir1d_depthwise(self, x, w):
+        """y[n][g][t] = sum_k w[g][0][k] * x[n][g][t + k]: F.conv1d(x, w, groups = G) with one channel per group, fp32."""
+        x, w = x.contiguous(), w.contiguous()
+        n, g, lin = x.shape
+        k = w.shape[2]
+        y = torch.empty([n, g, lin - k + 1], dtype=x.dtype, device=x.device)
+        ws = torch.empty([g + 4], dtype=torch.int32, device=x.device)
+        with _DeviceGuard(x):
+            _check(self._lib.lvg_fir1d_depthwise(_ptr(x), _ptr(w), _ptr(y), n, g, lin, k, _ptr(ws), ws.numel() * 4, _stream(x)), 'fir1d_depthwise')
+        return y
 
     def wgrad(self, x, dy, w_shape, padding, groups, stride=1):
         x, dy = x.contiguous(), dy.contiguous()

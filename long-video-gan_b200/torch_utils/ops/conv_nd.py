@@ -133,7 +133,19 @@ def conv_nd(x, w, bias=None, stride=1, padding=0, dilation=1, groups=1):
     return y
 
 
+def _is_long_depthwise_fir(x, w, bias, stride, padding, dilation, groups):
+    """BlurredNoise.blur (generator_lres.py:378-387): conv1d with one channel per group and a long kernel on a noise input --
+    no gradient flows into it (noise input, buffer filters)."""
+    return (enabled_for(x) and x.ndim == 3 and x.dtype == torch.float32 and w.dtype == torch.float32 and bias is None
+            and groups == x.shape[1] == w.shape[0] and w.shape[1] == 1 and w.shape[2] >= 16 and x.shape[2] >= w.shape[2]
+            and _tup(stride, 1) == (1,) and _tup(dilation, 1) == (1,) and isinstance(padding, int) and padding == 0
+            and groups <= 65535 and x.shape[0] <= 65535
+            and not (torch.is_grad_enabled() and (x.requires_grad or w.requires_grad)))
+
+
 def conv1d(input, weight, bias=None, stride=1, padding=0, dilation=1, groups=1):
+    if _is_long_depthwise_fir(input, weight, bias, stride, padding, dilation, groups):
+        return _get_plugin().fir1d_depthwise(input, weight)
     return conv_nd(input, weight, bias, stride, padding, dilation, groups)
 
 

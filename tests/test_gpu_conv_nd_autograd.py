@@ -66,6 +66,8 @@ def test_conv_transpose2d(dtype):
 
 def test_functional_proxy_runs_a_lowres_style_block():
     # a model file's view: F.conv3d -> bias_act -> F.conv3d(1x1x1), then a conv1d stack -- through the proxy
+    torch.backends.cudnn.allow_tf32 = False          # the yardstick (cuDNN) in strict fp32, as train_lres.py:269-270
+    torch.backends.cuda.matmul.allow_tf32 = False
     mod = types.ModuleType('fake_lres_model')
     mod.F = F
     conv_nd.install_functional(mod)
@@ -79,9 +81,33 @@ def test_functional_proxy_runs_a_lowres_style_block():
         return Fm.conv3d(h, w2)
     y = block(mod.F)
     r = block(F)
-    torch.backends.cudnn.allow_tf32 = False
     assert float((y - r).abs().max()) <= 5e-4 * float(r.abs().max())      # two split-precision convolutions in a row
     g = torch.autograd.grad(y.square().sum(), [x, w1, w2, b1])
     gr = torch.autograd.grad(r.square().sum(), [x, w1, w2, b1])
     for a, b in zip(g, gr):
         assert float((a - b).abs().max()) <= 1e-3 * float(b.abs().max())
+
+
+def test_blurred_noise_fir_bank():
+    # generator_lres.py:364-387: 128 right-aligned low-pass filters of very different lengths in a 5000-tap buffer
+    import numpy as np
+    import scipy.signal
+    taps, widths, rows, L = 5000, 128, 6, 640
+    filt = torch.zeros(widths, taps)
+    for i, sr in enumerate(np.exp(np.linspace(np.log(6.0), np.log(2 * taps), widths))):
+        nt = min(taps, max(3, int(np.ceil(sr / 2))))
+        filt[i, -nt:] = torch.as_tensor(scipy.signal.firwin(numtaps=nt, cutoff=1.0, width=2.0, fs=float(sr)), dtype=torch.float32)
+    filt = filt[:, None].to(DEV)
+    noise = rnd((rows, 1, L + taps - 1), 10).float().repeat(1, widths, 1)          # einops.repeat 'n c t -> (n c) b t'
+    y = conv_nd.conv1d(noise, filt, groups=widths)
+    r = F.conv1d(noise.double(), filt.double(), groups=widths)
+    assert y.shape == r.shape == (rows, widths, L)
+    assert float((y.double() - r).abs().max()) <= 2e-5 * float(r.abs().max())
+    # odd sizes, several tiles, a filter with no leading zeros
+    x2, w2 = rnd((3, 5, 2500), 11).float(), rnd((5, 1, 77), 12).float()
+    y2 = conv_nd.conv1d(x2, w2, groups=5)
+    assert float((y2.double() - F.conv1d(x2.double(), w2.double(), groups=5)).abs().max()) <= 1e-5 * float(y2.abs().max())
+    # with gradients requested the call takes the differentiable path (library), same numbers
+    xg = x2.clone().requires_grad_(True)
+    y3 = conv_nd.conv1d(xg, w2, groups=5)
+    assert y3.requires_grad and float((y3 - y2).abs().max()) <= 1e-4 * float(y2.abs().max())
