@@ -50,7 +50,7 @@ struct WgradParams {
     int n, groups, cin, cout;
     int h, w, ho, wo;
     int kh, kw, pad_h, pad_w;
-    int nt;                 // ci per n-tile (multiple of 16, <= 160 for KW = 3, <= 256 for KW = 1)
+    int nt;                 // ci per n-tile (multiple of 16, <= 160 = 32 * kMaxB)
     int x_pair_ok, dy_pair_ok;
 };
 
@@ -328,7 +328,7 @@ extern "C" int lvg_conv2d_wgrad(const void* x, const void* dy, void* dw, int dty
         set_error("conv2d_wgrad: a group's activations exceed 32-bit offsets");
         return LVG_UNSUPPORTED;
     }
-    const int nt_max = kw == 3 ? 160 : 256;
+    const int nt_max = 160;        // kMaxB B items per thread cover rows rsub + 32 s < 160 (a 256-row tile for 1x1 kernels left rows 160.. unstaged)
     const int ntiles = (cin + nt_max - 1) / nt_max;
     p.nt = (((cin + ntiles - 1) / ntiles) + 15) / 16 * 16;
     const int mt = (cout + kBM - 1) / kBM;

@@ -495,7 +495,8 @@ class Conv2dPlugin:
         if tuple(stride) != (1, 1) or tuple(dilation) != (1, 1):
             return False
         kh, kw = w.shape[2], w.shape[3]
-        if (kh, kw) not in ((3, 3), (1, 1)) or min(padding) < 0:
+        # the C side's envelope, all three legs: 3x3 / 1x1, 0 <= pad <= k - 1 (lvg_conv2d_dgrad), at least one sample
+        if (kh, kw) not in ((3, 3), (1, 1)) or min(padding) < 0 or padding[0] > kh - 1 or padding[1] > kw - 1 or x.shape[0] < 1 or x.numel() == 0:
             return False
         if x.shape[1] != w.shape[1] * groups or w.shape[0] % groups != 0:
             return False

@@ -122,7 +122,9 @@ def _use_codes(cfg, x):
 
 def _dense_as(dy, shape, stride):
     """dy with exactly the given (dense) layout: the codes are indexed by memory offset."""
-    if tuple(dy.shape) == tuple(shape) and tuple(dy.stride()) == tuple(stride):
+    # (a view with the right strides but a storage offset that is not 16-byte aligned -- e.g. the narrow of a dim-0 `cat`
+    # backward -- is copied as well: the code-passing kernels use 128-bit accesses only)
+    if tuple(dy.shape) == tuple(shape) and tuple(dy.stride()) == tuple(stride) and dy.data_ptr() % 16 == 0:
         return dy
     out = torch.empty_strided(shape, stride, dtype=dy.dtype, device=dy.device)
     out.copy_(dy)

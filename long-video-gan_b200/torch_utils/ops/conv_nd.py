@@ -179,6 +179,54 @@ def conv_transpose2d(input, weight, bias=None, stride=1, padding=0, output_paddi
     return y
 
 
+class _ConvBiasAct(torch.autograd.Function):
+    """conv -> bias_act in ONE kernel: the convolution's epilogue adds the bias, applies linear / lrelu, gain and clamp while
+    the accumulators leave tensor memory (no write + re-read of the pre-activation tensor). Backward: the activation
+    gradient from the saved output (bias_act semantics, bias_act.py:91-120), then the convolution gradients."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, padding, groups, stride, act, alpha, gain, clamp):
+        y = _get_plugin().fprop(x, w, padding, groups, bias=b, act=2 if act == 'lrelu' else 1, alpha=alpha, gain=gain,
+                                clamp=-1.0 if clamp is None else clamp, stride=stride)
+        ctx.save_for_backward(x, w, y)
+        ctx.cfg = (padding, groups, stride, act, alpha, gain, clamp, b is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        from . import bias_act as ba
+        x, w, y = ctx.saved_tensors
+        padding, groups, stride, act, alpha, gain, clamp, has_b = ctx.cfg
+        # d(pre-activation): the bias_act backward kernel from the saved output (sign of y = sign of the pre-activation)
+        spec = ba.activation_funcs[act]
+        dz = ba._plugin.bias_act(dy.contiguous(), None, None, y, None, 1, 1, spec.cuda_idx, alpha, gain, -1.0 if clamp is None else clamp)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = _ConvNdDgrad.apply(dz, w, x.shape, padding, groups, stride)
+        if ctx.needs_input_grad[1] and not _weights_off():
+            dw = _ConvNdWgrad.apply(dz, x, w.shape, padding, groups, stride)
+        if has_b and ctx.needs_input_grad[2]:
+            db = dz.float().sum([0] + list(range(2, dz.ndim))).to(dz.dtype)
+        return dx, dw, db, None, None, None, None, None, None, None
+
+
+def conv_bias_act(x, w, b=None, stride=1, padding=0, groups=1, act='linear', alpha=None, gain=None, clamp=None):
+    """``bias_act(conv(x, w), b, act=act, alpha=alpha, gain=gain, clamp=clamp)`` for act in ('linear', 'lrelu') -- what
+    Conv3dLayer / Conv2dLayer compute (discriminator_lres.py:135-213, discriminator_sres.py:192-204, generator_lres.py:578-589)
+    -- with the bias / activation / gain / clamp fused into the convolution's epilogue on CUDA. First order only (the
+    separate ops support double backward). Falls back to the two separate ops outside the engine's envelope."""
+    from . import bias_act as ba
+    assert act in ('linear', 'lrelu')
+    spec = ba.activation_funcs[act]
+    alpha = float(alpha if alpha is not None else spec.def_alpha)
+    gain = float(gain if gain is not None else spec.def_gain)
+    ok = _native_ok(x, w, stride, padding, 1, groups)
+    if ok is None or not ba._init():
+        return ba.bias_act(conv_nd(x, w, None, stride, padding, 1, groups), b, act=act, alpha=alpha, gain=gain, clamp=clamp)
+    pd, st = ok
+    return _ConvBiasAct.apply(x, w, b, pd, groups, st, act, alpha, gain, clamp)
+
+
 class _FunctionalProxy:
     """Stands in for the module-level name ``F`` of a reference model file: conv1d / conv2d / conv3d / conv_transpose2d go
     to the tensor-core engine, every other attribute to torch.nn.functional."""

@@ -116,3 +116,14 @@ def test_conv2d_resample_fp16_through_native_conv(name):
     y = conv2d_resample.conv2d_resample(x, w, **kw)
     ref = conv2d_resample.conv2d_resample(x.float().cpu(), w.float().cpu(), **kw)
     assert_close(y, ref, 3e-3, name)
+
+
+@pytest.mark.parametrize('cin', [256, 512])
+def test_round1_wgrad_1x1_wide_input_channels(cin, native_on):
+    # 1x1 kernels with more than 160 input channels per n-tile left B rows 160.. unstaged
+    g, cout, h, w = 1, 64, 12, 20
+    x = (torch.randn(1, g * cin, h, w, device=DEV) / 4).half()
+    dy = torch.randn(1, g * cout, h, w, device=DEV).half()
+    dw = conv2d_gradfix._native.wgrad(x, dy, (g * cout, cin, 1, 1), (0, 0), g)
+    ref = torch.einsum('nohw,nihw->oi', dy.float(), x.float())[:, :, None, None]
+    assert_close(dw, ref, 5e-3, 'dw')

@@ -111,3 +111,22 @@ def test_blurred_noise_fir_bank():
     xg = x2.clone().requires_grad_(True)
     y3 = conv_nd.conv1d(xg, w2, groups=5)
     assert y3.requires_grad and float((y3 - y2).abs().max()) <= 1e-4 * float(y2.abs().max())
+
+
+@pytest.mark.parametrize('dtype', [torch.float16, torch.float32], ids=['f16', 'f32'])
+def test_fused_conv_bias_act_matches_the_two_ops(dtype):
+    torch.backends.cudnn.allow_tf32 = False
+    x = rnd((2, 24, 6, 9, 16), 20).to(dtype).requires_grad_(True)
+    w = rnd((40, 24, 3, 3, 3), 21, 0.05).to(dtype).requires_grad_(True)
+    b = rnd((40,), 22).to(dtype).requires_grad_(True)
+    for act, clamp in (('lrelu', 0.9), ('linear', 256), ('lrelu', None)):
+        y = conv_nd.conv_bias_act(x, w, b, padding=(1, 1, 1), act=act, clamp=clamp)
+        r = bias_act.bias_act(F.conv3d(x.double(), w.double(), padding=1), b.double(), act=act, clamp=clamp, impl='ref')
+        tol = 3e-3 if dtype == torch.float16 else 1e-4
+        assert float((y.double() - r).abs().max()) <= tol * float(r.abs().max())
+        dy = rnd(tuple(y.shape), 23).to(dtype)
+        g = torch.autograd.grad(y, [x, w, b], dy)
+        gr = torch.autograd.grad(r, [x, w, b], dy.double())
+        for name, a, c in zip('xwb', g, gr):
+            # elements whose pre-activation sits within rounding of 0 / the clamp may take the other branch: L2 criterion
+            assert float((a.double() - c).norm() / c.norm()) <= 4 * tol, name

@@ -518,3 +518,19 @@ def test_grad_postprocess_matches_nan_to_num():
         ref = torch.nan_to_num(view * 0.125, nan=0.0, posinf=1e5, neginf=-1e5)
         postprocess_(view, scale=0.125)
         assert torch.equal(view, ref)
+
+
+def test_bias_act_backward_accepts_unaligned_upstream_gradient():
+    # a dy view with the right strides but a 4-byte-aligned storage offset (narrow of a dim-0 cat backward)
+    x = torch.randn(3, 8, 5, 7, device=DEV, requires_grad=True)
+    b = torch.randn(8, device=DEV, requires_grad=True)
+    y = bias_act.bias_act(x, b, act='lrelu', clamp=256)
+    flat = torch.randn(y.numel() + 1, device=DEV)
+    dy = flat[1:].view(y.shape)
+    assert dy.data_ptr() % 16 != 0 and dy.stride() == y.stride()
+    gx, gb = torch.autograd.grad(y, [x, b], dy)
+    xr, br = x.detach().double().requires_grad_(True), b.detach().double().requires_grad_(True)
+    yr = bias_act.bias_act(xr, br, act='lrelu', clamp=256, impl='ref')
+    rx, rb = torch.autograd.grad(yr, [xr, br], dy.double())
+    assert_close(gx, rx, 1e-5, 'dx')
+    assert_close(gb, rb, 1e-4, 'db')
