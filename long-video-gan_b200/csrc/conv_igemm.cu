@@ -42,7 +42,7 @@ using namespace tc;
 constexpr int kBM = 128;
 constexpr int kATile = kBM * 16 * 2;          // one 128 x 16 weight image: 4096 bytes
 constexpr int kThreads = 192;
-constexpr int kMaxStages = 4;
+constexpr int kMaxStages = 6;
 
 struct IgemmParams {
     const unsigned char* wp;     // packed weights [wgroups][mt][kc][taps_all][4096]
@@ -553,7 +553,7 @@ int run_igemm(const void* x, const void* w, void* y, int dtype, int n, int group
     p.stage_bytes = round_up(p.a_stage + p.ks * p.b_step + 512, 128);      // + slack: the last taps read a few pixels past the tile
     const int epi_bytes = 4 * 32 * 33 * 4 + 512;
     p.stages = 2;
-    const int smem_budget = 200 * 1024 - epi_bytes;
+    const int smem_budget = 224 * 1024 - epi_bytes;
     while (p.stages < kMaxStages && (p.stages + 1) * p.stage_bytes <= smem_budget) p.stages++;
     LVG_REQUIRE(p.stages * p.stage_bytes <= smem_budget + 16 * 1024, "convnd: stage does not fit shared memory (%d bytes)", p.stage_bytes);
     p.y_cs = (int64_t)p.to * p.hos * p.wos;
@@ -908,7 +908,7 @@ WgradPlan wgrad_plan(int dtype, int n, int groups, int cin, int cout, int t, int
     q.b_stage = (q.nt / 8) * q.rh * q.ps * 16;
     q.stage_bytes = round_up(nop * (q.a_stage + q.b_stage), 128);
     q.stages = 2;
-    while (q.stages < kMaxStages && (q.stages + 1) * q.stage_bytes <= 190 * 1024) q.stages++;
+    while (q.stages < kMaxStages && (q.stages + 1) * q.stage_bytes <= 220 * 1024) q.stages++;
     const size_t tile_bytes = (size_t)kBM * (32 * kw + 1) * 4;
     q.smem = (size_t)q.stages * q.stage_bytes + 256;
     if (tile_bytes > q.smem) q.smem = tile_bytes;
