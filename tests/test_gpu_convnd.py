@@ -136,3 +136,44 @@ def test_convnd_is_used_for_nan_free_padding(plug):
         y = plug.fprop(x, w, (2, 2), 1)
         dw = plug.wgrad(x, torch.ones_like(y), (19, 17, 3, 3), (2, 2), 1)
         assert torch.isfinite(y).all() and torch.isfinite(dw).all()
+
+
+def _trace_convs():
+    import json
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    tr = json.load(open(os.path.join(root, 'workloads', 'lres_step.json')))
+    seen, out = set(), []
+    for key in ('lres_G', 'lres_D'):
+        for c in tr[key]:
+            if c['op'] in ('conv3d', 'conv1d') and c['groups'] == 1:
+                sig = (tuple(c['x']), tuple(c['w']), str(c['padding']))
+                if sig not in seen:
+                    seen.add(sig)
+                    out.append(c)
+    return out
+
+
+@pytest.mark.parametrize('c', _trace_convs(), ids=lambda c: f"{c['op']}-{'x'.join(map(str, c['x'][1:]))}-w{'x'.join(map(str, c['w']))}")
+def test_every_lowres_convolution_signature(plug, c):
+    # every F.conv3d / F.conv1d call of one G + D pass of the low-res networks (workloads/lres_step.json, recorded from the
+    # reference modules), fp32, at batch 1 with the time axis cut to <= 24 frames: forward, input and weight gradient
+    xs, ws = list(c['x']), list(c['w'])
+    pad = c['padding'] if isinstance(c['padding'], (list, tuple)) else [c['padding']] * (len(xs) - 2)
+    if len(xs) == 5 and xs[2] > 24:
+        xs[2] = 24
+    x = rnd(xs, 31).float()
+    w = rnd(ws, 32, 1.0 / math.sqrt(math.prod(ws[1:]))).float()
+    xr, wr = x.double().requires_grad_(True), w.double().requires_grad_(True)
+    yr = conv_ref(xr, wr, tuple(pad), 1)
+    y = plug.fprop(x, w, tuple(pad), 1)
+    # split-precision products are exact to ~2^-16; the tensor core's fp32 accumulation adds an error that grows with the
+    # length of the sum (measured 6e-6 at K = 576 ... 7e-5 at K = 13824 products per output) -- still 15x inside 1e-3
+    tol = 5e-5 if math.prod(ws[1:]) < 4096 else 2e-4
+    assert float((y.double() - yr).abs().max()) <= tol * float(yr.detach().abs().max()), 'fprop'
+    dy = rnd(tuple(yr.shape), 33).float()
+    gx, gw = torch.autograd.grad(yr, [xr, wr], dy.double())
+    dx = plug.dgrad(dy, w, tuple(xs), tuple(pad), 1)
+    assert float((dx.double() - gx).abs().max()) <= tol * float(gx.abs().max()), 'dgrad'
+    dw = plug.wgrad(x, dy, tuple(ws), tuple(pad), 1)
+    assert float((dw.double() - gw).abs().max()) <= tol * float(gw.abs().max()), f'wgrad {float((dw.double() - gw).abs().max() / gw.abs().max()):.3e}'
