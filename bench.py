@@ -62,6 +62,11 @@ def make_filter(shape, gen):
     """Low-pass-like synthetic taps of the recorded shape (values do not affect timing)."""
     if shape is None:
         return None
+    if len(shape) == 2 and min(shape) > 1:
+        # the networks' 2-D filters are outer products of 1-D taps (setup_filter([1, 3, 3, 1]), upfirdn2d.py:103-108)
+        fy, fx = torch.rand(shape[0], generator=gen) + 0.1, torch.rand(shape[1], generator=gen) + 0.1
+        f = torch.outer(fy, fx)
+        return (f / f.sum()).float()
     f = torch.rand(*shape, generator=gen) + 0.1
     return (f / f.sum()).float()
 
