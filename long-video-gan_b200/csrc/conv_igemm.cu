@@ -29,6 +29,7 @@
 // (TMEM -> registers -> [bias, lrelu, gain, clamp] -> NC(T)HW global). Stages hand over through full/empty mbarriers.
 
 #include <cuda.h>
+#include <stdlib.h>
 #include <cuda_bf16.h>
 
 #include "common.cuh"
@@ -511,8 +512,10 @@ int run_igemm(const void* x, const void* w, void* y, int dtype, int n, int group
     p.kt = kt; p.kh = kh; p.kw = kw; p.pad_t = pad_t; p.pad_h = pad_h; p.pad_w = pad_w;
     // tile: whole rows (and, for small frames, several frames) up to 512 accumulator columns; wide images are cut into
     // column tiles. A tile of <= 256 columns leaves room for two accumulator buffers (epilogue overlap).
-    // (short K loops are epilogue-bound: they take <= 256 columns and alternate two accumulator buffers)
-    const int col_budget = (g.kc * kt <= 12) ? 256 : 512;
+    // (short K loops -- up to ~160 MMAs per tile -- are epilogue-bound: they take <= 256 columns and alternate two accumulator
+    // buffers; measured on the sres discriminator shapes: 0.173 vs 0.200 ms at 256 -> 256 channels 64x64)
+    const char* cb_env = getenv("LVG_CONV_COLS");
+    const int col_budget = cb_env ? atoi(cb_env) : ((g.kc * kt * kh * kw <= 160) ? 256 : 512);
     const int max_wt = 128 - (kw - 1);                        // a TMA box row is at most 256 8-byte elements
     p.tiles_x = (p.wo + max_wt - 1) / max_wt;
     p.wt = (p.wo + p.tiles_x - 1) / p.tiles_x;
