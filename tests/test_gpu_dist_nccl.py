@@ -39,12 +39,20 @@ def _worker(rank, world, port, ret):
             elif mode == 'overlap':
                 sync = FlatGradSync(net, overlap=True, buckets=3, backwards_per_sync=2)
             gen = torch.Generator().manual_seed(100 + rank)
+            poison = {'on': False}
+            first = next(net.parameters())
+
+            def spoil(g):          # a NaN born INSIDE backward on rank 0 (before the bucket leaves): must come out as 0 everywhere
+                if poison['on']:
+                    g = g.clone()
+                    g.view(-1)[0] = float('nan') if rank == 0 else 1.0
+                return g
+            first.register_hook(spoil)
             for it in range(3):
                 xa, xb = torch.randn(4, 3, 16, 16, generator=gen).to(dev), torch.randn(4, 3, 16, 16, generator=gen).to(dev)
+                poison['on'] = it == 1
                 net(xa).square().mean().backward()          # two backward passes per update, as update_D does
                 net(xb).tanh().mean().backward()
-                if it == 1:
-                    next(net.parameters()).grad.view(-1)[0] = float('nan') if rank == 0 else 1.0      # NaN -> 0 after the exchange
                 if mode == 'reference':                      # utils.py:116-124 restated on NCCL
                     ps = [p for p in net.parameters() if p.grad is not None]
                     flat = torch.cat([p.grad.flatten() for p in ps])
