@@ -55,7 +55,8 @@ struct IgemmParams {
     int bf16;                    // operands are bf16 (split fp32) instead of fp16
     int wgroups, cout, mt, kc;   // kc = 16-channel steps of the packed K axis
     int nblk;                    // channel blocks per instance in X8
-    int kb_wrap;                 // split mode: source block of packed block kb is kb < kb_wrap ? kb : kb - kb_wrap
+    int nimg;                    // operand images per k-step: 1 (fp16) or 2 (split: hi and lo halves of both operands)
+    int lo_blk;                  // split: block offset of the lo halves inside an instance of X8
     int to, ho, wo;              // output extent
     int kt, kh, kw, pad_t, pad_h, pad_w;
     int tt, th, wt, wtb, thb;    // tile frames / rows / cols, box cols / rows
@@ -67,7 +68,7 @@ struct IgemmParams {
     int64_t total_tiles;         // tiles_x * tiles_y * tiles_t * mt * instances
     int ks;                      // k-steps per stage (> 1 only when kt == 1)
     int stages;
-    int a_stage, b_step, b_bytes, stage_bytes;    // bytes: A per stage, B stride / payload per k-step, whole stage
+    int a_stage, b_step, b_bytes, b_box, stage_bytes;    // bytes: A per stage, B stride per k-step / per pair of blocks, TMA payload of a pair, whole stage
     int64_t y_cs;                // output channel stride (= to*hos*wos)
     int ostride, hos, wos;       // output decimation (strided convolution): only rows / columns divisible by ostride are stored
 };
@@ -144,8 +145,8 @@ int pack_act(const void* x, void* x8, int split, int64_t inst, int c, int cblk, 
 //   w[g * gstride + m * sm + k * sk + (flip ? taps-1-tap : tap)]
 // fprop: m = co, k = ci (sm = cin*taps, sk = taps); dgrad: m = ci, k = co (sm = taps, sk = cin*taps), taps mirrored.
 // Image of one 128 x 16 tile (K-major, no swizzle): byte offset(m, k) = (k/8)*2048 + (m/8)*128 + (m%8)*16 + (k%8)*2.
-// SPLIT: the packed K axis is three segments of kpad channels [hi | hi | lo], matching the activation blocks
-// [hi | lo | hi] visited by the main loop: hi*hi + lo*hi + hi*lo.
+// SPLIT: every (k-step, tap) gets TWO images, the bf16 hi and lo halves of the fp32 weights; the main loop pairs them with
+// the hi / lo activation blocks: hi*hi + hi*lo + lo*hi (each operand half is fetched once per k-step).
 // One CTA = one (group, m-tile, k-step). The 128 x 16 x taps source elements form contiguous RUNS in memory (fprop: one
 // run of 16*taps elements per output channel; dgrad: one run of 128*taps elements per k): a warp copies a run into shared
 // memory with aligned 4-byte loads (no per-element index arithmetic), then every thread assembles one 16-byte image row
@@ -161,9 +162,9 @@ __global__ void __launch_bounds__(256) conv_pack_w_kernel(const TIn* __restrict_
     const int kci = blockIdx.x % kc;
     const int mti = (blockIdx.x / kc) % mt;
     const int g = blockIdx.x / (kc * mt);
-    const int kp0 = kci * 16;                        // packed k of the chunk
-    const int seg = SPLIT ? kp0 / kpad : 0;
-    const int k0 = SPLIT ? kp0 - seg * kpad : kp0;
+    const int k0 = kci * 16;
+    (void)kpad;
+    constexpr int NIMG = SPLIT ? 2 : 1;
     const TIn* wg = w + (int64_t)g * gstride;
     const bool mrows = sk < sm;                      // fprop layout: runs along (k, tap) per m; else runs along (m, tap) per k
     const int R = rows_per_pass;
@@ -171,7 +172,7 @@ __global__ void __launch_bounds__(256) conv_pack_w_kernel(const TIn* __restrict_
     const int pitch = ((run_el * ES + 2 + 3) / 4) | 1;
     const int max_runs = mrows ? R : 16;
     int* s_off = reinterpret_cast<int*>(sw32 + (size_t)max_runs * pitch);
-    unsigned char* dst0 = wp + ((((int64_t)g * mt + mti) * kc + kci) * taps) * kATile;
+    unsigned char* dst0 = wp + ((((int64_t)g * mt + mti) * kc + kci) * taps) * (int64_t)(NIMG * kATile);
     const int kvalid = max(0, min(16, k_total - k0));
     for (int r0 = 0; r0 < kBM; r0 += R) {
         const int Rn = min(R, kBM - r0);
@@ -202,7 +203,7 @@ __global__ void __launch_bounds__(256) conv_pack_w_kernel(const TIn* __restrict_
             if (pow2) { mrow = o & (kBM - 1); k8 = (o >> 7) & 1; tap = o >> 8; }
             else { mrow = o % Rn; k8 = (o / Rn) % 2; tap = o / (2 * Rn); }
             const int wtap = flip ? taps - 1 - tap : tap;
-            alignas(16) unsigned short v[8];
+            alignas(16) unsigned short v[8], vlo[8];
 #pragma unroll
             for (int j = 0; j < 8; j++) {
                 const int k = k8 * 8 + j;
@@ -217,12 +218,15 @@ __global__ void __launch_bounds__(256) conv_pack_w_kernel(const TIn* __restrict_
                 if constexpr (SPLIT) {
                     if constexpr (ES == 2) f = __half2float(__ushort_as_half(hbits));
                     const unsigned short h = bf16_bits(f);
-                    v[j] = seg == 2 ? bf16_bits(f - bf16_val(h)) : h;
+                    v[j] = h;
+                    vlo[j] = bf16_bits(f - bf16_val(h));
                 } else {
                     v[j] = ES == 2 ? hbits : __half_as_ushort(__float2half_rn(f));
                 }
             }
-            *reinterpret_cast<uint4*>(dst0 + (size_t)tap * kATile + k8 * 2048 + (r0 + mrow) * 16) = *reinterpret_cast<const uint4*>(v);
+            unsigned char* dimg = dst0 + (size_t)tap * (NIMG * kATile) + k8 * 2048 + (r0 + mrow) * 16;
+            *reinterpret_cast<uint4*>(dimg) = *reinterpret_cast<const uint4*>(v);
+            if constexpr (SPLIT) *reinterpret_cast<uint4*>(dimg + kATile) = *reinterpret_cast<const uint4*>(vlo);
         }
         __syncthreads();
     }
@@ -293,7 +297,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
             int it = 0;
             for (int64_t L = blockIdx.x; L < p.total_tiles; L += gridDim.x) {
                 const TileCoord c = decode_tile(p, L);
-                const unsigned char* wpg = p.wp + (((int64_t)(c.inst % p.wgroups) * p.mt + c.mti) * p.kc) * (int64_t)(p.kt * taps2) * kATile;
+                const unsigned char* wpg = p.wp + (((int64_t)(c.inst % p.wgroups) * p.mt + c.mti) * p.kc) * (int64_t)(p.kt * taps2) * (p.nimg * kATile);
                 const int blk0 = c.inst * p.nblk;
                 for (int kt = 0; kt < p.kt; kt++) {
                     for (int kcix = 0; kcix < kchunks; kcix++, it++) {
@@ -302,15 +306,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
                         unsigned char* st = smem + (size_t)s * p.stage_bytes;
                         const int k0 = kcix * p.ks;
                         const int nks = min(p.ks, p.kc - k0);
-                        const uint32_t a_bytes = (uint32_t)(nks * taps2 * kATile);
-                        mbar_expect_tx(&full_bar[s], a_bytes + (uint32_t)(nks * p.b_bytes));
+                        const uint32_t a_bytes = (uint32_t)(nks * taps2 * p.nimg * kATile);
+                        mbar_expect_tx(&full_bar[s], a_bytes + (uint32_t)(nks * p.nimg * p.b_box));
                         // A: kt == 1 -> the nks steps' tiles are contiguous; kt > 1 -> ks == 1, the taps of this kt are contiguous
-                        bulk_copy_g2s(st, wpg + ((int64_t)k0 * p.kt + kt) * (int64_t)taps2 * kATile, a_bytes, &full_bar[s]);
+                        bulk_copy_g2s(st, wpg + ((int64_t)k0 * p.kt + kt) * (int64_t)taps2 * (p.nimg * kATile), a_bytes, &full_bar[s]);
                         for (int j = 0; j < nks; j++) {
                             const int kb = (k0 + j) * 2;
-                            const int sb = kb < p.kb_wrap ? kb : kb - p.kb_wrap;
-                            tma_load_4d(st + p.a_stage + (size_t)j * p.b_step, &tmx, 2 * (c.ox0 - p.pad_w), c.oy0 - p.pad_h, c.t0 + kt - p.pad_t,
-                                        blk0 + sb, &full_bar[s]);
+                            for (int im = 0; im < p.nimg; im++)
+                                tma_load_4d(st + p.a_stage + (size_t)j * p.b_step + (size_t)im * p.b_bytes, &tmx, 2 * (c.ox0 - p.pad_w), c.oy0 - p.pad_h,
+                                            c.t0 + kt - p.pad_t, blk0 + im * p.lo_blk + kb, &full_bar[s]);
                         }
                     }
                 }
@@ -322,7 +326,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
             const uint32_t ibase = (1u << 4) | (p.bf16 ? ((1u << 7) | (1u << 10)) : 0u) | ((uint32_t)(kBM >> 4) << 24);
             const int na = p.n0 > 0 ? p.n0 : p.ncols, nb = p.n0 > 0 ? p.ncols - p.n0 : 0;
             const uint32_t idesc_a = ibase | ((uint32_t)(na >> 3) << 17), idesc_b = ibase | ((uint32_t)(nb >> 3) << 17);
-            const uint32_t blk_bytes = (uint32_t)p.b_bytes / 2;
+            const uint32_t blk_bytes = (uint32_t)p.b_box / 2;
             int it = 0, i = 0;
             for (int64_t L = blockIdx.x; L < p.total_tiles; L += gridDim.x, i++) {
                 const int buf = i % p.nbuf;
@@ -338,15 +342,20 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
                         const uint32_t st = smem_u32(smem + (size_t)s * p.stage_bytes);
                         const int nks = min(p.ks, p.kc - kcix * p.ks);
                         for (int j = 0; j < nks; j++) {
-                            const uint32_t a0 = st + (uint32_t)(j * taps2) * kATile;
+                            const uint32_t a0 = st + (uint32_t)(j * taps2 * p.nimg) * kATile;
                             const uint32_t b0 = st + (uint32_t)p.a_stage + (uint32_t)j * (uint32_t)p.b_step;
                             for (int ky = 0; ky < p.kh; ky++) {
                                 for (int kx = 0; kx < p.kw; kx++) {
-                                    const uint64_t adesc = make_desc(a0 + (uint32_t)(ky * p.kw + kx) * kATile, 2048, 128);
+                                    const uint32_t at = a0 + (uint32_t)((ky * p.kw + kx) * p.nimg) * kATile;
                                     const uint32_t bs = b0 + (uint32_t)(ky * p.wtb + kx) * 16;
-                                    umma_f16(tmem_d, adesc, make_desc(bs, blk_bytes, 128), idesc_a, first ? 0u : 1u);
-                                    if (nb > 0) umma_f16(tmem_d + (uint32_t)na, adesc, make_desc(bs + (uint32_t)na * 16, blk_bytes, 128), idesc_b, first ? 0u : 1u);
-                                    first = false;
+                                    // fp16: one product; split: hi*hi, hi*lo, lo*hi (term t: A image t / 2, B image t % 2)
+                                    for (int term = 0; term < (p.nimg == 2 ? 3 : 1); term++) {
+                                        const uint64_t adesc = make_desc(at + (term == 2 ? (uint32_t)kATile : 0u), 2048, 128);
+                                        const uint32_t bt = bs + (term == 1 ? (uint32_t)p.b_bytes : 0u);
+                                        umma_f16(tmem_d, adesc, make_desc(bt, blk_bytes, 128), idesc_a, first ? 0u : 1u);
+                                        if (nb > 0) umma_f16(tmem_d + (uint32_t)na, adesc, make_desc(bt + (uint32_t)na * 16, blk_bytes, 128), idesc_b, first ? 0u : 1u);
+                                        first = false;
+                                    }
                                 }
                             }
                         }
@@ -460,7 +469,7 @@ int encode_map(CUtensorMap* tm, void* base, int w, int h, int t, int64_t blocks,
 inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
 
 struct Geometry {
-    int cpad, cblk, nblk, kpacked, kc, mt;
+    int cpad, cblk, nblk, nimg, kc, mt;
     int64_t act_bytes, w_bytes;
 };
 
@@ -471,11 +480,11 @@ Geometry geometry(int split, int64_t inst, int groups, int ck, int cm, int64_t t
     g.cpad = round_up(ck, 16);
     g.cblk = g.cpad / 8;
     g.nblk = split ? 2 * g.cblk : g.cblk;
-    g.kpacked = split ? 3 * g.cpad : g.cpad;
-    g.kc = g.kpacked / 16;
+    g.nimg = split ? 2 : 1;
+    g.kc = g.cpad / 16;
     g.mt = (cm + kBM - 1) / kBM;
     g.act_bytes = inst * g.nblk * thw * 16;
-    g.w_bytes = (int64_t)groups * g.mt * g.kc * taps * kATile;
+    g.w_bytes = (int64_t)groups * g.mt * g.kc * taps * g.nimg * kATile;
     return g;
 }
 
@@ -506,7 +515,7 @@ int run_igemm(const void* x, const void* w, void* y, int dtype, int n, int group
     p.wp = wp; p.y = y; p.bias = bias; p.act = act; p.alpha = alpha; p.gain = gain; p.clamp = clamp;
     p.out_f32 = split; p.bf16 = split;
     p.wgroups = groups; p.cout = cm; p.mt = g.mt; p.kc = g.kc; p.nblk = g.nblk;
-    p.kb_wrap = split ? 2 * g.cblk : (1 << 30);
+    p.nimg = g.nimg; p.lo_blk = g.cblk;
     p.to = t + 2 * pad_t - kt + 1; p.ho = h + 2 * pad_h - kh + 1; p.wo = wd + 2 * pad_w - kw + 1;
     LVG_REQUIRE(p.to >= 1 && p.ho >= 1 && p.wo >= 1, "convnd: empty output");
     p.kt = kt; p.kh = kh; p.kw = kw; p.pad_t = pad_t; p.pad_h = pad_h; p.pad_w = pad_w;
@@ -515,50 +524,54 @@ int run_igemm(const void* x, const void* w, void* y, int dtype, int n, int group
     // (short K loops -- up to ~160 MMAs per tile -- are epilogue-bound: they take <= 256 columns and alternate two accumulator
     // buffers; measured on the sres discriminator shapes: 0.173 vs 0.200 ms at 256 -> 256 channels 64x64)
     const char* cb_env = getenv("LVG_CONV_COLS");
-    const int col_budget = cb_env ? atoi(cb_env) : ((g.kc * kt * kh * kw <= 160) ? 256 : 512);
-    const int max_wt = 128 - (kw - 1);                        // a TMA box row is at most 256 8-byte elements
-    p.tiles_x = (p.wo + max_wt - 1) / max_wt;
-    p.wt = (p.wo + p.tiles_x - 1) / p.tiles_x;
-    p.wtb = p.wt + kw - 1;
-    p.th = col_budget / p.wtb;
-    if (p.th > p.ho) p.th = p.ho;
-    if (p.th < 1) p.th = 1;
-    p.tiles_y = (p.ho + p.th - 1) / p.th;
-    p.th = (p.ho + p.tiles_y - 1) / p.tiles_y;               // balance the row tiles
+    const int taps2 = kh * kw;
+    const int epi_bytes = 4 * 32 * 33 * 4 + 512;
+    const int smem_budget = 224 * 1024 - epi_bytes;
     p.ostride = ostride;
     p.hos = (p.ho - 1) / ostride + 1; p.wos = (p.wo - 1) / ostride + 1;
-    if (ostride > 1) {                                         // tile origins on the output lattice
-        if (p.tiles_x > 1) { p.wt = round_up(p.wt, ostride); p.wtb = p.wt + kw - 1; p.tiles_x = (p.wo + p.wt - 1) / p.wt; if (p.th * p.wtb > col_budget) p.th = col_budget / p.wtb; }
-        if (p.th < p.ho) { p.th = p.th / ostride * ostride; if (p.th < ostride) p.th = ostride; }
+    p.ks = (kt == 1) ? (taps2 == 1 ? 4 : (taps2 <= 3 ? 2 : 1)) : 1;
+    if (p.ks > g.kc) p.ks = g.kc;
+    p.a_stage = p.ks * taps2 * g.nimg * kATile;
+    // the column budget shrinks until two stages fit shared memory (split precision doubles both operands of a stage)
+    for (int col_budget = cb_env ? atoi(cb_env) : ((g.kc * kt * taps2 <= 160) ? 256 : 512);; col_budget -= 64) {
+        LVG_REQUIRE(col_budget >= 64, "convnd: no tile fits shared memory");
+        const int max_wt = 128 - (kw - 1);                    // a TMA box row is at most 256 8-byte elements
+        p.tiles_x = (p.wo + max_wt - 1) / max_wt;
+        p.wt = (p.wo + p.tiles_x - 1) / p.tiles_x;
+        p.wtb = p.wt + kw - 1;
+        p.th = col_budget / p.wtb;
+        if (p.th > p.ho) p.th = p.ho;
+        if (p.th < 1) p.th = 1;
         p.tiles_y = (p.ho + p.th - 1) / p.th;
-        LVG_REQUIRE(p.th * p.wtb <= 512, "convnd: strided tile does not fit");
+        p.th = (p.ho + p.tiles_y - 1) / p.tiles_y;           // balance the row tiles
+        if (ostride > 1) {                                     // tile origins on the output lattice
+            if (p.tiles_x > 1) { p.wt = round_up(p.wt, ostride); p.wtb = p.wt + kw - 1; p.tiles_x = (p.wo + p.wt - 1) / p.wt; if (p.th * p.wtb > col_budget) p.th = col_budget / p.wtb; }
+            if (p.th < p.ho) { p.th = p.th / ostride * ostride; if (p.th < ostride) p.th = ostride; }
+            p.tiles_y = (p.ho + p.th - 1) / p.th;
+        }
+        p.thb = p.th + kh - 1;
+        p.frame_px = p.thb * p.wtb;
+        p.tt = 1;
+        if (p.tiles_y == 1 && p.tiles_x == 1) {                // whole frames: take as many as fit
+            while (p.tt < p.to && p.tt * p.frame_px + p.th * p.wtb <= col_budget && p.tt < 64) p.tt++;
+        }
+        p.tiles_t = (p.to + p.tt - 1) / p.tt;
+        p.tt = (p.to + p.tiles_t - 1) / p.tiles_t;
+        p.ncols = round_up((p.tt - 1) * p.frame_px + p.th * p.wtb, 16);
+        // TMA writes the two 8-channel blocks of a k-step densely: block 1 starts tt*thb*wtb*16 bytes after block 0 (= LBO);
+        // every pair of blocks starts at a 128-byte multiple (TMA destination alignment)
+        p.b_box = 2 * p.tt * p.frame_px * 16;                  // one pair of blocks as TMA writes it
+        p.b_bytes = round_up(p.b_box, 128);
+        p.b_step = g.nimg * p.b_bytes;
+        p.stage_bytes = round_up(p.a_stage + p.ks * p.b_step + 512, 128);      // + slack: the last taps read a few pixels past the tile
+        if (p.ncols <= 512 && 2 * p.stage_bytes <= smem_budget) break;
+        if (p.th == 1 && p.tt == 1 && col_budget <= p.wtb) { LVG_REQUIRE(false, "convnd: a one-row tile does not fit shared memory"); }
     }
-    p.thb = p.th + kh - 1;
-    p.frame_px = p.thb * p.wtb;
-    p.tt = 1;
-    if (p.tiles_y == 1 && p.tiles_x == 1) {                    // whole frames: take as many as fit
-        while (p.tt < p.to && p.tt * p.frame_px + p.th * p.wtb <= col_budget && p.tt < 64) p.tt++;
-    }
-    p.tiles_t = (p.to + p.tt - 1) / p.tt;
-    p.tt = (p.to + p.tiles_t - 1) / p.tiles_t;
-    p.ncols = round_up((p.tt - 1) * p.frame_px + p.th * p.wtb, 16);
     LVG_REQUIRE(p.th >= 1 && p.ncols <= 512 && p.ncols >= 16, "convnd: tile geometry");
     p.nbuf = p.ncols <= 256 ? 2 : 1;
     p.n0 = p.ncols <= 256 ? 0 : round_up(p.ncols / 2, 16);
-    // TMA writes the two 8-channel blocks of a k-step densely: block 1 starts tt*thb*wtb*16 bytes after block 0 (= LBO);
-    // the k-steps of a stage start at 128-byte multiples (TMA destination alignment)
-    p.b_bytes = 2 * p.tt * p.frame_px * 16;
-    p.b_step = round_up(p.b_bytes, 128);
-    const int taps2 = kh * kw;
-    p.ks = (kt == 1) ? (taps2 == 1 ? 4 : (taps2 <= 3 ? 2 : 1)) : 1;
-    if (p.ks > g.kc) p.ks = g.kc;
-    p.a_stage = p.ks * taps2 * kATile;
-    p.stage_bytes = round_up(p.a_stage + p.ks * p.b_step + 512, 128);      // + slack: the last taps read a few pixels past the tile
-    const int epi_bytes = 4 * 32 * 33 * 4 + 512;
     p.stages = 2;
-    const int smem_budget = 224 * 1024 - epi_bytes;
     while (p.stages < kMaxStages && (p.stages + 1) * p.stage_bytes <= smem_budget) p.stages++;
-    LVG_REQUIRE(p.stages * p.stage_bytes <= smem_budget + 16 * 1024, "convnd: stage does not fit shared memory (%d bytes)", p.stage_bytes);
     p.y_cs = (int64_t)p.to * p.hos * p.wos;
     p.total_tiles = (int64_t)p.tiles_x * p.tiles_y * p.tiles_t * g.mt * inst;
 

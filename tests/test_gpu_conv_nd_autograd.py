@@ -121,12 +121,16 @@ def test_fused_conv_bias_act_matches_the_two_ops(dtype):
     b = rnd((40,), 22).to(dtype).requires_grad_(True)
     for act, clamp in (('lrelu', 0.875), ('linear', 256), ('lrelu', None)):          # clamps that fp16 represents exactly
         y = conv_nd.conv_bias_act(x, w, b, padding=(1, 1, 1), act=act, clamp=clamp)
+        y2 = bias_act.bias_act(conv_nd.conv3d(x, w, padding=(1, 1, 1)), b, act=act, clamp=clamp)        # the two separate ops
         r = bias_act.bias_act(F.conv3d(x.double(), w.double(), padding=1), b.double(), act=act, clamp=clamp, impl='ref')
         tol = 3e-3 if dtype == torch.float16 else 1e-4
         assert float((y.double() - r).abs().max()) <= tol * float(r.abs().max())
         dy = rnd(tuple(y.shape), 23).to(dtype)
         g = torch.autograd.grad(y, [x, w, b], dy)
+        g2 = torch.autograd.grad(y2, [x, w, b], dy)
         gr = torch.autograd.grad(r, [x, w, b], dy.double())
-        for name, a, c in zip('xwb', g, gr):
-            # elements whose pre-activation sits within rounding of 0 / the clamp may take the other branch: L2 criterion
-            assert float((a.double() - c).norm() / c.norm()) <= 4 * tol, name
+        for name, a, a2, c in zip('xwb', g, g2, gr):
+            # fp16 storage decides "clamped?" / "negative?" on the rounded output, so a clamp-active fp16 case sits ~2 % (L2) from
+            # the float64 graph for the separate ops as well; the fused op (one rounding less) must be at least as close
+            e, e2 = float((a.double() - c.double()).norm() / c.double().norm()), float((a2.double() - c.double()).norm() / c.double().norm())
+            assert e <= max(4 * tol, 1.1 * e2), f'{name}: fused {e:.3e}, separate ops {e2:.3e}'
