@@ -342,6 +342,27 @@ def cpu_sample_reference(workload, budget_s=20.0):
             return float(c['x'][0] * c['w'][0] * out) * float(np.prod(c['w'][1:]))
         return float(np.prod(c['x']))
 
+    def bounded(c):
+        """(call to run, factor): calls that would take many seconds on the host are cut along the time / plane axis (their cost
+        is linear in it) and the measured time is scaled back by `factor` -- keeps every single sample, and so the arm, bounded."""
+        cap = 4e9 if c['op'] in CONV_OPS else 2.5e7
+        wgt = weight(c)
+        if wgt <= cap:
+            return c, 1.0
+        xs = list(c['x'])
+        axis = 2 if (c['op'] in CONV_OPS and len(xs) == 5) else max(range(min(3, len(xs))), key=lambda i: xs[i])
+        lo = 4 * (c['w'][2] if c['op'] in CONV_OPS and len(xs) == 5 else 1)
+        new = max(lo, min(xs[axis], int(xs[axis] * cap / wgt)))
+        if c['op'] == 'bias_act' and axis == c.get('dim', 1):
+            return c, 1.0                              # (the bias axis keeps its length)
+        if new >= xs[axis]:
+            return c, 1.0
+        c2 = dict(c)
+        xs2 = list(xs)
+        xs2[axis] = new
+        c2['x'] = xs2
+        return c2, xs[axis] / float(new)
+
     for k in groups:
         groups[k].sort(key=lambda c: -weight(c))
     stat = {k: dict(tf=0.0, tb=0.0, done=0, total=sum(weight(c) for c in v)) for k, v in groups.items()}
@@ -358,9 +379,10 @@ def cpu_sample_reference(workload, budget_s=20.0):
             rp._fwd(rp.items[0], rp.items[0]['x'])
     n_done = 0
     t_start = time.perf_counter()
-    for key, c in order:
+    for key, c_full in order:
         if time.perf_counter() - t_start > budget_s:
             break
+        c, factor = bounded(c_full)
         rp = Replay([c], 1, torch.device('cpu'), 'fp32', ops=ops)     # fp32 on CPU, as the reference's CPU path runs
         it = rp.items[0]
         x = it['x'].detach().requires_grad_(True)
@@ -378,13 +400,14 @@ def cpu_sample_reference(workload, budget_s=20.0):
             torch.autograd.grad(y, leaves, it['dy'], allow_unused=True)
         t2 = time.perf_counter()
         st = stat[key]
-        st['tf'] += t1 - t0
-        st['tb'] += t2 - t1
-        st['done'] += weight(c)
+        st['tf'] += (t1 - t0) * factor
+        st['tb'] += (t2 - t1) * factor
+        st['done'] += weight(c_full)
         n_done += 1
     for key, v in groups.items():          # a group the budget did not reach: its median call, so that every group has a rate
         if stat[key]['done'] == 0:
-            c = v[len(v) // 2]
+            c_full = v[len(v) // 2]
+            c, factor = bounded(c_full)
             rp = Replay([c], 1, torch.device('cpu'), 'fp32', ops=ops)
             it = rp.items[0]
             x = it['x'].detach().requires_grad_(True)
@@ -397,9 +420,9 @@ def cpu_sample_reference(workload, budget_s=20.0):
             t1 = time.perf_counter()
             if y.requires_grad:
                 torch.autograd.grad(y, leaves, it['dy'], allow_unused=True)
-            stat[key]['tf'] += t1 - t0
-            stat[key]['tb'] += time.perf_counter() - t1
-            stat[key]['done'] += weight(c)
+            stat[key]['tf'] += (t1 - t0) * factor
+            stat[key]['tb'] += (time.perf_counter() - t1) * factor
+            stat[key]['done'] += weight(c_full)
             n_done += 1
     est = 0.0
     for (net, _), st in stat.items():
@@ -411,7 +434,7 @@ def cpu_sample_reference(workload, budget_s=20.0):
     used = time.perf_counter() - t_start
     desc = (f"reference's own _ref ops (oracle/_ref/src, torch {torch.__version__} CPU, {threads} threads): forward+backward of {n_done} of "
             f"{len(order)} hot-path op calls of one G+D pass at batch 1 (of {batch}), {used:.1f} s, covering "
-            f"{100.0 * sum(done_bytes.values()) / max(1, sum(all_bytes.values())):.0f} % of the pass's work (rest extrapolated per (network, op) group: by elements, by multiply-adds for convolutions); "
+            f"{100.0 * sum(done_bytes.values()) / max(1, sum(all_bytes.values())):.0f} % of the pass's work (rest extrapolated per (network, op) group: by elements, by multiply-adds for convolutions; calls above 4e9 multiply-adds / 2.5e7 elements are cut along the time axis and scaled back); "
             f"step = G 2 fwd + 1 bwd, D 3 fwd + 3 bwd")
     return fps, desc, threads, 'reference'
 
