@@ -360,14 +360,16 @@ Cfg pick(int fu_w, int fu_h, int fd_w, int fd_h, int up, int down)
 // Output tile height. 64x24 tiles fit three CTAs per SM (66 KB, <= 85 registers) and measured 12-18 % faster than
 // 64x32 (two CTAs) on the up2/down2 layers; the up4 configuration has a larger halo and is faster with 64x32.
 // An image that a single 32-row tile covers keeps the tall tile. LVG_FL_TOH=24|32 overrides (experiments).
-bool tall_tiles(int up, int oh)
+int tile_rows(int up, int oh)
 {
     static int forced = -1;
     if (forced < 0) { const char* e = getenv("LVG_FL_TOH"); forced = e ? atoi(e) : 0; }
-    if (forced == 24) return false;
-    if (forced == 32) return true;
-    if (up == 4) return true;
-    return oh > 24 && oh <= 32;
+    if (forced == 24 || forced == 32) return forced;
+    (void)up;
+    // fewest padded rows wins, ties go to the 24-row tile (3 CTAs per SM). Measured on B200 (fp16, NT = 64): L10 (up 4, 92 rows)
+    // 8.65 ms with 24 vs 9.74 with 32; L3 (38 rows) 0.85 vs 1.06; L5 (56 rows) 2.45 vs 2.30; 16-row tiles lose everywhere.
+    const int pad24 = (oh + 23) / 24 * 24, pad32 = (oh + 31) / 32 * 32;
+    return pad32 < pad24 ? 32 : 24;
 }
 
 template <class T>
@@ -375,8 +377,10 @@ int dispatch(Cfg cfg, FlParams& p, int mode, cudaStream_t s)
 {
     switch (cfg) {
         case CFG_1x1:  return launch_1x1<T>(p, mode, s);
-        case CFG_U2D2: return tall_tiles(2, p.oh) ? launch_cfg<T, 2, 12, 2, 12, 64, 32>(p, mode, s) : launch_cfg<T, 2, 12, 2, 12, 64, 24>(p, mode, s);
-        case CFG_U4D2: return tall_tiles(4, p.oh) ? launch_cfg<T, 4, 24, 2, 12, 64, 32>(p, mode, s) : launch_cfg<T, 4, 24, 2, 12, 64, 24>(p, mode, s);
+        case CFG_U2D2: { const int r = tile_rows(2, p.oh);
+                         return r == 32 ? launch_cfg<T, 2, 12, 2, 12, 64, 32>(p, mode, s) : launch_cfg<T, 2, 12, 2, 12, 64, 24>(p, mode, s); }
+        case CFG_U4D2: { const int r = tile_rows(4, p.oh);
+                         return r == 32 ? launch_cfg<T, 4, 24, 2, 12, 64, 32>(p, mode, s) : launch_cfg<T, 4, 24, 2, 12, 64, 24>(p, mode, s); }
         case CFG_U2D4: return launch_cfg<T, 2, 12, 4, 24, 32, 16>(p, mode, s);
         default: break;
     }
