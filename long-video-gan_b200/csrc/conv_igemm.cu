@@ -609,7 +609,9 @@ int run_igemm(const void* x, const void* w, void* y, int dtype, int n, int group
     }
     const size_t smem = (size_t)p.stages * p.stage_bytes + epi_bytes + 128;
     LVG_CUDA(cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int64_t ctas = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
+    const char* cta_env = getenv("LVG_CONV_CTAS");          // experiments: fewer persistent CTAs than SMs
+    const int max_ctas = cta_env ? atoi(cta_env) : num_sms();
+    int64_t ctas = p.total_tiles < max_ctas ? p.total_tiles : max_ctas;
     conv_igemm_kernel<<<(unsigned)ctas, kThreads, smem, s>>>(tm, p);
     LVG_LAUNCH_CHECK();
     return LVG_OK;
