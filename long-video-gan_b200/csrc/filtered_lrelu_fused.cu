@@ -19,30 +19,18 @@
 
 #include "common.cuh"
 #include "fir_passes.cuh"
+#include "filtered_lrelu_v3.cuh"
 #include <stdlib.h>
 
 namespace lvg {
+namespace flv3 {
+template <class T> int launch(int cfg, FlParams& p, int mode, cudaStream_t s);     // filtered_lrelu_v3.cu
+}
 namespace {
+using flv3::FlParams;
 
 enum { SIGN_NONE = 0, SIGN_WRITE = 1, SIGN_READ = 2 };
 
-struct FlParams {
-    const void* x;
-    const float* fu;
-    const float* fd;
-    const void* b;
-    const uint8_t* si;
-    void* y;
-    uint8_t* so;
-    int64_t xs[4], ys[4];
-    int n, c, ih, iw, oh, ow;
-    int px0, py0;
-    int s_h, s_wb, sx, sy;
-    int sw_active;          // write mode: samples at U >= sw_active get code 0
-    int tiles_x, tiles_y;
-    float gain, slope, clamp;
-    int flip;
-};
 
 constexpr int kThreads = 256;
 constexpr int kR = 4;       // outputs (down passes) / input groups (up passes) per thread
@@ -372,9 +360,19 @@ int tile_rows(int up, int oh)
     return pad32 < pad24 ? 32 : 24;
 }
 
+// LVG_FL_ENGINE=r2 keeps the scalar-access kernels of this file (A/B measurements); default: the vectorised kernels
+bool use_v3()
+{
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("LVG_FL_ENGINE"); v = (e && e[0] == 'r' && e[1] == '2') ? 0 : 1; }
+    return v == 1;
+}
+
 template <class T>
 int dispatch(Cfg cfg, FlParams& p, int mode, cudaStream_t s)
 {
+    if (use_v3() && p.slope <= 1.f && (cfg == CFG_U2D2 || cfg == CFG_U4D2 || cfg == CFG_U2D4))
+        return flv3::launch<T>(cfg == CFG_U2D2 ? 1 : cfg == CFG_U4D2 ? 2 : 3, p, mode, s);
     switch (cfg) {
         case CFG_1x1:  return launch_1x1<T>(p, mode, s);
         case CFG_U2D2: { const int r = tile_rows(2, p.oh);
