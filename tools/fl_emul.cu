@@ -204,7 +204,7 @@ int main()
     int bad = 0;
     typedef Geom<2, 12, 2, 12, 56, 24, 6, 4, 4, 4> U2D2;
     typedef Geom<4, 24, 2, 12, 56, 24, 2, 2, 4, 4> U4D2;
-    typedef Geom<2, 12, 4, 24, 32, 16, 4, 4, 4, 2> U2D4;
+    typedef Geom<2, 12, 4, 24, 31, 16, 8, 6, 4, 2> U2D4;
     printf("U2D2 smem %zu B, U4D2 %zu B, U2D4 %zu B\n", U2D2::smem_bytes(SIGN_READ), U4D2::smem_bytes(SIGN_READ), U2D4::smem_bytes(SIGN_READ));
     {
         Case c = {2, 12, 2, 12, 31, 38, 9, 8, 9, 8, 1.4142135f, 0.2f, 256.f, 0, 1.f};
