@@ -267,6 +267,23 @@ int lvg_fir1d_depthwise(const float* x, const float* w, float* y, int n, int gro
  */
 int lvg_grad_postprocess(float* g, int64_t n, float scale, float limit, void* stream);
 
+/*
+ * Fused tail of a training update over flat fp32 buffers, one pass, in place:
+ *   g' = nan_to_num(g * grad_scale, nan = 0, +-inf = +-grad_limit)      only if grad_limit > 0 (utils.py:120-121)
+ *   m  = lerp(m, g', 1 - beta1);  v = v * beta2 + (1 - beta2) * g'^2
+ *   p  = p - lr / (1 - beta1^step) * m / (sqrt(v) / sqrt(1 - beta2^step) + eps)
+ *        -- torch.optim.Adam.step() as the reference configures it (model/video_gan_lres.py:84-85: no weight decay,
+ *           no amsgrad), `step` counting from 1
+ *   p_ema = lerp(p_ema, p, 1 - ema_beta)                                 only if p_ema != NULL
+ *        -- update_G_ema (model/video_gan_lres.py:208-214)
+ * write_grad != 0 stores g' back (what utils.sync_grads leaves in .grad). Replaces ~300 per-tensor launches.
+ */
+int lvg_adam_step(float* p, float* g, float* m, float* v, float* p_ema, int64_t n, float lr, float beta1, float beta2,
+                  float eps, int64_t step, float grad_scale, float grad_limit, int write_grad, float ema_beta, void* stream);
+
+/* a = torch.lerp(a, b, weight) over flat fp32 buffers (the buffers of update_G_ema) */
+int lvg_lerp(float* a, const float* b, int64_t n, float weight, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

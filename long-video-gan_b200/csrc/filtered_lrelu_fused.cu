@@ -371,7 +371,9 @@ bool use_v3()
 template <class T>
 int dispatch(Cfg cfg, FlParams& p, int mode, cudaStream_t s)
 {
-    if (use_v3() && p.slope <= 1.f && (cfg == CFG_U2D2 || cfg == CFG_U4D2 || cfg == CFG_U2D4))
+    // the vectorised kernels serve slope <= 1 (leaky ReLU as a max) and word-aligned sign rows; anything else: the kernels below
+    const bool v3_ok = p.slope <= 1.f && (mode != SIGN_READ || (p.s_wb % 4 == 0 && (reinterpret_cast<uintptr_t>(p.si) & 3) == 0));
+    if (use_v3() && v3_ok && (cfg == CFG_U2D2 || cfg == CFG_U4D2 || cfg == CFG_U2D4))
         return flv3::launch<T>(cfg == CFG_U2D2 ? 1 : cfg == CFG_U4D2 ? 2 : 3, p, mode, s);
     switch (cfg) {
         case CFG_1x1:  return launch_1x1<T>(p, mode, s);

@@ -270,7 +270,7 @@ struct Geom {
     static constexpr int NINY = (RDY - 1) * DOWN + FD;
     static constexpr int A_SIZE = cmax(A_IN, A_ACT), B_SIZE = cmax(B_UX, B_DX);
     static constexpr int TAPS = 2 * (2 * UP * KT) + 2 * FD + 32;      // gx pairs, gy pairs, fd pairs, sign multiplier table
-    static constexpr int SIGN_PITCH = UW / 4 + 2;
+    static constexpr int SIGN_PITCH = rup(UW / 4 + 2 + 3, 4);        // staged bytes per row: a thread's two bytes + word-alignment slack
     static constexpr int SIGN_BYTES = rup(UH * SIGN_PITCH, 16);
     static constexpr bool STREAM_TAPS = FD > 12;           // 24-tap down filters: taps read per use instead of held in registers
     static_assert(FU % UP == 0 && K % 2 == 0, "filter length must be an even multiple of the up-sampling factor");
@@ -387,14 +387,19 @@ FL_HD void stage0(const FlParams& p, const Tile& t, const Smem& s, int tid)
             const int c = (i & 1) ? ((i >> 1) >> 2) : ((i >> 1) & 3);          // entry n = i/2 holds the multipliers of codes n&3, n>>2
             s.lut[i] = (c & 2) ? 0.f : ((c & 1) ? p.slope : 1.f);
         }
+        // the tile's slab of the sign tensor, staged with aligned 32-bit loads (rows are multiples of 4 bytes, host-checked):
+        // staged row r holds global bytes [gb_al, gb_al + SIGN_PITCH) of row V0 + sy + r, gb_al = first needed byte rounded down
         const uint8_t* sgn = p.si + t.plane * (int64_t)p.s_h * p.s_wb;
-        const int gy0 = t.V0 + p.sy, gb0 = (t.U0 + p.sx) >> 2;                 // arithmetic shift = floor
-        for (int i = tid; i < t.uh_e * G::SIGN_PITCH; i += kThreads) {
-            const int row = i / G::SIGN_PITCH, bb = i - row * G::SIGN_PITCH;
-            const int gy = gy0 + row, gb = gb0 + bb;
-            uint8_t v = 0;
-            if ((unsigned)gy < (unsigned)p.s_h && (unsigned)gb < (unsigned)p.s_wb) v = sgn[(int64_t)gy * p.s_wb + gb];
-            s.sign[i] = v;
+        const int gy0 = t.V0 + p.sy, gb_al = ((t.U0 + p.sx) >> 2) & ~3;         // arithmetic shift / mask = floor
+        constexpr int W4 = G::SIGN_PITCH / 4;
+        uint32_t* dst = reinterpret_cast<uint32_t*>(s.sign);
+        for (int i = tid; i < t.uh_e * W4; i += kThreads) {
+            const int row = i / W4, w = i - row * W4;
+            const int gy = gy0 + row, gb = gb_al + 4 * w;
+            uint32_t v = 0;
+            if ((unsigned)gy < (unsigned)p.s_h && (unsigned)gb < (unsigned)p.s_wb)
+                v = *reinterpret_cast<const uint32_t*>(sgn + (int64_t)gy * p.s_wb + gb);
+            dst[i] = v;
         }
     }
 }
@@ -511,6 +516,7 @@ FL_HD void stage3(const FlParams& p, const Tile& t, const Smem& s, int tid)
     uint8_t* so = MODE == SIGN_WRITE ? p.so + t.plane * (int64_t)p.s_h * p.s_wb + (int64_t)t.V0 * p.s_wb + b0 : nullptr;
     const int s_wb = p.s_wb;
     const int sh2 = ((t.U0 + p.sx) & 3) * 2;                // read mode: bit offset of the first sample inside its byte
+    const int sgn_skew = ((t.U0 + p.sx) >> 2) & 3;          //            first needed byte inside the staged (word-aligned) row
 
     const int nitems = t.ncg_e * t.ntgy_e;
     const FastDiv by_cg(t.ncg_e);
@@ -527,7 +533,7 @@ FL_HD void stage3(const FlParams& p, const Tile& t, const Smem& s, int tid)
             rows_left = cg < nb ? nr - tgy * RY * UP : 0;
         }
         float* dst_item = s.A + (tgy * (RY / 2) * UP) * G::S_A + 4 * cg;
-        const uint8_t* sr_item = MODE == SIGN_READ ? s.sign + (tgy * RY * UP) * G::SIGN_PITCH + cg : nullptr;
+        const uint8_t* sr_item = MODE == SIGN_READ ? s.sign + (tgy * RY * UP) * G::SIGN_PITCH + cg + sgn_skew : nullptr;
 #pragma unroll
         for (int ph = 0; ph < UP; ph++) {
             float2 g[KT];

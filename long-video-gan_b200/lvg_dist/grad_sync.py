@@ -165,8 +165,11 @@ class FlatGradSync:
         if src:
             torch._foreach_copy_(dst, src)
 
-    def sync(self, gain=None):
-        """Average the gradients over the process group, scale by `gain` (None = 1, utils.py:120), sanitise NaN/Inf."""
+    def sync(self, gain=None, postprocess=True):
+        """Average the gradients over the process group, scale by `gain` (None = 1, utils.py:120), sanitise NaN/Inf.
+        ``postprocess=False`` leaves the summed gradients in the buffer and the outstanding factor in ``pending_scale``:
+        ``FlatAdam.step(grad_scale=sync.pending_scale)`` then scales and sanitises inside the optimiser kernel."""
+        self.pending_scale = 1.0
         if self.flat.numel() == 0:
             return
         world = self._world()
@@ -188,7 +191,11 @@ class FlatGradSync:
                 dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
         if isinstance(gain, torch.Tensor):
             gain = gain.item()
-        postprocess_(self.flat, scale=(1.0 if gain is None else float(gain)) / world, limit=_GRAD_LIMIT)
+        scale = (1.0 if gain is None else float(gain)) / world
+        if postprocess:
+            postprocess_(self.flat, scale=scale, limit=_GRAD_LIMIT)
+        else:
+            self.pending_scale = scale
 
 
 def postprocess_(flat, scale, limit=_GRAD_LIMIT):

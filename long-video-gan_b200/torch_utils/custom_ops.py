@@ -43,6 +43,8 @@ _SIGNATURES = {
     'lvg_build_info': (ctypes.c_char_p, []),
     'lvg_launch_count': (_c_i64, []),
     'lvg_grad_postprocess': (_c_int, [_c_void_p, _c_i64, _c_float, _c_float, _c_void_p]),
+    'lvg_adam_step': (_c_int, [_c_void_p] * 5 + [_c_i64] + [_c_float] * 4 + [_c_i64, _c_float, _c_float, _c_int, _c_float, _c_void_p]),
+    'lvg_lerp': (_c_int, [_c_void_p, _c_void_p, _c_i64, _c_float, _c_void_p]),
     'lvg_bias_act': (_c_int, [_c_void_p] * 6 + [_c_int, _c_i64, _c_i64, _c_i64, _c_int, _c_int, _c_float, _c_float, _c_float, _c_void_p]),
     'lvg_bias_act_grad_db': (_c_int, [_c_void_p] * 6 + [_c_int, _c_i64, _c_i64, _c_i64, _c_int, _c_float, _c_float, _c_float, _c_void_p]),
     'lvg_bias_act_fwd_codes': (_c_int, [_c_void_p] * 4 + [_c_int, _c_i64, _c_i64, _c_i64, _c_int, _c_float, _c_float, _c_float, _c_void_p]),

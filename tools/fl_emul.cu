@@ -172,7 +172,7 @@ static int run_case(const Case& c, const char* name)
 
     // ---- read mode: random sign tensor of a different size, offsets sx, sy (incl. negative / beyond the tensor)
     for (int trial = 0; trial < 3; trial++) {
-        const int s2h = sh + (trial == 1 ? -7 : 5), s2wb = s_wb + (trial == 1 ? -1 : 2);
+        const int s2h = sh + (trial == 1 ? -7 : 5), s2wb = s_wb + (trial == 1 ? -4 : 4);    // rows of the sign tensor are multiples of 4 bytes (the kernel loads words)
         std::vector<uint8_t> si((size_t)C * s2h * s2wb);
         for (auto& v : si) v = (uint8_t)(rand() & 0xFF);
         const int sx = trial == 0 ? 3 : (trial == 1 ? -5 : 6), sy = trial == 0 ? 2 : (trial == 1 ? -3 : 0);
