@@ -513,13 +513,48 @@ class _InjectGrad(torch.autograd.Function):
         return g, None
 
 
+class UpdateTail:
+    """The optimiser side of an update at the networks' parameter counts: FlatAdam over one flat fp32 buffer (+ the EMA copy
+    for the generator, update_G_ema) -- sanitise, Adam and EMA in ONE kernel (lvg_adam_step) instead of the reference's
+    ~900 per-tensor launches (utils.py:116-124, video_gan_lres.py:84-85,208-214). Gradients: the all-reduced flat buffer
+    (several GPUs) or a synthetic one of the same size."""
+
+    def __init__(self, n_elems, device, ema, params=None, grad_sync=None):
+        from lvg_dist.flat_optim import FlatAdam
+        if params is None:
+            params = [torch.nn.Parameter(torch.randn(n_elems, device=device) * 0.02)]
+        self.opt = FlatAdam(list(params), lr=3e-3, betas=(0.0, 0.99), grad_sync=grad_sync)
+        if grad_sync is None:
+            self.opt.flat_grads.normal_(0, 1e-3)
+            for p, v in zip(self.opt.params, self.opt._grad_views):
+                p.grad = v
+        self.ema_flat = torch.zeros_like(self.opt.flat_params) if ema else None
+        if ema:
+            owner = self
+
+            class _Ema:          # the parameters' EMA buffer, updated inside the optimiser kernel
+                flat_params = owner.ema_flat
+
+                @staticmethod
+                def lerp_range(a, b, beta):
+                    pass
+
+                @staticmethod
+                def update_buffers(beta):
+                    pass
+            self.opt._ema = _Ema
+
+    def step(self, grad_scale=1.0):
+        self.opt.step(grad_scale=grad_scale, ema_beta=0.999 if self.ema_flat is not None else None)
+
+
 class GradExchange:
     """The gradient side of a network for the data-parallel step: `n_elems` fp32 parameters in tensors of the sizes a
     conv stack has, registered with FlatGradSync(overlap=True): each backward_bucket(k) runs a REAL autograd backward
     over the parameters of bucket k (AccumulateGrad -> post-accumulate hooks -> the bucket's asynchronous NCCL
     all-reduce starts while the remaining segments of the pass execute), finish() = FlatGradSync.sync()."""
 
-    def __init__(self, n_elems, device, buckets):
+    def __init__(self, n_elems, device, buckets, ema=False):
         from lvg_dist.grad_sync import FlatGradSync
         n_tensors = 96
         sizes = [n_elems // n_tensors] * n_tensors
@@ -527,6 +562,7 @@ class GradExchange:
         self.module = torch.nn.Module()
         self.module.ps = torch.nn.ParameterList([torch.nn.Parameter(torch.zeros(sz, device=device)) for sz in sizes])
         self.sync = FlatGradSync(self.module, overlap=True, buckets=buckets, backwards_per_sync=1)
+        self.tail = UpdateTail(n_elems, device, ema, params=self.module.ps, grad_sync=self.sync)
         self.grads = [torch.randn(sz, device=device) * 1e-3 for sz in sizes]
         self.members = [[] for _ in range(len(self.sync._slices))]
         for i, b in self.sync._bucket_of.items():
@@ -538,7 +574,9 @@ class GradExchange:
         torch.autograd.backward(outs)
 
     def finish(self, gain):
-        self.sync.sync(gain=gain)
+        # the tail of the update in ONE kernel: scale + nan_to_num of the all-reduced gradients, Adam, EMA (lvg_adam_step)
+        self.sync.sync(gain=gain, postprocess=False)
+        self.tail.step(self.sync.pending_scale)
 
     def begin(self):
         self.sync.zero_grad()
@@ -560,7 +598,10 @@ def run_ours(args, workload, scope, steps, rank, world, local_rank, device, with
     ex_g = ex_d = None
     if world > 1:
         ng, nd = GRAD_ELEMS[workload]
-        ex_g, ex_d = GradExchange(ng, device, kBuckets), GradExchange(nd, device, kBuckets)
+        ex_g, ex_d = GradExchange(ng, device, kBuckets, ema=True), GradExchange(nd, device, kBuckets)
+    else:
+        ng, nd = GRAD_ELEMS[workload]
+        tail_g, tail_d = UpdateTail(ng, device, ema=True), UpdateTail(nd, device, ema=False)
 
     # e2e: the step's real-video batch comes from pinned host memory and ENTERS the replay: lres -- the discriminator's
     # first layer (pad to 64x64, 1x1x1 conv 3->32, discriminator_lres.py:135-213; a library conv, row N1) is computed from
@@ -598,8 +639,9 @@ def run_ours(args, workload, scope, steps, rank, world, local_rank, device, with
         return [half + (n - half) * k // kBuckets for k in range(kBuckets + 1)]
 
     if world == 1:
-        segs_a = [lambda timer=None: (G.forward_backward(timer), D.forward_backward(timer))]
-        segs_b = [lambda timer=None: (G.forward_only(), D.forward_backward(timer), D.forward_backward(timer))]
+        # every update ends with its optimiser tail (G: Adam + EMA of the generator, D: Adam) at the networks' parameter counts
+        segs_a = [lambda timer=None: (G.forward_backward(timer), D.forward_backward(timer), tail_g.step())]
+        segs_b = [lambda timer=None: (G.forward_only(), D.forward_backward(timer), D.forward_backward(timer), tail_d.step())]
     else:
         ca, cb = tail_cuts(len(G.items)), tail_cuts(len(D.items))
         segs_a = [lambda timer=None: (D.forward_backward(timer), G.forward_backward(timer, 0, ca[0]))]

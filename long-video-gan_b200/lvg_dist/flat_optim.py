@@ -48,15 +48,13 @@ class FlatAdam:
                 raise RuntimeError('FlatAdam expects fp32 master parameters (as the reference trains)')
         device = self.params[0].device
         self.param_groups = [dict(params=self.params, lr=float(lr), betas=(float(betas[0]), float(betas[1])), eps=float(eps))]
-        sizes = [p.numel() for p in self.params]
-        self._offsets = [0]
-        for n in sizes:
-            self._offsets.append(self._offsets[-1] + n)
+        from lvg_dist.grad_sync import flat_offsets
+        self._offsets = flat_offsets([p.numel() for p in self.params])      # 256-byte aligned starts, as FlatGradSync lays out
         total = self._offsets[-1]
-        self.flat_params = torch.empty(total, dtype=torch.float32, device=device)
+        self.flat_params = torch.zeros(total, dtype=torch.float32, device=device)
         with torch.no_grad():
-            for p, a, b in zip(self.params, self._offsets[:-1], self._offsets[1:]):
-                view = self.flat_params[a:b].view_as(p)
+            for p, a in zip(self.params, self._offsets[:-1]):
+                view = self.flat_params[a:a + p.numel()].view_as(p)
                 view.copy_(p)
                 p.data = view
         if grad_sync is not None:
@@ -66,7 +64,7 @@ class FlatAdam:
             self._grad_views = grad_sync._views
         else:
             self.flat_grads = torch.zeros(total, dtype=torch.float32, device=device)
-            self._grad_views = [self.flat_grads[a:b].view_as(p) for p, a, b in zip(self.params, self._offsets[:-1], self._offsets[1:])]
+            self._grad_views = [self.flat_grads[a:a + p.numel()].view_as(p) for p, a in zip(self.params, self._offsets[:-1])]
             for p, v in zip(self.params, self._grad_views):
                 if p.grad is not None:
                     v.copy_(p.grad)
@@ -186,10 +184,10 @@ class FlatEMA:
         params, params_ema = list(net.parameters()), list(net_ema.parameters())
         if [id(p) for p in params] != [id(p) for p in optimizer.params] or len(params) != len(params_ema):
             raise ValueError('FlatEMA: the optimiser must own exactly the parameters of `net`, in order')
-        self.flat_params = torch.empty_like(optimizer.flat_params)
+        self.flat_params = torch.zeros_like(optimizer.flat_params)
         with torch.no_grad():
-            for q, a, b in zip(params_ema, optimizer._offsets[:-1], optimizer._offsets[1:]):
-                view = self.flat_params[a:b].view_as(q)
+            for q, a in zip(params_ema, optimizer._offsets[:-1]):
+                view = self.flat_params[a:a + q.numel()].view_as(q)
                 view.copy_(q)
                 q.data = view
         bufs = [(b, be) for b, be in zip(net.buffers(), net_ema.buffers())]

@@ -26,6 +26,17 @@ import torch.distributed as dist
 _GRAD_LIMIT = 1e5     # utils.py:121
 
 
+def flat_offsets(sizes, align=64):
+    """Start offsets (in elements) of tensors of the given sizes in a flat buffer, each on an `align`-element boundary;
+    the last entry is the buffer length."""
+    offsets, ofs = [], 0
+    for n in sizes:
+        offsets.append(ofs)
+        ofs += (n + align - 1) // align * align
+    offsets.append(ofs)
+    return offsets
+
+
 class FlatGradSync:
     """Owns one flat fp32 gradient buffer for a module and exchanges it across ranks.
 
@@ -60,11 +71,12 @@ class FlatGradSync:
             self.flat = torch.zeros(0)
             return
         device = self.params[0].device
-        total = sum(p.numel() for p in self.params)
-        self.flat = torch.zeros(total, dtype=torch.float32, device=device)
+        # every tensor starts on a 256-byte boundary of the flat buffer (vector accesses, and library kernels pick the same
+        # code path as for separately allocated tensors); the padding elements stay zero
+        self.offsets = flat_offsets([p.numel() for p in self.params])
+        self.flat = torch.zeros(self.offsets[-1], dtype=torch.float32, device=device)
         self._views = []
-        ofs = 0
-        for p in self.params:
+        for p, ofs in zip(self.params, self.offsets):
             if p.dtype != torch.float32:
                 raise RuntimeError('FlatGradSync expects fp32 master parameters (as the reference trains)')
             view = self.flat[ofs:ofs + p.numel()].view_as(p)
@@ -73,7 +85,6 @@ class FlatGradSync:
                     view.copy_(p.grad)
                 p.grad = view
             self._views.append(view)
-            ofs += p.numel()
         if self.overlap:
             self._make_buckets(max(1, int(buckets)))
 
@@ -82,12 +93,12 @@ class FlatGradSync:
         """Contiguous slices of the flat buffer of ~equal size; bucket 0 holds the LAST parameters (ready first)."""
         total = self.flat.numel()
         target = (total + n_buckets - 1) // n_buckets
-        ofs, start, count = 0, 0, 0
+        start, count = 0, 0
         groups, cur = [], []
         for i, p in enumerate(self.params):
             cur.append(i)
-            count += p.numel()
-            ofs += p.numel()
+            ofs = self.offsets[i + 1]
+            count = ofs - start
             if count >= target or i == len(self.params) - 1:
                 groups.append((cur, start, ofs))
                 cur, start, count = [], ofs, 0
@@ -145,6 +156,13 @@ class FlatGradSync:
 
     def _world(self):
         return dist.get_world_size(self.group) if dist.is_available() and dist.is_initialized() else 1
+
+    def packed(self):
+        """The gradients without the alignment padding, concatenated in parameter order (a copy) -- what
+        ``torch.cat([p.grad.flatten() ...])`` of the reference's ``sync_grads`` holds."""
+        if not self.params:
+            return self.flat.clone()
+        return torch.cat([v.reshape(-1) for v in self._views])
 
     def zero_grad(self):
         """Zero in place (``set_to_none`` would detach the views from the flat buffer)."""

@@ -45,17 +45,17 @@ def _worker(rank, world, port, ret):
         net.ps = torch.nn.ParameterList([torch.nn.Parameter(torch.zeros(5, 3)), torch.nn.Parameter(torch.zeros(7)),
                                          torch.nn.Parameter(torch.zeros(2, 2, 2))])
         sync = FlatGradSync(net)
-        assert sync.flat.numel() == 15 + 7 + 8
+        assert sync.packed().numel() == 15 + 7 + 8 and sync.flat.numel() % 64 == 0
         for p, g in zip(sync.params, _make_grads(rank)):
             p.grad.copy_(g.reshape(p.shape))                 # what backward() does: write through the view
         assert all(p.grad.data_ptr() >= sync.flat.data_ptr() for p in sync.params)
         sync.sync(gain=0.5)
-        out1 = sync.flat.clone()
+        out1 = sync.packed()
         # a replaced .grad (e.g. optimizer.zero_grad(set_to_none=True) followed by backward) is folded back in
         for p, g in zip(sync.params, _make_grads(rank)):
             p.grad = g.reshape(p.shape).clone()
         sync.sync(gain=0.5)
-        out2 = sync.flat.clone()
+        out2 = sync.packed()
         # functional form keeps one buffer per module
         s2 = sync_grads(net, gain=1.0)
         assert s2 is sync_grads(net, gain=1.0)
@@ -115,7 +115,7 @@ def _overlap_worker(rank, world, port, ret):
                 if overlap and it == 1:
                     assert any(w is not None for w in sync._works)     # buckets left during the backward pass
                 sync.sync(gain=0.5)
-                outs.append(sync.flat.clone())
+                outs.append(sync.packed())
         ret[rank] = outs
     finally:
         dist.destroy_process_group()
@@ -182,7 +182,7 @@ def _loop_worker(rank, world, port, ret):
                         p.grad = g.reshape(p.shape)
                 elif mode == 'dropin':
                     s = grad_sync.sync_grads(net, gain=gain)
-                    assert s.flat.numel() == sum(p.numel() for p in net.parameters())     # built although requires_grad was False
+                    assert s.packed().numel() == sum(p.numel() for p in net.parameters())     # built although requires_grad was False
                 else:
                     if it == 1:
                         assert any(w is not None for w in sync._works)                 # buckets left during backward
