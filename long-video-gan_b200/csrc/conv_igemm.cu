@@ -36,6 +36,14 @@
 #include "tcgen05.cuh"
 
 namespace lvg {
+// conv_pointwise.cu: streaming fp32 kernels for 1x1x1 convolutions with few channels (HBM-bound; the engine would re-tile and pad)
+bool pw_supported(int dtype, int groups, int cin, int cout, int kt, int kh, int kw, int pad_t, int pad_h, int pad_w, int stride, int64_t P, int wgrad);
+int pw_conv(const float* x, const float* w, float* y, int n, int cin, int cout, int64_t P, int64_t w_sco, int64_t w_sci, cudaStream_t s);
+int64_t pw_wgrad_workspace(int cin, int cout);
+int pw_wgrad(const float* x, const float* dy, float* dw, int n, int cin, int cout, int64_t P, void* workspace, int64_t workspace_bytes, cudaStream_t s);
+}
+
+namespace lvg {
 namespace {
 
 using namespace tc;
@@ -647,6 +655,9 @@ extern "C" int lvg_convnd_fprop(const void* x, const void* w, void* y, int dtype
                                 float gain, float clamp, void* workspace, int64_t workspace_bytes, void* stream)
 {
     LVG_REQUIRE(x && w && y, "convnd_fprop: x, w, y must not be NULL");
+    if (!bias && act == 0 && gain == 1.f && clamp < 0.f &&
+        pw_supported(dtype, groups, cin, cout, kt, kh, kw, pad_t, pad_h, pad_w, stride, (int64_t)t * h * wd, 0))
+        return pw_conv((const float*)x, (const float*)w, (float*)y, n, cin, cout, (int64_t)t * h * wd, cin, 1, (cudaStream_t)stream);
     if (!nd_supported(dtype, kt, kh, kw) || n < 1 || pad_t < 0 || pad_h < 0 || pad_w < 0 || stride < 1 || stride > 4) {
         set_error("convnd_fprop: outside the tensor-core kernel's envelope");
         return LVG_UNSUPPORTED;
@@ -661,6 +672,8 @@ extern "C" int lvg_convnd_dgrad(const void* dy, const void* w, void* dx, int dty
                                 void* stream)
 {
     LVG_REQUIRE(dy && w && dx, "convnd_dgrad: dy, w, dx must not be NULL");
+    if (pw_supported(dtype, groups, cin, cout, kt, kh, kw, pad_t, pad_h, pad_w, stride, (int64_t)t * h * wd, 0))   // dx = W^T dy
+        return pw_conv((const float*)dy, (const float*)w, (float*)dx, n, cout, cin, (int64_t)t * h * wd, 1, cin, (cudaStream_t)stream);
     if (!nd_supported(dtype, kt, kh, kw) || n < 1 || pad_t < 0 || pad_h < 0 || pad_w < 0 || pad_t > kt - 1 || pad_h > kh - 1 || pad_w > kw - 1 ||
         stride < 1 || stride > 4) {
         set_error("convnd_dgrad: outside the tensor-core kernel's envelope");
@@ -931,13 +944,27 @@ WgradPlan wgrad_plan(int dtype, int n, int groups, int cin, int cout, int t, int
     q.smem = (size_t)q.stages * q.stage_bytes + 256;
     if (tile_bytes > q.smem) q.smem = tile_bytes;
     q.smem += 128;
-    // split the pixel range until the grid fills the machine about twice
+    // Split the pixel range over `nsplit` CTAs per output tile. One CTA per SM is resident, so the kernel runs in waves of
+    // num_sms CTAs: choose the split that minimises waves x (stages per CTA + a fixed per-CTA cost of ~4 stages: clearing
+    // shared memory, the TMEM -> global epilogue) -- e.g. 3 output tiles: 49 splits = 147 CTAs = one wave of 470 stages
+    // instead of 64 splits = 192 CTAs = two waves of 360. Partial sums are capped at 256 MB.
     const int64_t ctas = (int64_t)q.ntiles * kh * kt * q.mt * groups;
     const int64_t stages = (int64_t)n * to * q.nseg * ((ho + q.rh - 1) / q.rh);
-    int64_t ns = (2 * 148 + ctas - 1) / ctas;
-    if (ns > stages) ns = stages;
-    if (ns > 64) ns = 64;
-    if (ns < 1) ns = 1;
+    const int sms = 148;
+    int64_t cap = 160;
+    if (cap > stages) cap = stages;
+    while (cap > 1 && cap * q.dw_elems * 4 > (256ll << 20)) cap--;
+    int64_t ns = 1;
+    double best = 1e300;
+    for (int64_t k = 1; k <= cap; k++) {
+        const int64_t waves = (ctas * k + sms - 1) / sms;
+        const double t = (double)waves * ((double)((stages + k - 1) / k) + 4.0);
+        if (t < best * 0.999) { best = t; ns = k; }
+    }
+    {
+        const char* e = getenv("LVG_WGRAD_NSPLIT");       // experiments
+        if (e && atoi(e) >= 1) ns = atoi(e) < stages ? atoi(e) : stages;
+    }
     q.nsplit = (int)ns;
     q.part_bytes = q.nsplit > 1 ? q.nsplit * q.dw_elems * 4 : 0;
     return q;
@@ -952,6 +979,7 @@ extern "C" int64_t lvg_convnd_wgrad_workspace(int dtype, int n, int groups, int 
     if (!nd_supported(dtype, kt, kh, kw) || n < 1 || groups < 1 || kw > 3) return -1;
     const int to = t + 2 * pad_t - kt + 1, ho = h + 2 * pad_h - kh + 1, wo = wd + 2 * pad_w - kw + 1;
     if (to < 1 || ho < 1 || wo < 1 || wo > 4 * (128 - kw + 1)) return -1;
+    if (pw_supported(dtype, groups, cin, cout, kt, kh, kw, pad_t, pad_h, pad_w, 1, (int64_t)t * h * wd, 1)) return pw_wgrad_workspace(cin, cout);
     const WgradPlan q = wgrad_plan(dtype, n, groups, cin, cout, t, h, wd, to, ho, wo, kt, kh, kw);
     return q.a_bytes + q.b_bytes + q.part_bytes + 1024;
 }
@@ -961,6 +989,10 @@ extern "C" int lvg_convnd_wgrad(const void* x, const void* dy, void* dw, int dty
                                 void* stream)
 {
     LVG_REQUIRE(x && dy && dw, "convnd_wgrad: x, dy, dw must not be NULL");
+    if (pw_supported(dtype, groups, cin, cout, kt, kh, kw, pad_t, pad_h, pad_w, stride, (int64_t)t * h * wd, 1)) {
+        LVG_REQUIRE(workspace, "convnd_wgrad: workspace must not be NULL");
+        return pw_wgrad((const float*)x, (const float*)dy, (float*)dw, n, cin, cout, (int64_t)t * h * wd, workspace, workspace_bytes, (cudaStream_t)stream);
+    }
     const int to = t + 2 * pad_t - kt + 1, ho = h + 2 * pad_h - kh + 1, wo = wd + 2 * pad_w - kw + 1;
     if (!nd_supported(dtype, kt, kh, kw) || n < 1 || kw > 3 || pad_t < 0 || pad_h < 0 || pad_w < 0 || to < 1 || ho < 1 || wo < 1 ||
         wo > 4 * (128 - kw + 1) || stride < 1 || stride > 4) {

@@ -113,7 +113,7 @@ def test_fused_step_sanitises_like_sync_grads_cuda():
     ref.grad = torch.nan_to_num(g * 0.5, nan=0, posinf=1e5, neginf=-1e5)
     ro.step()
     assert torch.isfinite(p).all() and _close(p.detach(), ref.detach(), 5e-6)
-    assert torch.equal(opt.flat_grads, ref.grad)                                 # the sanitised gradient is what stays in .grad
+    assert torch.equal(opt.flat_grads[:1000], ref.grad)                                 # the sanitised gradient is what stays in .grad
 
 
 @pytest.mark.gpu

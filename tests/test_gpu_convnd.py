@@ -46,6 +46,13 @@ CASES = [
     ('3d 3x3x3 3x4 image', (2, 40, 7, 3, 4), (40, 40, 3, 3, 3), (1, 1, 1), 1),
     ('1d k3', (2, 64, 16), (32, 64, 3), (1,), 1),
     ('1d k1', (3, 200, 16), (50, 200, 1), (0,), 1),
+    # few channels, 1x1x1, fp32: the streaming SIMT kernels of csrc/conv_pointwise.cu (fp16 / more channels: the engine)
+    ('3d 1x1x1 pointwise 3->32', (2, 3, 5, 16, 20), (32, 3, 1, 1, 1), (0, 0, 0), 1),
+    ('3d 1x1x1 pointwise 64->3', (2, 64, 3, 36, 64), (3, 64, 1, 1, 1), (0, 0, 0), 1),
+    ('3d 1x1x1 pointwise 64->64', (2, 64, 7, 18, 30), (64, 64, 1, 1, 1), (0, 0, 0), 1),
+    ('3d 1x1x1 pointwise 61->128 ragged', (3, 61, 3, 9, 12), (128, 61, 1, 1, 1), (0, 0, 0), 1),
+    ('3d 1x1x1 pointwise 128->33', (1, 128, 2, 10, 14), (33, 128, 1, 1, 1), (0, 0, 0), 1),
+    ('2d 1x1 pointwise 5->7 tiny', (4, 5, 2, 2), (7, 5, 1, 1), (0, 0), 1),
 ]
 
 
