@@ -22,6 +22,8 @@ def main(path):
         if r is hdr or len(r) < len(hdr) or r[ix['Metric Name']] != 'gpu__time_duration.sum':
             continue
         val = float(r[ix['Metric Value']].replace(',', ''))
+        if val != val:          # ncu occasionally reports nan for a launch
+            continue
         unit = r[ix['Metric Unit']]
         us = val / 1e3 if unit in ('ns', 'nsecond') else val * 1e3 if unit in ('ms', 'msecond') else val
         k = short(r[ix['Kernel Name']])
