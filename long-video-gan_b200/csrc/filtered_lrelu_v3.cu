@@ -6,7 +6,7 @@ namespace lvg {
 namespace flv3 {
 
 template <class T, class G, int MODE>
-__global__ void __launch_bounds__(kThreads, G::CTAS) filtered_lrelu_v3_kernel(FlParams p)
+__global__ void __launch_bounds__(kThreads, G::ctas(MODE)) filtered_lrelu_v3_kernel(FlParams p)
 {
     extern __shared__ __align__(16) float smem[];
     const Tile t = make_tile<G>(p, blockIdx.x);

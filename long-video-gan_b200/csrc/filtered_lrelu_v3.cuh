@@ -282,8 +282,13 @@ struct Geom {
     {
         return (size_t)(A_SIZE + B_SIZE + TAPS) * sizeof(float) + (mode == SIGN_READ ? SIGN_BYTES : 0);
     }
-    // resident CTAs per SM the kernel is compiled for (227 KB of shared memory per SM, 1 KB reserved per CTA)
-    static constexpr int CTAS = ((A_SIZE + B_SIZE + TAPS) * 4 + SIGN_BYTES + 1024) * 3 <= 232448 ? 3 : 2;
+    // resident CTAs per SM the kernel is compiled for (227 KB of shared memory per SM, 1 KB reserved per CTA). Four CTAs
+    // mean 64 registers per thread: the up-4 configuration fits without spilling, up-2 / down-2 spills 60-140 bytes.
+    static constexpr int ctas(int mode)
+    {
+        const int bytes = (A_SIZE + B_SIZE + TAPS) * 4 + (mode == SIGN_READ ? SIGN_BYTES : 0) + 1024;
+        return bytes * 4 <= 232448 ? 4 : bytes * 3 <= 232448 ? 3 : 2;
+    }
 };
 
 struct Tile {
@@ -463,6 +468,7 @@ FL_HD void stage2(const Tile& t, const Smem& s, int tid)
     constexpr int UP = G::UP, KT = G::KT, RX = G::RX;
     const int nitems = t.nrp_e * t.ntg_e;
     const FastDiv by_rp(t.nrp_e);
+#pragma unroll 1
     for (int id = tid; id < nitems; id += kThreads) {
         const int tg = by_rp.div(id), rp = id - tg * t.nrp_e;
         const float* src = s.A + rp * G::S_IN + 2 * RX * tg;
@@ -520,6 +526,7 @@ FL_HD void stage3(const FlParams& p, const Tile& t, const Smem& s, int tid)
 
     const int nitems = t.ncg_e * t.ntgy_e;
     const FastDiv by_cg(t.ncg_e);
+#pragma unroll 1
     for (int id = tid; id < nitems; id += kThreads) {
         const int tgy = by_cg.div(id), cg = id - tgy * t.ncg_e;
         const float* src = s.B + (tgy * (RY / 2)) * G::P_UX + 4 * cg;
@@ -644,6 +651,7 @@ FL_HD void stage4(const Tile& t, const Smem& s, int tid)
     const int nm_e = cdiv(t.tuh_e, 2 * G::UP) * G::UP;
     const int ntd_e = cdiv(t.tow_e, RDX);
     const FastDiv by_m(nm_e);
+#pragma unroll 1
     for (int id = tid; id < nm_e * ntd_e; id += kThreads) {
         const int tgd = by_m.div(id), m = id - tgd * nm_e;
         const float* src = s.A + m * G::S_A + DOWN * RDX * tgd;
@@ -697,6 +705,7 @@ FL_HD void stage5(const FlParams& p, const Tile& t, const Smem& s, int tid)
     const int ys2 = (int)p.ys[2], ys3 = (int)p.ys[3];      // a plane spans < 2^31 elements (host check)
     const int ncp_e = cdiv(t.tow_e, 2), ntg5_e = cdiv(t.toh_e, RDY);
     const FastDiv by_cp(ncp_e);
+#pragma unroll 1
     for (int id = tid; id < ncp_e * ntg5_e; id += kThreads) {
         const int tg5 = by_cp.div(id), cp = id - tg5 * ncp_e;
         const int mb = (DOWN * RDY * tg5) / (2 * UP) * UP;

@@ -120,6 +120,12 @@ def _use_codes(cfg, x):
             and hasattr(_plugin, 'bias_act_fwd_codes') and os.environ.get('LVG_BIAS_ACT_CODES', '1') != '0')
 
 
+def _fused_db():
+    # The fused bias gradient folds per-warp partial sums with fp32 atomics: the summation ORDER varies from run to run
+    # (differences of a few ulp). LVG_BIAS_ACT_FUSED_DB=0 computes db = dx.sum(...) like the reference -- bitwise reproducible.
+    return os.environ.get('LVG_BIAS_ACT_FUSED_DB', '1') != '0'
+
+
 def _dense_as(dy, shape, stride):
     """dy with exactly the given (dense) layout: the codes are indexed by memory offset."""
     # (a view with the right strides but a storage offset that is not 16-byte aligned -- e.g. the narrow of a dim-0 `cat`
@@ -165,7 +171,8 @@ class _BiasAct(torch.autograd.Function):
                 if torch.is_grad_enabled():          # create_graph: stay differentiable in dy
                     dx = _BiasActGradCodes.apply(dy, codes, cfg)
                 else:
-                    dx, db = _plugin.bias_act_bwd_codes(dy, codes, cfg.dim, cfg.spec.cuda_idx, cfg.alpha, cfg.gain, cfg.clamp, need_b)
+                    dx, db = _plugin.bias_act_bwd_codes(dy, codes, cfg.dim, cfg.spec.cuda_idx, cfg.alpha, cfg.gain, cfg.clamp,
+                                                        need_b and _fused_db())
             if need_b and db is None:
                 db = cfg.reduce_bias_grad(dx)
             return dx, db, None
@@ -181,7 +188,7 @@ class _BiasAct(torch.autograd.Function):
             if cfg.is_identity:
                 dx = dy
             elif (need_b and not torch.is_grad_enabled() and dy.dtype != torch.float64
-                  and hasattr(_plugin, 'bias_act_grad_db')):
+                  and hasattr(_plugin, 'bias_act_grad_db') and _fused_db()):
                 # plain backward (no create_graph): one kernel produces dx and the bias gradient
                 fused = _plugin.bias_act_grad_db(dy, b, x, y, cfg.dim, cfg.spec.cuda_idx, cfg.alpha, cfg.gain, cfg.clamp)
                 if fused is not None:

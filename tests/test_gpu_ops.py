@@ -534,3 +534,21 @@ def test_bias_act_backward_accepts_unaligned_upstream_gradient():
     rx, rb = torch.autograd.grad(yr, [xr, br], dy.double())
     assert_close(gx, rx, 1e-5, 'dx')
     assert_close(gb, rb, 1e-4, 'db')
+
+
+def test_bias_act_reproducible_bias_gradient_switch(monkeypatch):
+    """LVG_BIAS_ACT_FUSED_DB=0: db is the separate reduction of dx (bitwise equal to dx.sum, as the reference computes it);
+    the default fused path agrees with it to rounding."""
+    x = torch.randn(4, 48, 6, 9, 16, device=DEV)
+    b = torch.randn(48, device=DEV)
+    dy = torch.randn_like(x)
+    out = {}
+    for mode in ('1', '0'):
+        monkeypatch.setenv('LVG_BIAS_ACT_FUSED_DB', mode)
+        xg, bg = x.clone().requires_grad_(True), b.clone().requires_grad_(True)
+        y = bias_act.bias_act(xg, bg, act='lrelu', clamp=256)
+        dx, db = torch.autograd.grad(y, [xg, bg], dy)
+        out[mode] = (dx, db)
+    assert torch.equal(out['0'][0], out['1'][0])
+    assert torch.equal(out['0'][1], out['0'][0].sum([0, 2, 3, 4]))
+    torch.testing.assert_close(out['1'][1], out['0'][1], rtol=1e-5, atol=1e-4)
