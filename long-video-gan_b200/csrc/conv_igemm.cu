@@ -51,6 +51,8 @@ using namespace tc;
 constexpr int kBM = 128;
 constexpr int kATile = kBM * 16 * 2;          // one 128 x 16 weight image: 4096 bytes
 constexpr int kThreads = 192;
+constexpr int kEpiWarps = 8;                          // conv_igemm_kernel: two epilogue warps per TMEM lane quadrant (they alternate 32-column blocks)
+constexpr int kIgemmThreads = 64 + 32 * kEpiWarps;
 constexpr int kMaxStages = 6;
 
 struct IgemmParams {
@@ -71,6 +73,7 @@ struct IgemmParams {
     int frame_px;                // thb * wtb: accumulator columns from one frame of the tile to the next
     int ncols;                   // accumulator columns (multiple of 16, <= 512)
     int n0;                      // columns of the first MMA of a tap (the second one takes ncols - n0; 0 = single MMA)
+    int epi_warps;               // epilogue warps that take part (4 or 8)
     int nbuf;                    // accumulator buffers in TMEM: 2 when ncols <= 256 (epilogue of tile i overlaps tile i + 1)
     int tiles_x, tiles_y, tiles_t;
     int64_t total_tiles;         // tiles_x * tiles_y * tiles_t * mt * instances
@@ -159,6 +162,23 @@ int pack_act(const void* x, void* x8, int split, int64_t inst, int c, int cblk, 
 // run of 16*taps elements per output channel; dgrad: one run of 128*taps elements per k): a warp copies a run into shared
 // memory with aligned 4-byte loads (no per-element index arithmetic), then every thread assembles one 16-byte image row
 // from 8 shared-memory reads and consecutive threads write consecutive rows (512 contiguous bytes per warp).
+// Rows of the 128-row weight image (= TMEM lanes of the accumulator). An epilogue warp can only read the 32 lanes of its
+// quadrant, so an m-tile with fewer than 128 output channels spreads them evenly over the four quadrants (`per` channels at
+// the start of each) instead of filling quadrant after quadrant: all epilogue warps share the store work of a 32- or
+// 64-channel layer. Channels >= 4 * per (zero rows) take the remaining rows in order.
+__host__ __device__ __forceinline__ int m_rows_per_quadrant(int channels_left)
+{
+    const int cv = channels_left < kBM ? (channels_left > 0 ? channels_left : 0) : kBM;
+    return cv >= kBM ? 32 : (cv + 3) / 4 > 0 ? (cv + 3) / 4 : 1;
+}
+__host__ __device__ __forceinline__ int m_row_of_channel(int ch, int per)
+{
+    if (per >= 32) return ch;
+    if (ch < 4 * per) return (ch / per) * 32 + ch % per;
+    const int r = ch - 4 * per;
+    return (r / (32 - per)) * 32 + per + r % (32 - per);
+}
+
 template <class TIn, bool SPLIT>
 __global__ void __launch_bounds__(256) conv_pack_w_kernel(const TIn* __restrict__ w, unsigned char* __restrict__ wp, int m_total, int k_total,
                                                            int kpad, int taps, int64_t gstride, int64_t sm, int64_t sk, int flip, int mt, int kc,
@@ -182,6 +202,7 @@ __global__ void __launch_bounds__(256) conv_pack_w_kernel(const TIn* __restrict_
     int* s_off = reinterpret_cast<int*>(sw32 + (size_t)max_runs * pitch);
     unsigned char* dst0 = wp + ((((int64_t)g * mt + mti) * kc + kci) * taps) * (int64_t)(NIMG * kATile);
     const int kvalid = max(0, min(16, k_total - k0));
+    const int per = m_rows_per_quadrant(m_total - mti * kBM);
     for (int r0 = 0; r0 < kBM; r0 += R) {
         const int Rn = min(R, kBM - r0);
         const int m0 = mti * kBM + r0;
@@ -232,7 +253,7 @@ __global__ void __launch_bounds__(256) conv_pack_w_kernel(const TIn* __restrict_
                     v[j] = ES == 2 ? hbits : __half_as_ushort(__float2half_rn(f));
                 }
             }
-            unsigned char* dimg = dst0 + (size_t)tap * (NIMG * kATile) + k8 * 2048 + (r0 + mrow) * 16;
+            unsigned char* dimg = dst0 + (size_t)tap * (NIMG * kATile) + k8 * 2048 + m_row_of_channel(r0 + mrow, per) * 16;
             *reinterpret_cast<uint4*>(dimg) = *reinterpret_cast<const uint4*>(v);
             if constexpr (SPLIT) *reinterpret_cast<uint4*>(dimg + kATile) = *reinterpret_cast<const uint4*>(vlo);
         }
@@ -275,7 +296,7 @@ __device__ __forceinline__ TileCoord decode_tile(const IgemmParams& p, int64_t L
 // Persistent: CTA b works on tiles b, b + gridDim.x, ... (pixel tile fastest, so that concurrently running CTAs share the
 // weight tiles of one (instance, m-tile) in L2). The operand ring runs across tile boundaries; with <= 256 accumulator
 // columns two TMEM buffers alternate, so the epilogue of tile i overlaps the main loop of tile i + 1.
-__global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_constant__ CUtensorMap tmx, const IgemmParams p)
+__global__ void __launch_bounds__(kIgemmThreads, 1) conv_igemm_kernel(const __grid_constant__ CUtensorMap tmx, const IgemmParams p)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t full_bar[kMaxStages], empty_bar[kMaxStages], acc_full[2], acc_empty[2];
@@ -288,7 +309,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.stages; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int b = 0; b < 2; b++) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 4); }
+        for (int b = 0; b < 2; b++) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], (uint32_t)p.epi_warps); }
         fence_barrier_init();
     }
     if (warp == 1) {
@@ -373,10 +394,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
                 umma_commit(&acc_full[buf]);
             }
         }
-    } else {
-        // ---- epilogue warps: TMEM lane quadrant = warp % 4; each warp owns 32 output channels of the tile and a private
-        // 32 x 33 transposition buffer so that a store instruction covers 32 consecutive pixels of one channel
-        const int q = warp % 4;
+    } else if (warp - 2 < p.epi_warps) {
+        // ---- epilogue warps: TMEM lane quadrant = warp % 4 (a warp can only read its own 32 lanes = 32 output channels of the
+        // tile); the two warps of a quadrant alternate the 32-column blocks. Each warp has a private 32 x 33 transposition
+        // buffer so that a store instruction covers 32 consecutive pixels of one channel. With short K loops (1x3x3 / 1x1x1
+        // layers, few channels) this epilogue, not the MMA loop, bounds the kernel (ncu on the 32 -> 64 layer of the low-res
+        // discriminator: tensor pipe 30 % active with ONE latency-bound warp per quadrant storing channel by channel), hence
+        // two warps per quadrant (p.epi_warps = 8) for short K loops and eight independent shared-memory reads in flight
+        // before their stores. Long K loops keep four warps: the second set's transposition buffers would cost a pipeline stage.
+        const int q = warp % 4, half = (warp - 2) / 4, nhalf = p.epi_warps / 4;
         float* sT = reinterpret_cast<float*>(smem + (size_t)p.stages * p.stage_bytes + 512) + (warp - 2) * (32 * 33);
         int i = 0;
         for (int64_t L = blockIdx.x; L < p.total_tiles; L += gridDim.x, i++) {
@@ -385,12 +411,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
             mbar_wait(&acc_full[buf], (uint32_t)((i / p.nbuf) & 1));
             tc_fence_after();
             const uint32_t tmem_d = tmem_base + (uint32_t)buf * 256;
-            const int m_lane = c.mti * kBM + q * 32 + lane;         // this lane's channel while the values are in registers
-            const float b = (p.bias != nullptr && m_lane < p.cout) ? __ldg(p.bias + (int64_t)(c.inst % p.wgroups) * p.cout + m_lane) : 0.f;
-            const int m0 = c.mti * kBM + q * 32;
-            const int rows_ok = min(32, p.cout - m0);               // channels of this warp that exist
+            const int per = m_rows_per_quadrant(p.cout - c.mti * kBM);     // channels per lane quadrant (conv_pack_w_kernel's row order)
+            const int m0 = c.mti * kBM + q * per;
+            const int rows_ok = min(per, p.cout - m0);               // channels of this warp that exist (lanes 0 .. rows_ok - 1)
+            const int m_lane = m0 + lane;                            // this lane's channel while the values are in registers
+            const float b = (p.bias != nullptr && lane < rows_ok) ? __ldg(p.bias + (int64_t)(c.inst % p.wgroups) * p.cout + m_lane) : 0.f;
             const int64_t ch0 = ((int64_t)c.inst * p.cout + m0) * p.y_cs;
-            for (int n0 = 0; n0 < p.ncols; n0 += 32) {
+            for (int n0 = 32 * half; n0 < p.ncols && rows_ok > 0; n0 += 32 * nhalf) {
                 uint32_t acc[32];
                 tmem_ld32(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)n0, acc);
 #pragma unroll
@@ -419,12 +446,25 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
                     off = ch0 + ((int64_t)ot * p.hos + oy / p.ostride) * p.wos + ox / p.ostride;
                 }
                 if (ok) {
+                    const float* src = sT + lane * 33;
                     if (p.out_f32) {
                         float* y = reinterpret_cast<float*>(p.y) + off;
-                        for (int row = 0; row < rows_ok; row++) y[(int64_t)row * p.y_cs] = sT[lane * 33 + row];
+                        for (int row0 = 0; row0 < rows_ok; row0 += 8, y += 8 * p.y_cs) {
+                            float v8[8];
+#pragma unroll
+                            for (int k = 0; k < 8; k++) v8[k] = src[row0 + k];
+#pragma unroll
+                            for (int k = 0; k < 8; k++) if (row0 + k < rows_ok) y[(int64_t)k * p.y_cs] = v8[k];
+                        }
                     } else {
                         __half* y = reinterpret_cast<__half*>(p.y) + off;
-                        for (int row = 0; row < rows_ok; row++) y[(int64_t)row * p.y_cs] = __float2half_rn(sT[lane * 33 + row]);
+                        for (int row0 = 0; row0 < rows_ok; row0 += 8, y += 8 * p.y_cs) {
+                            float v8[8];
+#pragma unroll
+                            for (int k = 0; k < 8; k++) v8[k] = src[row0 + k];
+#pragma unroll
+                            for (int k = 0; k < 8; k++) if (row0 + k < rows_ok) y[(int64_t)k * p.y_cs] = __float2half_rn(v8[k]);
+                        }
                     }
                 }
                 __syncwarp();
@@ -533,8 +573,8 @@ int run_igemm(const void* x, const void* w, void* y, int dtype, int n, int group
     // buffers; measured on the sres discriminator shapes: 0.173 vs 0.200 ms at 256 -> 256 channels 64x64)
     const char* cb_env = getenv("LVG_CONV_COLS");
     const int taps2 = kh * kw;
-    const int epi_bytes = 4 * 32 * 33 * 4 + 512;
-    const int smem_budget = 224 * 1024 - epi_bytes;
+    int epi_bytes = 4 * 32 * 33 * 4 + 512;              // four epilogue warps; eight when that costs neither tile size nor the second stage (below)
+    int smem_budget = 224 * 1024 - epi_bytes;
     p.ostride = ostride;
     p.hos = (p.ho - 1) / ostride + 1; p.wos = (p.wo - 1) / ostride + 1;
     p.ks = (kt == 1) ? (taps2 == 1 ? 4 : (taps2 <= 3 ? 2 : 1)) : 1;
@@ -576,10 +616,20 @@ int run_igemm(const void* x, const void* w, void* y, int dtype, int n, int group
         if (p.th == 1 && p.tt == 1 && col_budget <= p.wtb) { LVG_REQUIRE(false, "convnd: a one-row tile does not fit shared memory"); }
     }
     LVG_REQUIRE(p.th >= 1 && p.ncols <= 512 && p.ncols >= 16, "convnd: tile geometry");
+    // epilogue warps: eight when their extra transposition buffers cost no pipeline stage (every layer gains: the fp16
+    // 539 -> 512 layer 1.29 -> 1.17 ms), or when the K loop is short anyway (epilogue-bound layers: 32 -> 32 1x3x3 of the
+    // low-res discriminator 1.81 -> 1.22 ms); else four (the fp32 512-channel 3x3x3 layer loses a stage: 3.9 -> 6.5 ms with eight)
+    auto stages_for = [&](int budget) { int st = 2; while (st < kMaxStages && (st + 1) * p.stage_bytes <= budget) st++; return st; };
+    const int budget8 = 224 * 1024 - (kEpiWarps * 32 * 33 * 4 + 512);
+    p.epi_warps = 4;
+    if (2 * p.stage_bytes <= budget8 && (stages_for(budget8) == stages_for(smem_budget) || g.kc * kt * taps2 <= 160)) {
+        p.epi_warps = kEpiWarps;
+        epi_bytes = kEpiWarps * 32 * 33 * 4 + 512;
+        smem_budget = budget8;
+    }
     p.nbuf = p.ncols <= 256 ? 2 : 1;
     p.n0 = p.ncols <= 256 ? 0 : round_up(p.ncols / 2, 16);
-    p.stages = 2;
-    while (p.stages < kMaxStages && (p.stages + 1) * p.stage_bytes <= smem_budget) p.stages++;
+    p.stages = stages_for(smem_budget);
     p.y_cs = (int64_t)p.to * p.hos * p.wos;
     p.total_tiles = (int64_t)p.tiles_x * p.tiles_y * p.tiles_t * g.mt * inst;
 
@@ -620,7 +670,7 @@ int run_igemm(const void* x, const void* w, void* y, int dtype, int n, int group
     const char* cta_env = getenv("LVG_CONV_CTAS");          // experiments: fewer persistent CTAs than SMs
     const int max_ctas = cta_env ? atoi(cta_env) : num_sms();
     int64_t ctas = p.total_tiles < max_ctas ? p.total_tiles : max_ctas;
-    conv_igemm_kernel<<<(unsigned)ctas, kThreads, smem, s>>>(tm, p);
+    conv_igemm_kernel<<<(unsigned)ctas, kIgemmThreads, smem, s>>>(tm, p);
     LVG_LAUNCH_CHECK();
     return LVG_OK;
 }
