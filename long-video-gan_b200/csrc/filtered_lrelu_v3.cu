@@ -50,7 +50,7 @@ template <class T>
 int launch(int cfg, FlParams& p, int mode, cudaStream_t s)
 {
     switch (cfg) {
-        case 1: return launch_cfg<T, Geom<2, 12, 2, 12, 56, 24, 6, 4, 4, 4>>(p, mode, s);
+        case 1: return launch_cfg<T, Geom<2, 12, 2, 12, 56, 24, 6, 2, 4, 4>>(p, mode, s);
         case 2: return launch_cfg<T, Geom<4, 24, 2, 12, 56, 24, 2, 2, 4, 4>>(p, mode, s);
         case 3: return launch_cfg<T, Geom<2, 12, 4, 24, 31, 16, 8, 6, 4, 2>>(p, mode, s);
         default: break;

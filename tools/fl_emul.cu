@@ -202,7 +202,7 @@ int main()
 {
     srand(1);
     int bad = 0;
-    typedef Geom<2, 12, 2, 12, 56, 24, 6, 4, 4, 4> U2D2;
+    typedef Geom<2, 12, 2, 12, 56, 24, 6, 2, 4, 4> U2D2;
     typedef Geom<4, 24, 2, 12, 56, 24, 2, 2, 4, 4> U4D2;
     typedef Geom<2, 12, 4, 24, 31, 16, 8, 6, 4, 2> U2D4;
     printf("U2D2 smem %zu B, U4D2 %zu B, U2D4 %zu B\n", U2D2::smem_bytes(SIGN_READ), U4D2::smem_bytes(SIGN_READ), U2D4::smem_bytes(SIGN_READ));
