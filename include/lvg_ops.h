@@ -247,6 +247,24 @@ int64_t lvg_convnd_wgrad_workspace(int dtype, int n, int groups, int cin, int co
 int lvg_convnd_wgrad(const void* x, const void* dy, void* dw, int dtype, int n, int groups, int cin, int cout,
                      int t, int h, int wd, int kt, int kh, int kw, int pad_t, int pad_h, int pad_w, int stride,
                      void* workspace, int64_t workspace_bytes, void* stream);
+/*
+ * Introspection: the tiling lvg_convnd_wgrad launches with, as 32 ints -- split, cpad_a, cpad_b, nt, ntiles, mt, nsplit,
+ * ablk, khc, nseg, ps, rh, stages, a_stage, b_stage, stage_bytes, tail_bytes, smem, seg_w[4], seg_x0[4], pointwise, 0... --
+ * host arithmetic only (no device needed): tests/test_wgrad_emul.py replays the kernel's addressing with it on the CPU.
+ */
+int lvg_convnd_wgrad_plan(int dtype, int n, int groups, int cin, int cout, int t, int h, int wd, int kt, int kh, int kw,
+                          int pad_t, int pad_h, int pad_w, int* out, int out_len);
+/*
+ * Both gradients of one convolution call (what autograd asks of F.conv3d / conv2d_gradfix in a first-order backward pass,
+ * conv2d_gradfix.py:118-141): dx as lvg_convnd_dgrad, dw as lvg_convnd_wgrad, with dy re-tiled ONCE for the two kernels
+ * (the separate entry points re-tile it once each). Argument list = the FORWARD convolution; `workspace`:
+ * lvg_convnd_backward_workspace bytes.
+ */
+int64_t lvg_convnd_backward_workspace(int dtype, int n, int groups, int cin, int cout, int t, int h, int wd,
+                                      int kt, int kh, int kw, int pad_t, int pad_h, int pad_w);
+int lvg_convnd_backward(const void* x, const void* dy, const void* w, void* dx, void* dw, int dtype, int n, int groups,
+                        int cin, int cout, int t, int h, int wd, int kt, int kh, int kw, int pad_t, int pad_h, int pad_w,
+                        int stride, void* workspace, int64_t workspace_bytes, void* stream);
 
 /*
  * Depthwise long FIR along the last axis (cross-correlation, no padding), fp32:

@@ -182,7 +182,7 @@ __host__ __device__ __forceinline__ int m_row_of_channel(int ch, int per)
 template <class TIn, bool SPLIT>
 __global__ void __launch_bounds__(256) conv_pack_w_kernel(const TIn* __restrict__ w, unsigned char* __restrict__ wp, int m_total, int k_total,
                                                            int kpad, int taps, int64_t gstride, int64_t sm, int64_t sk, int flip, int mt, int kc,
-                                                           int rows_per_pass)
+                                                           int rows_per_pass, int rows_per_cta)
 {
     extern __shared__ uint32_t sw32[];               // [runs][pitch] words, then the runs' element offsets
     constexpr int ES = (int)sizeof(TIn);
@@ -203,12 +203,15 @@ __global__ void __launch_bounds__(256) conv_pack_w_kernel(const TIn* __restrict_
     unsigned char* dst0 = wp + ((((int64_t)g * mt + mti) * kc + kci) * taps) * (int64_t)(NIMG * kATile);
     const int kvalid = max(0, min(16, k_total - k0));
     const int per = m_rows_per_quadrant(m_total - mti * kBM);
-    for (int r0 = 0; r0 < kBM; r0 += R) {
-        const int Rn = min(R, kBM - r0);
+    // blockIdx.y = chunk of rows_per_cta image rows (small layers have only a handful of (group, m-tile, k-step) blocks: the
+    // row chunks spread their latency-bound staging over more SMs)
+    const int row_end = min(kBM, ((int)blockIdx.y + 1) * rows_per_cta);
+    for (int r0 = (int)blockIdx.y * rows_per_cta; r0 < row_end; r0 += R) {
+        const int Rn = min(R, row_end - r0);
         const int m0 = mti * kBM + r0;
         const int mvalid = max(0, min(Rn, m_total - m0));
-        const int nruns = mrows ? mvalid : kvalid;
         const int len = mrows ? kvalid * taps : mvalid * taps;             // valid elements of a run
+        const int nruns = len > 0 ? (mrows ? mvalid : kvalid) : 0;
         for (int run = warp; run < nruns; run += 8) {
             const int64_t e0 = mrows ? (int64_t)(m0 + run) * sm + (int64_t)k0 * sk : (int64_t)(k0 + run) * sk + (int64_t)m0 * sm;
             const unsigned char* gb = reinterpret_cast<const unsigned char*>(wg + e0);
@@ -216,13 +219,18 @@ __global__ void __launch_bounds__(256) conv_pack_w_kernel(const TIn* __restrict_
             const uint32_t* gw = reinterpret_cast<const uint32_t*>(gb - a);
             const int nbytes = len * ES + a;
             const int nwords = (nbytes + 3) / 4;
-            for (int wi = lane; wi < nwords; wi += 32) {
-                uint32_t v;
-                if (wi == 0 && a != 0) v = (uint32_t)__ldg(reinterpret_cast<const unsigned short*>(gb)) << 16;                       // do not touch bytes before the run
-                else if (wi == nwords - 1 && (nbytes & 3) != 0) v = (uint32_t)__ldg(reinterpret_cast<const unsigned short*>(gw + wi));   // ... or after it
-                else v = __ldg(gw + wi);
-                sw32[run * pitch + wi] = v;
+            // whole words strictly inside the run: four independent loads in flight per lane
+            const int w_lo = a != 0 ? 1 : 0, w_hi = (nbytes & 3) != 0 ? nwords - 1 : nwords;
+            int wi = w_lo + lane;
+            for (; wi + 96 < w_hi; wi += 128) {
+                const uint32_t v0 = __ldg(gw + wi), v1 = __ldg(gw + wi + 32), v2 = __ldg(gw + wi + 64), v3 = __ldg(gw + wi + 96);
+                uint32_t* d = sw32 + run * pitch + wi;
+                d[0] = v0; d[32] = v1; d[64] = v2; d[96] = v3;
             }
+            for (; wi < w_hi; wi += 32) sw32[run * pitch + wi] = __ldg(gw + wi);
+            if (lane == 0 && a != 0) sw32[run * pitch] = (uint32_t)__ldg(reinterpret_cast<const unsigned short*>(gb)) << 16;              // do not touch bytes before the run
+            if (lane == 1 && w_hi < nwords && !(a != 0 && nwords == 1))
+                sw32[run * pitch + nwords - 1] = (uint32_t)__ldg(reinterpret_cast<const unsigned short*>(gw + nwords - 1));              // ... or after it
             if (lane == 0) s_off[run] = a / ES;
         }
         __syncthreads();
@@ -541,22 +549,24 @@ Geometry geometry(int split, int64_t inst, int groups, int ck, int cm, int64_t t
 // a strided convolution); `ostride` > 1: only every ostride-th output row / column is stored (strided forward convolution).
 int run_igemm(const void* x, const void* w, void* y, int dtype, int n, int groups, int ck, int cm, int t, int h, int wd, int kt, int kh,
               int kw, int pad_t, int pad_h, int pad_w, int64_t w_gs, int64_t w_sm, int64_t w_sk, int flip, const float* bias, int act,
-              float alpha, float gain, float clamp, int xin_h, int xin_w, int dil, int ostride, void* workspace, int64_t workspace_bytes,
-              cudaStream_t s)
+              float alpha, float gain, float clamp, int xin_h, int xin_w, int dil, int ostride, const unsigned char* x8_pre, void* workspace,
+              int64_t workspace_bytes, cudaStream_t s)
 {
+    // `x8_pre` != nullptr: x is already re-tiled there (lvg_convnd_backward shares dy8 with the weight gradient); the workspace
+    // then only holds the packed weights
     const int split = dtype == LVG_F32 ? 1 : 0;
     const int taps = kt * kh * kw;
     const int64_t inst = (int64_t)n * groups;
     const int64_t thw = (int64_t)t * h * wd;
     const Geometry g = geometry(split, inst, groups, ck, cm, thw, taps);
-    LVG_REQUIRE(workspace && workspace_bytes >= g.act_bytes + g.w_bytes + 256, "convnd: workspace too small");
+    LVG_REQUIRE(workspace && workspace_bytes >= (x8_pre ? 0 : g.act_bytes) + g.w_bytes + 256, "convnd: workspace too small");
     LVG_REQUIRE(aligned16(workspace), "convnd: workspace must be 16-byte aligned");
     LVG_REQUIRE(inst * g.nblk < (1ll << 31), "convnd: too many channel blocks for a tensor map");
     EncodeTiledFn enc = encode_fn();
     LVG_REQUIRE(enc != nullptr, "convnd: cuTensorMapEncodeTiled is not available from this driver");
 
     unsigned char* wp = reinterpret_cast<unsigned char*>(workspace);
-    unsigned char* x8 = wp + ((g.w_bytes + 127) / 128) * 128;
+    unsigned char* x8 = x8_pre ? const_cast<unsigned char*>(x8_pre) : wp + ((g.w_bytes + 127) / 128) * 128;
 
     IgemmParams p;
     memset(&p, 0, sizeof(p));
@@ -635,7 +645,7 @@ int run_igemm(const void* x, const void* w, void* y, int dtype, int n, int group
 
     // re-tile the operands
     {
-        const int rc = pack_act(x, x8, split, inst, ck, g.cblk, t, xin_h, xin_w, h, wd, dil, s);
+        const int rc = x8_pre ? LVG_OK : pack_act(x, x8, split, inst, ck, g.cblk, t, xin_h, xin_w, h, wd, dil, s);
         if (rc) return rc;
         const int64_t wblocks = (int64_t)groups * g.mt * g.kc;
         LVG_REQUIRE(wblocks < (1ll << 31), "convnd: too many weight tiles");
@@ -649,12 +659,21 @@ int run_igemm(const void* x, const void* w, void* y, int dtype, int n, int group
         const int pitch = ((run_el * es + 2 + 3) / 4) | 1;
         const int max_runs = mrows ? rpp : 16;
         const size_t wsm = ((size_t)max_runs * pitch + max_runs + 4) * 4;
+        // row chunks per 128-row image: enough CTAs for two per SM (1, 2, 4 or 8 chunks of 128 / chunks rows)
+        int chunks = 1;
+        {
+            const char* e = getenv("LVG_PACKW_CHUNKS");       // experiments
+            if (e && atoi(e) >= 1) chunks = atoi(e) >= 8 ? 8 : (atoi(e) >= 4 ? 4 : (atoi(e) >= 2 ? 2 : 1));
+            else while (chunks < 8 && wblocks * chunks < 2 * (int64_t)num_sms()) chunks *= 2;
+        }
+        const int rows_per_cta = kBM / chunks;
+        const dim3 wgrid((unsigned)wblocks, (unsigned)chunks);
         if (split) {
             LVG_CUDA(cudaFuncSetAttribute(conv_pack_w_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsm));
-            conv_pack_w_kernel<float, true><<<(unsigned)wblocks, 256, wsm, s>>>((const float*)w, wp, cm, ck, g.cpad, taps, w_gs, w_sm, w_sk, flip, g.mt, g.kc, rpp);
+            conv_pack_w_kernel<float, true><<<wgrid, 256, wsm, s>>>((const float*)w, wp, cm, ck, g.cpad, taps, w_gs, w_sm, w_sk, flip, g.mt, g.kc, rpp, rows_per_cta);
         } else {
             LVG_CUDA(cudaFuncSetAttribute(conv_pack_w_kernel<__half, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsm));
-            conv_pack_w_kernel<__half, false><<<(unsigned)wblocks, 256, wsm, s>>>((const __half*)w, wp, cm, ck, g.cpad, taps, w_gs, w_sm, w_sk, flip, g.mt, g.kc, rpp);
+            conv_pack_w_kernel<__half, false><<<wgrid, 256, wsm, s>>>((const __half*)w, wp, cm, ck, g.cpad, taps, w_gs, w_sm, w_sk, flip, g.mt, g.kc, rpp, rows_per_cta);
         }
         LVG_LAUNCH_CHECK();
     }
@@ -714,7 +733,8 @@ extern "C" int lvg_convnd_fprop(const void* x, const void* w, void* y, int dtype
     }
     const int taps = kt * kh * kw;
     return run_igemm(x, w, y, dtype, n, groups, cin, cout, t, h, wd, kt, kh, kw, pad_t, pad_h, pad_w, (int64_t)cout * cin * taps,
-                     (int64_t)cin * taps, taps, 0, bias, act, alpha, gain, clamp, h, wd, 1, stride, workspace, workspace_bytes, (cudaStream_t)stream);
+                     (int64_t)cin * taps, taps, 0, bias, act, alpha, gain, clamp, h, wd, 1, stride, nullptr, workspace, workspace_bytes,
+                     (cudaStream_t)stream);
 }
 
 extern "C" int lvg_convnd_dgrad(const void* dy, const void* w, void* dx, int dtype, int n, int groups, int cin, int cout, int t, int h, int wd,
@@ -735,7 +755,7 @@ extern "C" int lvg_convnd_dgrad(const void* dy, const void* w, void* dx, int dty
     const int to = t + 2 * pad_t - kt + 1, ho = h + 2 * pad_h - kh + 1, wo = wd + 2 * pad_w - kw + 1;
     const int hos = (ho - 1) / stride + 1, wos = (wo - 1) / stride + 1;
     return run_igemm(dy, w, dx, dtype, n, groups, cout, cin, to, ho, wo, kt, kh, kw, kt - 1 - pad_t, kh - 1 - pad_h, kw - 1 - pad_w,
-                     (int64_t)cout * cin * taps, taps, (int64_t)cin * taps, 1, nullptr, 0, 0.f, 1.f, -1.f, hos, wos, stride, 1, workspace,
+                     (int64_t)cout * cin * taps, taps, (int64_t)cin * taps, 1, nullptr, 0, 0.f, 1.f, -1.f, hos, wos, stride, 1, nullptr, workspace,
                      workspace_bytes, (cudaStream_t)stream);
 }
 
@@ -768,10 +788,13 @@ struct WgradV2Params {
     int nblk_a, nblk_b;          // channel blocks per instance in dy8 / x8 (incl. the lo half in split mode)
     int lo_a, lo_b;              // block offset of the lo half
     int nseg, seg_w[4], seg_x0[4], ps[4];
-    int rh;                      // rows per stage
+    int rh;                      // dy rows per stage
+    int khc;                     // tap rows (ky) per CTA: 1, or kh (folded: one dy tile and one x tile of rh + kh - 1 rows serve all ky)
+    int ablk;                    // channel blocks of one dy image in a stage (16, or fewer for cout < 128: the rest of the 128 MMA rows is never stored)
     int nsplit;
     int a_bytes, b_bytes, stage_bytes, stages;      // per stage: one A (B) operand image; a stage holds split+1 of each
     int64_t split_stride;        // elements between fp32 partials
+    int tail_bytes;              // shared memory behind the stage ring that the MMAs may read (kx-shifted last rows; the 128 - 8 * ablk rows without data)
 };
 
 struct WgradMaps { CUtensorMap a[4]; CUtensorMap b; };     // dy8 clipped to each column segment; x8
@@ -786,7 +809,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_v2_kernel(const __grid
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
     int bx = blockIdx.x;
     const int sp = bx % p.nsplit; bx /= p.nsplit;
-    const int ky = bx % p.kh; bx /= p.kh;
+    int ky0 = 0;
+    if (p.khc == 1) { ky0 = bx % p.kh; bx /= p.kh; }
     const int kt = bx % p.kt;
     const int nti = bx / p.kt;
     const int mti = blockIdx.y, g = blockIdx.z;
@@ -807,7 +831,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_v2_kernel(const __grid
     // zero the slack behind the stage buffers (the kx-shifted reads of the last block run 32 bytes past its end; the dy
     // values they meet are zero, and zero * garbage must not become NaN)
     // (uninitialised shared memory may hold NaN patterns: clear all of it once)
-    for (int i = threadIdx.x; i < (p.stages * p.stage_bytes + 256) / 16; i += kThreads) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = threadIdx.x; i < (p.stages * p.stage_bytes + p.tail_bytes) / 16; i += kThreads) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_slot)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -834,7 +858,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_v2_kernel(const __grid
                 const int oy0 = rb * p.rh;
                 for (int o = 0; o < nop; o++) {
                     tma_load_4d(st + (size_t)o * p.a_bytes, &maps.a[seg], 0, oy0, t, inst * p.nblk_a + o * p.lo_a + mti * 16, &full_bar[slot]);
-                    tma_load_4d(st + (size_t)nop * p.a_bytes + (size_t)o * p.b_bytes, &maps.b, 2 * (p.seg_x0[seg] - p.pad_w), oy0 + ky - p.pad_h,
+                    tma_load_4d(st + (size_t)nop * p.a_bytes + (size_t)o * p.b_bytes, &maps.b, 2 * (p.seg_x0[seg] - p.pad_w), oy0 + ky0 - p.pad_h,
                                 t + kt - p.pad_t, inst * p.nblk_b + o * p.lo_b + nti * (NT / 8), &full_bar[slot]);
                 }
             }
@@ -851,7 +875,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_v2_kernel(const __grid
                 const int rb = s % rblocks;
                 const int rows = min(p.rh, p.ho - rb * p.rh);
                 const int ksteps = (rows * p.ps[seg] + 15) / 16;                 // (a trailing half step reads the zero-filled next row)
-                const uint32_t blk = (uint32_t)(p.rh * p.ps[seg] * 16);          // bytes of one channel block of the stage tile
+                const uint32_t blk_a = (uint32_t)(p.rh * p.ps[seg] * 16);                    // bytes of one channel block of the dy tile
+                const uint32_t blk_b = (uint32_t)((p.rh + p.khc - 1) * p.ps[seg] * 16);      // ... of the x tile (kh - 1 halo rows when folded)
+                const uint32_t ky_step = (uint32_t)(p.ps[seg] * 16);                          // one tap row down = one tile row further
                 mbar_wait(&full_bar[slot], (uint32_t)((it / p.stages) & 1));
                 tc_fence_after();
                 const uint32_t a0 = smem_u32(smem + (size_t)slot * p.stage_bytes);
@@ -860,10 +886,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_v2_kernel(const __grid
                     const uint32_t at = a0 + (term == 1 ? (uint32_t)p.a_bytes : 0u);     // hi*hi, lo*hi, hi*lo
                     const uint32_t bt = b0 + (term == 2 ? (uint32_t)p.b_bytes : 0u);
                     for (int k = 0; k < ksteps; k++) {
-                        const uint64_t adesc = make_desc(at + (uint32_t)k * 256, 128, blk);
-                        for (int kx = 0; kx < p.kw; kx++) {
-                            const uint64_t bdesc = make_desc(bt + (uint32_t)k * 256 + (uint32_t)kx * 16, 128, blk);
-                            umma_f16(tmem_d + (uint32_t)(kx * NT), adesc, bdesc, idesc, (first && k == 0) ? 0u : 1u);
+                        const uint64_t adesc = make_desc(at + (uint32_t)k * 256, 128, blk_a);
+                        for (int kyi = 0; kyi < p.khc; kyi++) {
+                            for (int kx = 0; kx < p.kw; kx++) {
+                                const uint64_t bdesc = make_desc(bt + (uint32_t)k * 256 + (uint32_t)kyi * ky_step + (uint32_t)kx * 16, 128, blk_b);
+                                umma_f16(tmem_d + (uint32_t)((kyi * p.kw + kx) * NT), adesc, bdesc, idesc, (first && k == 0) ? 0u : 1u);
+                            }
                         }
                     }
                     first = false;
@@ -884,15 +912,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_v2_kernel(const __grid
     {
         const int taps = p.kt * p.kh * p.kw;
         const int ci0 = nti * NT, co0 = mti * kBM;
-        const int tap0 = (kt * p.kh + ky) * p.kw;
         const bool any = s1 > s0;
-        for (int c0 = 0; c0 < NT; c0 += 32) {
+        for (int kc0 = 0; kc0 < p.khc * ((NT + 31) / 32); kc0++) {
+            const int kyi = kc0 / ((NT + 31) / 32), c0 = (kc0 - kyi * ((NT + 31) / 32)) * 32;      // tap row of this CTA, first of 32 input channels
+            const int tap0 = (kt * p.kh + ky0 + kyi) * p.kw;
             if (warp >= 2) {
                 const int q = warp % 4;
                 const int r = q * 32 + lane;
                 for (int kx = 0; kx < p.kw; kx++) {
                     uint32_t acc[32];
-                    tmem_ld32(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(kx * NT + c0), acc);
+                    tmem_ld32(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)((kyi * p.kw + kx) * NT + c0), acc);
 #pragma unroll
                     for (int j = 0; j < 32; j++) tile[r * row_pitch + j * p.kw + kx] = any ? __uint_as_float(acc[j]) : 0.f;
                 }
@@ -939,19 +968,37 @@ __global__ void __launch_bounds__(256) conv_wgrad_reduce_kernel(const float* __r
 
 struct WgradPlan {
     int split, cpad_a, cpad_b, nt, ntiles, mt, nsplit;
+    int ablk, khc;
     int nseg, seg_w[4], seg_x0[4], ps, rh, stages;
-    int a_stage, b_stage, stage_bytes;
+    int a_stage, b_stage, stage_bytes, tail_bytes;
     size_t smem;
     int64_t a_bytes, b_bytes, part_bytes, dw_elems;
 };
+
+inline int env_flag(const char* name, int dflt)
+{
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+
+// channel padding of the dy8 operand of the weight gradient. cout < 128: only the channel blocks that exist (the same
+// tensor the input gradient reads, so one re-tiling pass serves both; the remaining rows of the 128-row MMA read whatever
+// follows in shared memory and are never stored -- rows of D depend on the same rows of A only). Otherwise whole m-tiles.
+inline int wgrad_cpad_a(int cout) { return (cout < kBM && env_flag("LVG_WGRAD_COMPACT", 1)) ? round_up(cout, 16) : round_up(cout, kBM); }
 
 WgradPlan wgrad_plan(int dtype, int n, int groups, int cin, int cout, int t, int h, int wd, int to, int ho, int wo, int kt, int kh, int kw)
 {
     WgradPlan q;
     q.split = dtype == LVG_F32;
-    q.cpad_a = round_up(cout, 128);          // whole m-tiles of 16 blocks
+    q.cpad_a = wgrad_cpad_a(cout);
+    q.ablk = q.cpad_a < kBM ? q.cpad_a / 8 : 16;
     q.cpad_b = round_up(cin, 16);
-    int nt_cap = (512 / kw) / 16 * 16;
+    // Few input channels (<= 64): ONE CTA takes all kh tap rows -- the x tile carries kh - 1 halo rows and a tap row is a
+    // start-address shift of one tile row, like kx is a shift of one pixel -- so dy and x are fetched once per (kt, n-tile)
+    // instead of once per (kt, ky): these layers (32-64 channels at 64x64 ... 36x64) are bound by the L2 -> SM operand
+    // traffic, not by the tensor pipe. The kh * kw accumulators of NT columns each must fit the 512 TMEM columns.
+    q.khc = (kh > 1 && cin <= 64 && env_flag("LVG_WGRAD_FOLD", 1)) ? kh : 1;
+    int nt_cap = (512 / (q.khc * kw)) / 16 * 16;
     if (nt_cap > 256) nt_cap = 256;
     if (q.split && nt_cap > 128) nt_cap = 128;
     // column segments (a TMA box row is at most 128 pixels incl. the kw - 1 halo) and the common tile pitch
@@ -960,45 +1007,51 @@ WgradPlan wgrad_plan(int dtype, int n, int groups, int cin, int cout, int t, int
     const int w0 = (wo + q.nseg - 1) / q.nseg;
     for (int j = 0; j < 4; j++) { q.seg_x0[j] = j * w0; q.seg_w[j] = j < q.nseg ? (wo - j * w0 < w0 ? wo - j * w0 : w0) : 0; }
     q.ps = round_up(w0 + kw - 1, 8);                           // rows x pitch must be a multiple of 16 pixels (one MMA K step)
+    const int nop = q.split ? 2 : 1;
+    // bytes of a stage with `rows` dy rows and an n-tile of `nt` channels
+    auto stage_of = [&](int rows, int nt) { return nop * (q.ablk * rows + (nt / 8) * (rows + q.khc - 1)) * q.ps * 16; };
     {   // a pitch of 8 mod 16 needs row pairs: take it only when two stages of two rows fit with a useful n-tile
-        const int nop0 = q.split ? 2 : 1;
-        if (q.ps % 16 != 0 && 2 * nop0 * (16 + 64 / 8) * 2 * q.ps * 16 > 200 * 1024) q.ps = round_up(q.ps, 16);
+        if (q.ps % 16 != 0 && 2 * stage_of(2, 64 < nt_cap ? 64 : nt_cap) > 200 * 1024) q.ps = round_up(q.ps, 16);
     }
     {   // the smallest stage (1 or 2 rows) must leave room for two stages
         const int min_rows = q.ps % 16 != 0 ? 2 : 1;
-        const int nop0 = q.split ? 2 : 1;
-        while (nt_cap > 16 && 2 * nop0 * (16 + nt_cap / 8) * min_rows * q.ps * 16 > 200 * 1024) nt_cap -= 16;
+        while (nt_cap > 16 && 2 * stage_of(min_rows, nt_cap) > 200 * 1024) nt_cap -= 16;
     }
     q.ntiles = (q.cpad_b + nt_cap - 1) / nt_cap;
     q.nt = round_up((q.cpad_b + q.ntiles - 1) / q.ntiles, 16);
     q.cpad_b = q.nt * q.ntiles;
-    q.mt = q.cpad_a / 128;
+    q.mt = (q.cpad_a + kBM - 1) / kBM;
     const int64_t inst = (int64_t)n * groups;
-    q.a_bytes = inst * (q.split ? 2 : 1) * (q.cpad_a / 8) * (int64_t)to * ho * wo * 16;
-    q.b_bytes = inst * (q.split ? 2 : 1) * (q.cpad_b / 8) * (int64_t)t * h * wd * 16;
+    q.a_bytes = inst * nop * (q.cpad_a / 8) * (int64_t)to * ho * wo * 16;
+    q.b_bytes = inst * nop * (q.cpad_b / 8) * (int64_t)t * h * wd * 16;
     q.dw_elems = (int64_t)groups * cout * cin * kt * kh * kw;
     // rows per stage: about 80 KB of operands per stage
-    const int nop = q.split ? 2 : 1;
-    const int per_row = nop * (16 + q.nt / 8) * q.ps * 16;
-    q.rh = (80 * 1024) / per_row;
-    if (q.rh < 1) q.rh = 1;
-    if (q.rh > ho) q.rh = ho;
-    if (q.rh > 254) q.rh = 254;
+    q.rh = 1;
+    while (q.rh < ho && q.rh < 255 - q.khc && stage_of(q.rh + 1, q.nt) <= 80 * 1024) q.rh++;
     if (q.ps % 16 != 0) q.rh = q.rh >= 2 ? q.rh / 2 * 2 : 2;   // even row count (rows past the image are zero-filled)
-    q.a_stage = 16 * q.rh * q.ps * 16;
-    q.b_stage = (q.nt / 8) * q.rh * q.ps * 16;
-    q.stage_bytes = round_up(nop * (q.a_stage + q.b_stage), 128);
+    // behind the ring: the kx-shifted reads of the last block (32 bytes) and, with fewer than 16 dy blocks, the rows of the
+    // 128-row MMA beyond them (read from the lo image's start: (nop - 1) * a_stage + 16 blocks). Two stages + tail must fit.
+    for (;;) {
+        q.a_stage = q.ablk * q.rh * q.ps * 16;
+        q.b_stage = (q.nt / 8) * (q.rh + q.khc - 1) * q.ps * 16;
+        q.stage_bytes = round_up(nop * (q.a_stage + q.b_stage), 128);
+        const int over = (nop - 1) * q.a_stage + 16 * q.rh * q.ps * 16 - q.stage_bytes;
+        q.tail_bytes = round_up(256 + (over > 0 ? over : 0), 128);
+        const int step = q.ps % 16 != 0 ? 2 : 1;
+        if (2 * q.stage_bytes + q.tail_bytes <= 220 * 1024 || q.rh <= step) break;
+        q.rh -= step;
+    }
     q.stages = 2;
-    while (q.stages < kMaxStages && (q.stages + 1) * q.stage_bytes <= 220 * 1024) q.stages++;
+    while (q.stages < kMaxStages && (q.stages + 1) * q.stage_bytes + q.tail_bytes <= 220 * 1024) q.stages++;
     const size_t tile_bytes = (size_t)kBM * (32 * kw + 1) * 4;
-    q.smem = (size_t)q.stages * q.stage_bytes + 256;
+    q.smem = (size_t)q.stages * q.stage_bytes + q.tail_bytes;
     if (tile_bytes > q.smem) q.smem = tile_bytes;
     q.smem += 128;
     // Split the pixel range over `nsplit` CTAs per output tile. One CTA per SM is resident, so the kernel runs in waves of
     // num_sms CTAs: choose the split that minimises waves x (stages per CTA + a fixed per-CTA cost of ~4 stages: clearing
     // shared memory, the TMEM -> global epilogue) -- e.g. 3 output tiles: 49 splits = 147 CTAs = one wave of 470 stages
     // instead of 64 splits = 192 CTAs = two waves of 360. Partial sums are capped at 256 MB.
-    const int64_t ctas = (int64_t)q.ntiles * kh * kt * q.mt * groups;
+    const int64_t ctas = (int64_t)q.ntiles * (kh / q.khc) * kt * q.mt * groups;
     const int64_t stages = (int64_t)n * to * q.nseg * ((ho + q.rh - 1) / q.rh);
     const int sms = 148;
     int64_t cap = 160;
@@ -1008,8 +1061,8 @@ WgradPlan wgrad_plan(int dtype, int n, int groups, int cin, int cout, int t, int
     double best = 1e300;
     for (int64_t k = 1; k <= cap; k++) {
         const int64_t waves = (ctas * k + sms - 1) / sms;
-        const double t = (double)waves * ((double)((stages + k - 1) / k) + 4.0);
-        if (t < best * 0.999) { best = t; ns = k; }
+        const double tm = (double)waves * ((double)((stages + k - 1) / k) + 4.0 * q.khc);
+        if (tm < best * 0.999) { best = tm; ns = k; }
     }
     {
         const char* e = getenv("LVG_WGRAD_NSPLIT");       // experiments
@@ -1020,48 +1073,25 @@ WgradPlan wgrad_plan(int dtype, int n, int groups, int cin, int cout, int t, int
     return q;
 }
 
-}  // namespace
-}  // namespace lvg
-
-extern "C" int64_t lvg_convnd_wgrad_workspace(int dtype, int n, int groups, int cin, int cout, int t, int h, int wd, int kt, int kh, int kw,
-                                              int pad_t, int pad_h, int pad_w)
+// the weight-gradient launch; `dy8_pre` != nullptr: dy is already re-tiled (the tensor the input gradient of the same call read)
+int run_wgrad(const void* x, const void* dy, void* dw, int dtype, int n, int groups, int cin, int cout, int t, int h, int wd, int kt, int kh,
+              int kw, int pad_t, int pad_h, int pad_w, int stride, const unsigned char* dy8_pre, void* workspace, int64_t workspace_bytes,
+              cudaStream_t s)
 {
-    if (!nd_supported(dtype, kt, kh, kw) || n < 1 || groups < 1 || kw > 3) return -1;
     const int to = t + 2 * pad_t - kt + 1, ho = h + 2 * pad_h - kh + 1, wo = wd + 2 * pad_w - kw + 1;
-    if (to < 1 || ho < 1 || wo < 1 || wo > 4 * (128 - kw + 1)) return -1;
-    if (pw_supported(dtype, groups, cin, cout, kt, kh, kw, pad_t, pad_h, pad_w, 1, (int64_t)t * h * wd, 1)) return pw_wgrad_workspace(cin, cout);
     const WgradPlan q = wgrad_plan(dtype, n, groups, cin, cout, t, h, wd, to, ho, wo, kt, kh, kw);
-    return q.a_bytes + q.b_bytes + q.part_bytes + 1024;
-}
-
-extern "C" int lvg_convnd_wgrad(const void* x, const void* dy, void* dw, int dtype, int n, int groups, int cin, int cout, int t, int h, int wd,
-                                int kt, int kh, int kw, int pad_t, int pad_h, int pad_w, int stride, void* workspace, int64_t workspace_bytes,
-                                void* stream)
-{
-    LVG_REQUIRE(x && dy && dw, "convnd_wgrad: x, dy, dw must not be NULL");
-    if (pw_supported(dtype, groups, cin, cout, kt, kh, kw, pad_t, pad_h, pad_w, stride, (int64_t)t * h * wd, 1)) {
-        LVG_REQUIRE(workspace, "convnd_wgrad: workspace must not be NULL");
-        return pw_wgrad((const float*)x, (const float*)dy, (float*)dw, n, cin, cout, (int64_t)t * h * wd, workspace, workspace_bytes, (cudaStream_t)stream);
-    }
-    const int to = t + 2 * pad_t - kt + 1, ho = h + 2 * pad_h - kh + 1, wo = wd + 2 * pad_w - kw + 1;
-    if (!nd_supported(dtype, kt, kh, kw) || n < 1 || kw > 3 || pad_t < 0 || pad_h < 0 || pad_w < 0 || to < 1 || ho < 1 || wo < 1 ||
-        wo > 4 * (128 - kw + 1) || stride < 1 || stride > 4) {
-        set_error("convnd_wgrad: outside the tensor-core kernel's envelope");
-        return LVG_UNSUPPORTED;
-    }
-    cudaStream_t s = (cudaStream_t)stream;
-    const WgradPlan q = wgrad_plan(dtype, n, groups, cin, cout, t, h, wd, to, ho, wo, kt, kh, kw);
-    LVG_REQUIRE(workspace && workspace_bytes >= q.a_bytes + q.b_bytes + q.part_bytes + 768, "convnd_wgrad: workspace too small");
+    const int64_t a_room = dy8_pre ? 0 : ((q.a_bytes + 255) / 256) * 256;
+    LVG_REQUIRE(workspace && workspace_bytes >= a_room + q.b_bytes + q.part_bytes + 768, "convnd_wgrad: workspace too small");
     LVG_REQUIRE(aligned16(workspace), "convnd_wgrad: workspace must be 16-byte aligned");
     LVG_REQUIRE(groups <= 65535 && q.mt <= 65535, "convnd_wgrad: too many groups / channel tiles");
     const int64_t inst = (int64_t)n * groups;
-    unsigned char* dy8 = reinterpret_cast<unsigned char*>(workspace);
-    unsigned char* x8 = dy8 + ((q.a_bytes + 255) / 256) * 256;
+    unsigned char* x8 = reinterpret_cast<unsigned char*>(workspace) + a_room;
+    unsigned char* dy8 = dy8_pre ? const_cast<unsigned char*>(dy8_pre) : reinterpret_cast<unsigned char*>(workspace);
     float* part = reinterpret_cast<float*>(x8 + ((q.b_bytes + 255) / 256) * 256);
     const int64_t thw_a = (int64_t)to * ho * wo, thw_b = (int64_t)t * h * wd;
     {
         // dy of a strided convolution is spread over every stride-th pixel of the stride-1 output grid (zeros between)
-        int rc = pack_act(dy, dy8, q.split, inst, cout, q.cpad_a / 8, to, (ho - 1) / stride + 1, (wo - 1) / stride + 1, ho, wo, stride, s);
+        int rc = dy8_pre ? LVG_OK : pack_act(dy, dy8, q.split, inst, cout, q.cpad_a / 8, to, (ho - 1) / stride + 1, (wo - 1) / stride + 1, ho, wo, stride, s);
         if (rc) return rc;
         rc = pack_act(x, x8, q.split, inst, cin, q.cpad_b / 8, t, h, wd, h, wd, 1, s);
         if (rc) return rc;
@@ -1076,29 +1106,28 @@ extern "C" int lvg_convnd_wgrad(const void* x, const void* dy, void* dw, int dty
     p.lo_a = q.cpad_a / 8; p.lo_b = q.cpad_b / 8;
     p.nseg = q.nseg;
     for (int j = 0; j < 4; j++) { p.seg_w[j] = q.seg_w[j]; p.seg_x0[j] = q.seg_x0[j]; p.ps[j] = q.ps; }
-    const int nop = q.split ? 2 : 1;
-    (void)nop;
-    p.rh = q.rh;
-    p.a_bytes = q.a_stage; p.b_bytes = q.b_stage; p.stage_bytes = q.stage_bytes; p.stages = q.stages;
+    p.rh = q.rh; p.khc = q.khc; p.ablk = q.ablk;
+    p.a_bytes = q.a_stage; p.b_bytes = q.b_stage; p.stage_bytes = q.stage_bytes; p.stages = q.stages; p.tail_bytes = q.tail_bytes;
     const size_t smem = q.smem;
     LVG_REQUIRE(smem <= 227 * 1024, "convnd_wgrad: stage does not fit shared memory (%zu bytes)", smem);
+    LVG_REQUIRE(q.khc * kw * q.nt <= 512, "convnd_wgrad: accumulators exceed tensor memory");
     p.nsplit = q.nsplit;
     p.split_stride = q.dw_elems;
     p.dw = q.nsplit > 1 ? (void*)part : dw;
-    // NOTE the per-segment tile pitch: a stage tile of segment j is [block][rh][ps[j]][16 B] -- the box width IS the pitch
+    // NOTE the per-segment tile pitch: a stage tile of segment j is [block][rows][ps[j]][16 B] -- the box width IS the pitch
     WgradMaps maps;
     memset(&maps, 0, sizeof(maps));
     for (int j = 0; j < p.nseg; j++) {
         const int rc = encode_map(&maps.a[j], dy8 + (size_t)p.seg_x0[j] * 16, p.seg_w[j], ho, to, inst * p.nblk_a, wo, (int64_t)ho * wo, thw_a,
-                                  p.ps[j], p.rh, 1, 16);
+                                  p.ps[j], p.rh, 1, q.ablk);
         if (rc) return rc;
     }
     {
-        const int rc = encode_map(&maps.b, x8, wd, h, t, inst * p.nblk_b, wd, (int64_t)h * wd, thw_b, p.ps[0], p.rh, 1, q.nt / 8);
+        const int rc = encode_map(&maps.b, x8, wd, h, t, inst * p.nblk_b, wd, (int64_t)h * wd, thw_b, p.ps[0], p.rh + q.khc - 1, 1, q.nt / 8);
         if (rc) return rc;
     }
     LVG_CUDA(cudaFuncSetAttribute(conv_wgrad_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid((unsigned)(q.ntiles * kt * kh * q.nsplit), (unsigned)q.mt, (unsigned)groups);
+    dim3 grid((unsigned)(q.ntiles * kt * (kh / q.khc) * q.nsplit), (unsigned)q.mt, (unsigned)groups);
     conv_wgrad_v2_kernel<<<grid, kThreads, smem, s>>>(maps, p);
     LVG_LAUNCH_CHECK();
     if (q.nsplit > 1) {
@@ -1110,4 +1139,125 @@ extern "C" int lvg_convnd_wgrad(const void* x, const void* dy, void* dw, int dty
         LVG_LAUNCH_CHECK();
     }
     return LVG_OK;
+}
+
+bool wgrad_in_envelope(int dtype, int n, int groups, int t, int h, int wd, int kt, int kh, int kw, int pad_t, int pad_h, int pad_w, int stride)
+{
+    const int to = t + 2 * pad_t - kt + 1, ho = h + 2 * pad_h - kh + 1, wo = wd + 2 * pad_w - kw + 1;
+    return nd_supported(dtype, kt, kh, kw) && n >= 1 && groups >= 1 && kw <= 3 && pad_t >= 0 && pad_h >= 0 && pad_w >= 0 && to >= 1 && ho >= 1 &&
+           wo >= 1 && wo <= 4 * (128 - kw + 1) && stride >= 1 && stride <= 4;
+}
+
+}  // namespace
+}  // namespace lvg
+
+extern "C" int64_t lvg_convnd_wgrad_workspace(int dtype, int n, int groups, int cin, int cout, int t, int h, int wd, int kt, int kh, int kw,
+                                              int pad_t, int pad_h, int pad_w)
+{
+    if (!wgrad_in_envelope(dtype, n, groups, t, h, wd, kt, kh, kw, pad_t, pad_h, pad_w, 1)) return -1;
+    const int to = t + 2 * pad_t - kt + 1, ho = h + 2 * pad_h - kh + 1, wo = wd + 2 * pad_w - kw + 1;
+    if (pw_supported(dtype, groups, cin, cout, kt, kh, kw, pad_t, pad_h, pad_w, 1, (int64_t)t * h * wd, 1)) return pw_wgrad_workspace(cin, cout);
+    const WgradPlan q = wgrad_plan(dtype, n, groups, cin, cout, t, h, wd, to, ho, wo, kt, kh, kw);
+    return q.a_bytes + q.b_bytes + q.part_bytes + 1024;
+}
+
+extern "C" int lvg_convnd_wgrad(const void* x, const void* dy, void* dw, int dtype, int n, int groups, int cin, int cout, int t, int h, int wd,
+                                int kt, int kh, int kw, int pad_t, int pad_h, int pad_w, int stride, void* workspace, int64_t workspace_bytes,
+                                void* stream)
+{
+    LVG_REQUIRE(x && dy && dw, "convnd_wgrad: x, dy, dw must not be NULL");
+    if (pw_supported(dtype, groups, cin, cout, kt, kh, kw, pad_t, pad_h, pad_w, stride, (int64_t)t * h * wd, 1)) {
+        LVG_REQUIRE(workspace, "convnd_wgrad: workspace must not be NULL");
+        return pw_wgrad((const float*)x, (const float*)dy, (float*)dw, n, cin, cout, (int64_t)t * h * wd, workspace, workspace_bytes, (cudaStream_t)stream);
+    }
+    if (!wgrad_in_envelope(dtype, n, groups, t, h, wd, kt, kh, kw, pad_t, pad_h, pad_w, stride)) {
+        set_error("convnd_wgrad: outside the tensor-core kernel's envelope");
+        return LVG_UNSUPPORTED;
+    }
+    return run_wgrad(x, dy, dw, dtype, n, groups, cin, cout, t, h, wd, kt, kh, kw, pad_t, pad_h, pad_w, stride, nullptr, workspace, workspace_bytes,
+                     (cudaStream_t)stream);
+}
+
+// the tiling lvg_convnd_wgrad would launch with (host arithmetic only; tests/test_wgrad_emul.py replays it on the CPU, tools print it)
+extern "C" int lvg_convnd_wgrad_plan(int dtype, int n, int groups, int cin, int cout, int t, int h, int wd, int kt, int kh, int kw, int pad_t,
+                                     int pad_h, int pad_w, int* out, int out_len)
+{
+    LVG_REQUIRE(out && out_len >= 32, "convnd_wgrad_plan: out must hold 32 ints");
+    if (!wgrad_in_envelope(dtype, n, groups, t, h, wd, kt, kh, kw, pad_t, pad_h, pad_w, 1)) {
+        set_error("convnd_wgrad_plan: outside the tensor-core kernel's envelope");
+        return LVG_UNSUPPORTED;
+    }
+    const int to = t + 2 * pad_t - kt + 1, ho = h + 2 * pad_h - kh + 1, wo = wd + 2 * pad_w - kw + 1;
+    const WgradPlan q = wgrad_plan(dtype, n, groups, cin, cout, t, h, wd, to, ho, wo, kt, kh, kw);
+    const int v[32] = {q.split, q.cpad_a, q.cpad_b, q.nt, q.ntiles, q.mt, q.nsplit, q.ablk, q.khc, q.nseg, q.ps, q.rh, q.stages, q.a_stage, q.b_stage,
+                       q.stage_bytes, q.tail_bytes, (int)q.smem, q.seg_w[0], q.seg_w[1], q.seg_w[2], q.seg_w[3], q.seg_x0[0], q.seg_x0[1], q.seg_x0[2],
+                       q.seg_x0[3], pw_supported(dtype, groups, cin, cout, kt, kh, kw, pad_t, pad_h, pad_w, 1, (int64_t)t * h * wd, 1) ? 1 : 0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < 32; i++) out[i] = v[i];
+    return LVG_OK;
+}
+
+// ---- both gradients of one convolution call. dy is re-tiled ONCE: the input gradient (forward kernel on dy) and the weight
+// gradient (dy as the M-side operand) read the same channel-block tensor whenever their paddings agree (cout < 128 or a
+// multiple of 128: every layer of the networks); otherwise, and for the streaming 1x1x1 kernels, the two entry points above run
+// one after the other. Workspace layout of the shared case: [dy8][packed weights of the input gradient][x8][partial sums].
+namespace lvg {
+namespace {
+bool backward_shares_dy8(int dtype, int n, int groups, int cin, int cout, int t, int h, int wd, int kt, int kh, int kw, int pad_t, int pad_h,
+                         int pad_w, int stride)
+{
+    const int64_t P = (int64_t)t * h * wd;
+    if (!env_flag("LVG_CONV_SHARED_DY8", 1)) return false;
+    if (pw_supported(dtype, groups, cin, cout, kt, kh, kw, pad_t, pad_h, pad_w, stride, P, 0) ||
+        pw_supported(dtype, groups, cin, cout, kt, kh, kw, pad_t, pad_h, pad_w, stride, P, 1))
+        return false;
+    return wgrad_cpad_a(cout) == round_up(cout, 16);
+}
+}  // namespace
+}  // namespace lvg
+
+extern "C" int64_t lvg_convnd_backward_workspace(int dtype, int n, int groups, int cin, int cout, int t, int h, int wd, int kt, int kh, int kw,
+                                                 int pad_t, int pad_h, int pad_w)
+{
+    const int64_t a = lvg_convnd_workspace(dtype, n, groups, cin, cout, t, h, wd, kt, kh, kw, pad_t, pad_h, pad_w);
+    const int64_t b = lvg_convnd_wgrad_workspace(dtype, n, groups, cin, cout, t, h, wd, kt, kh, kw, pad_t, pad_h, pad_w);
+    if (a < 0 || b < 0) return -1;
+    // (the shared layout never needs more than the two separate ones together)
+    return a + b + 1024;
+}
+
+extern "C" int lvg_convnd_backward(const void* x, const void* dy, const void* w, void* dx, void* dw, int dtype, int n, int groups, int cin, int cout,
+                                   int t, int h, int wd, int kt, int kh, int kw, int pad_t, int pad_h, int pad_w, int stride, void* workspace,
+                                   int64_t workspace_bytes, void* stream)
+{
+    LVG_REQUIRE(x && dy && w && dx && dw, "convnd_backward: x, dy, w, dx, dw must not be NULL");
+    LVG_REQUIRE(workspace && aligned16(workspace), "convnd_backward: workspace must be 16-byte aligned and not NULL");
+    const bool tc_ok = wgrad_in_envelope(dtype, n, groups, t, h, wd, kt, kh, kw, pad_t, pad_h, pad_w, stride) && pad_t <= kt - 1 && pad_h <= kh - 1 &&
+                       pad_w <= kw - 1;
+    if (!tc_ok || !backward_shares_dy8(dtype, n, groups, cin, cout, t, h, wd, kt, kh, kw, pad_t, pad_h, pad_w, stride)) {
+        const int rc = lvg_convnd_dgrad(dy, w, dx, dtype, n, groups, cin, cout, t, h, wd, kt, kh, kw, pad_t, pad_h, pad_w, stride, workspace,
+                                        workspace_bytes, stream);
+        if (rc) return rc;
+        return lvg_convnd_wgrad(x, dy, dw, dtype, n, groups, cin, cout, t, h, wd, kt, kh, kw, pad_t, pad_h, pad_w, stride, workspace, workspace_bytes,
+                                stream);
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    const int split = dtype == LVG_F32 ? 1 : 0;
+    const int taps = kt * kh * kw;
+    const int to = t + 2 * pad_t - kt + 1, ho = h + 2 * pad_h - kh + 1, wo = wd + 2 * pad_w - kw + 1;
+    const int hos = (ho - 1) / stride + 1, wos = (wo - 1) / stride + 1;
+    const int64_t inst = (int64_t)n * groups;
+    const Geometry gd = geometry(split, inst, groups, cout, cin, (int64_t)to * ho * wo, taps);      // the input gradient's operands
+    const int64_t dy8_room = ((gd.act_bytes + 255) / 256) * 256;
+    const int64_t wp_room = ((gd.w_bytes + 255) / 256) * 256 + 256;
+    LVG_REQUIRE(workspace_bytes >= dy8_room + wp_room, "convnd_backward: workspace too small");
+    unsigned char* dy8 = reinterpret_cast<unsigned char*>(workspace);
+    unsigned char* rest = dy8 + dy8_room;
+    int rc = pack_act(dy, dy8, split, inst, cout, gd.cblk, to, hos, wos, ho, wo, stride, s);
+    if (rc) return rc;
+    rc = run_igemm(dy, w, dx, dtype, n, groups, cout, cin, to, ho, wo, kt, kh, kw, kt - 1 - pad_t, kh - 1 - pad_h, kw - 1 - pad_w,
+                   (int64_t)cout * cin * taps, taps, (int64_t)cin * taps, 1, nullptr, 0, 0.f, 1.f, -1.f, hos, wos, stride, 1, dy8, rest, wp_room, s);
+    if (rc) return rc;
+    // (stream order: the weight gradient's re-tiling of x overwrites the packed weights only after the input gradient read them)
+    return run_wgrad(x, dy, dw, dtype, n, groups, cin, cout, t, h, wd, kt, kh, kw, pad_t, pad_h, pad_w, stride, dy8, rest,
+                     workspace_bytes - dy8_room, s);
 }

@@ -69,6 +69,9 @@ _SIGNATURES = {
     'lvg_convnd_dgrad': (_c_int, [_c_void_p] * 3 + [_c_int] * 15 + [_c_void_p, _c_i64, _c_void_p]),
     'lvg_convnd_wgrad_workspace': (_c_i64, [_c_int] * 14),
     'lvg_convnd_wgrad': (_c_int, [_c_void_p] * 3 + [_c_int] * 15 + [_c_void_p, _c_i64, _c_void_p]),
+    'lvg_convnd_wgrad_plan': (_c_int, [_c_int] * 14 + [ctypes.POINTER(_c_int), _c_int]),
+    'lvg_convnd_backward_workspace': (_c_i64, [_c_int] * 14),
+    'lvg_convnd_backward': (_c_int, [_c_void_p] * 5 + [_c_int] * 15 + [_c_void_p, _c_i64, _c_void_p]),
 }
 
 LVG_UNSUPPORTED = -1
@@ -667,6 +670,20 @@ class ConvNdPlugin:
         if rc == LVG_UNSUPPORTED:
             raise RuntimeError('convnd_wgrad: ' + self._lib.lvg_last_error().decode())
         return dw
+
+    def backward(self, x, dy, w, padding, groups, stride=1):
+        """(dx, dw) of y = conv(x, w) in one call: dy is re-tiled once for the input- and the weight-gradient kernels."""
+        x, dy, w = x.contiguous(), dy.contiguous(), w.contiguous()
+        a, sp, k, pad = self._args(tuple(x.shape), tuple(w.shape), padding, groups, x.dtype)
+        dx = torch.empty_like(x)
+        dw = torch.empty_like(w)
+        ws = self._workspace(x.device, self._lib.lvg_convnd_backward_workspace(*a))
+        with _DeviceGuard(x):
+            rc = _check(self._lib.lvg_convnd_backward(_ptr(x), _ptr(dy), _ptr(w), _ptr(dx), _ptr(dw), *a, int(stride), _ptr(ws), ws.numel(),
+                                                      _stream(x)), 'convnd_backward')
+        if rc == LVG_UNSUPPORTED:
+            raise RuntimeError('convnd_backward: ' + self._lib.lvg_last_error().decode())
+        return dx, dw
 
 
 _PLUGIN_CLASSES = {

@@ -45,6 +45,12 @@ def _weights_off():
     return weight_gradients_disabled or conv2d_gradfix.weight_gradients_disabled
 
 
+def _fused_backward_ok(dy):
+    """First-order backward pass asking for both gradients: one call that re-tiles dy once (lvg_convnd_backward). With
+    create_graph=True (the R1 penalty's double backward) the two gradient Functions below are recorded instead."""
+    return not torch.is_grad_enabled() and os.environ.get('LVG_CONV_FUSED_BACKWARD', '1') != '0' and hasattr(_get_plugin(), 'backward')
+
+
 class _ConvNd(torch.autograd.Function):
     """y = conv(x, w); gradients of any order through the two classes below."""
 
@@ -59,9 +65,13 @@ class _ConvNd(torch.autograd.Function):
         x, w = ctx.saved_tensors
         padding, groups, stride = ctx.cfg
         dx = dw = None
+        want_dw = ctx.needs_input_grad[1] and not _weights_off()
+        if ctx.needs_input_grad[0] and want_dw and _fused_backward_ok(dy):
+            dx, dw = _get_plugin().backward(x, dy, w, padding, groups, stride=stride)
+            return dx, dw, None, None, None
         if ctx.needs_input_grad[0]:
             dx = _ConvNdDgrad.apply(dy, w, x.shape, padding, groups, stride)
-        if ctx.needs_input_grad[1] and not _weights_off():
+        if want_dw:
             dw = _ConvNdWgrad.apply(dy, x, w.shape, padding, groups, stride)
         return dx, dw, None, None, None
 
@@ -201,10 +211,14 @@ class _ConvBiasAct(torch.autograd.Function):
         spec = ba.activation_funcs[act]
         dz = ba._plugin.bias_act(dy.contiguous(), None, None, y, None, 1, 1, spec.cuda_idx, alpha, gain, -1.0 if clamp is None else clamp)
         dx = dw = db = None
-        if ctx.needs_input_grad[0]:
-            dx = _ConvNdDgrad.apply(dz, w, x.shape, padding, groups, stride)
-        if ctx.needs_input_grad[1] and not _weights_off():
-            dw = _ConvNdWgrad.apply(dz, x, w.shape, padding, groups, stride)
+        want_dw = ctx.needs_input_grad[1] and not _weights_off()
+        if ctx.needs_input_grad[0] and want_dw and _fused_backward_ok(dz):
+            dx, dw = _get_plugin().backward(x, dz, w, padding, groups, stride=stride)
+        else:
+            if ctx.needs_input_grad[0]:
+                dx = _ConvNdDgrad.apply(dz, w, x.shape, padding, groups, stride)
+            if want_dw:
+                dw = _ConvNdWgrad.apply(dz, x, w.shape, padding, groups, stride)
         if has_b and ctx.needs_input_grad[2]:
             db = dz.float().sum([0] + list(range(2, dz.ndim))).to(dz.dtype)
         return dx, dw, db, None, None, None, None, None, None, None

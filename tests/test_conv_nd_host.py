@@ -13,7 +13,7 @@ class TorchBackedPlugin:
     """convnd_plugin stand-in: same methods, torch arithmetic (float64 CPU). Test-only."""
 
     def __init__(self):
-        self.calls = dict(fprop=0, dgrad=0, wgrad=0)
+        self.calls = dict(fprop=0, dgrad=0, wgrad=0, backward=0)
 
     def supported(self, x, w, stride, padding, dilation, groups):
         return x.ndim in (3, 4, 5) and all(d == 1 for d in dilation)
@@ -46,6 +46,13 @@ class TorchBackedPlugin:
         with torch.enable_grad():
             y = self._f(nd)(x, w, None, self._st(nd, stride), padding, 1, groups)
             return torch.autograd.grad(y, [w], dy)[0]
+
+    def backward(self, x, dy, w, padding, groups, stride=1):
+        self.calls['backward'] += 1
+        n = dict(self.calls)
+        out = self.dgrad(dy, w, tuple(x.shape), padding, groups, stride), self.wgrad(x, dy, tuple(w.shape), padding, groups, stride)
+        self.calls.update(dgrad=n['dgrad'], wgrad=n['wgrad'])
+        return out
 
 
 @pytest.fixture
@@ -126,3 +133,26 @@ def test_calls_outside_the_envelope_use_torch(plug):
     y = conv_nd.conv2d(x, w, padding=2, dilation=2)
     assert torch.allclose(y, F.conv2d(x, w, padding=2, dilation=2)) and plug.calls['fprop'] == n0
     assert torch.allclose(conv_nd.conv2d(x, w, padding='same'), F.conv2d(x, w, padding='same'))
+
+
+@pytest.mark.parametrize('fn,xs,ws,kw', CASES)
+def test_first_order_backward_is_one_fused_call(plug, fn, xs, ws, kw):
+    """Both gradients in a plain backward pass = ONE plugin.backward call (dy re-tiled once); with create_graph=True the two
+    gradient Functions are recorded instead (they must stay differentiable)."""
+    gen = torch.Generator().manual_seed(3)
+    x0, w0 = torch.randn(*xs, generator=gen, dtype=torch.float64), torch.randn(*ws, generator=gen, dtype=torch.float64)
+    x, w = x0.clone().requires_grad_(True), w0.clone().requires_grad_(True)
+    getattr(conv_nd, fn)(x, w, None, **kw).square().sum().backward()
+    assert plug.calls['backward'] == 1 and plug.calls['dgrad'] == 0 and plug.calls['wgrad'] == 0
+    xr, wr = x0.clone().requires_grad_(True), w0.clone().requires_grad_(True)
+    getattr(F, fn)(xr, wr, None, **kw).square().sum().backward()
+    torch.testing.assert_close(x.grad, xr.grad)
+    torch.testing.assert_close(w.grad, wr.grad)
+    # only one gradient wanted -> the single-gradient entry points
+    x2 = x0.clone().requires_grad_(True)
+    getattr(conv_nd, fn)(x2, w0, None, **kw).sum().backward()
+    assert plug.calls['backward'] == 1 and plug.calls['dgrad'] == 1
+    # create_graph -> separate differentiable Functions
+    x3, w3 = x0.clone().requires_grad_(True), w0.clone().requires_grad_(True)
+    gx, gw = torch.autograd.grad(getattr(conv_nd, fn)(x3, w3, None, **kw).square().sum(), [x3, w3], create_graph=True)
+    assert plug.calls['backward'] == 1 and gx.requires_grad and gw.requires_grad

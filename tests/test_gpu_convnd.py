@@ -184,3 +184,78 @@ def test_every_lowres_convolution_signature(plug, c):
     assert float((dx.double() - gx).abs().max()) <= tol * float(gx.abs().max()), 'dgrad'
     dw = plug.wgrad(x, dy, tuple(ws), tuple(pad), 1)
     assert float((dw.double() - gw).abs().max()) <= tol * float(gw.abs().max()), f'wgrad {float((dw.double() - gw).abs().max() / gw.abs().max()):.3e}'
+
+
+# ---- weight gradient with few channels: folded tap rows (one CTA takes all ky) and the compact dy8 operand (cout < 128)
+
+FEWCH = [
+    # name, x shape, w shape, padding -- the low-res discriminator / generator layers at reduced extent, plus ragged ones
+    ('D 32->32 1x3x3 64x64', (2, 32, 3, 64, 64), (32, 32, 1, 3, 3), (0, 1, 1)),
+    ('D 32->64 1x3x3', (1, 32, 4, 40, 64), (64, 32, 1, 3, 3), (0, 1, 1)),
+    ('D 64->64 5x3x3 (two n-tiles of 32)', (1, 64, 7, 32, 32), (64, 64, 5, 3, 3), (2, 1, 1)),
+    ('D 64->128 5x3x3', (1, 64, 6, 16, 32), (128, 64, 5, 3, 3), (2, 1, 1)),
+    ('G 64->64 1x3x3 36x64', (1, 64, 5, 36, 64), (64, 64, 1, 3, 3), (0, 1, 1)),
+    ('48 channels (n-tile 48), odd rows, pitch 8 mod 16', (2, 48, 2, 9, 20), (40, 48, 1, 3, 3), (0, 1, 1)),
+    ('8 -> 16 channels, tiny', (3, 8, 1, 5, 7), (16, 8, 1, 3, 3), (0, 1, 1)),
+    ('3 -> 24 channels 3x3x3', (2, 3, 4, 12, 18), (24, 3, 3, 3, 3), (1, 1, 1)),
+    ('27 channels, two column segments', (1, 27, 1, 6, 150), (72, 27, 1, 3, 3), (0, 2, 2)),
+    ('3x1 kernel (kw 1)', (2, 32, 2, 16, 24), (32, 32, 1, 3, 1), (0, 1, 0)),
+    ('no padding', (2, 16, 3, 14, 30), (20, 16, 3, 3, 3), (0, 0, 0)),
+]
+
+
+def _wgrad_ref(x, dy, ws, pad):
+    wr = torch.zeros(*ws, device=DEV, dtype=torch.float64, requires_grad=True)
+    gw, = torch.autograd.grad(F.conv3d(x.double(), wr, padding=pad), [wr], dy.double())
+    return gw
+
+
+@pytest.mark.parametrize('dtype', [torch.float16, torch.float32], ids=['f16', 'f32split'])
+@pytest.mark.parametrize('name,xs,ws,pad', FEWCH, ids=[c[0] for c in FEWCH])
+def test_convnd_wgrad_few_channels_all_variants(plug, monkeypatch, name, xs, ws, pad, dtype):
+    """Default (folded + compact), each switched off, both off: all four against float64 -- the knobs select different
+    tilings of the same sums, so they also agree with each other to rounding."""
+    x = rnd(xs, 21).to(dtype)
+    ys = tuple(F.conv3d(torch.zeros(1, *xs[1:], device=DEV), torch.zeros(*ws, device=DEV), padding=pad).shape[1:])
+    dy = rnd((xs[0],) + ys, 22).to(dtype)
+    gw = _wgrad_ref(x, dy, ws, pad)
+    tol = 2e-3 if dtype == torch.float16 else 5e-5
+    for fold, compact in ((1, 1), (0, 1), (1, 0), (0, 0)):
+        monkeypatch.setenv('LVG_WGRAD_FOLD', str(fold))
+        monkeypatch.setenv('LVG_WGRAD_COMPACT', str(compact))
+        dw = plug.wgrad(x, dy, ws, pad, 1)
+        err = float((dw.double() - gw).abs().max()) / float(gw.abs().max())
+        assert err <= tol, f'fold={fold} compact={compact}: {err:.3e}'
+
+
+BACKWARD = [
+    ('3d 1x3x3 32->32', (2, 32, 3, 20, 32), (32, 32, 1, 3, 3), (0, 1, 1), 1, 1),
+    ('3d 3x3x3 40->130 (two m-tiles, padded dy8: separate re-tiling)', (1, 40, 4, 6, 8), (130, 40, 3, 3, 3), (1, 1, 1), 1, 1),
+    ('3d 3x3x3 64->128', (1, 64, 3, 9, 16), (128, 64, 3, 3, 3), (1, 1, 1), 1, 1),
+    ('3d 1x1x1 pointwise 64->64 (streaming kernels)', (2, 64, 3, 8, 10), (64, 64, 1, 1, 1), (0, 0, 0), 1, 1),
+    ('3d 1x1x1 256->128 (engine)', (1, 256, 2, 8, 16), (128, 256, 1, 1, 1), (0, 0, 0), 1, 1),
+    ('2d modulated groups 4', (1, 4 * 24, 20, 26), (4 * 40, 24, 3, 3), (1, 1), 4, 1),
+    ('2d stride 2', (2, 32, 35, 42), (48, 32, 3, 3), (0, 0), 1, 2),
+    ('1d k3', (2, 64, 16), (32, 64, 3), (1,), 1, 1),
+]
+
+
+@pytest.mark.parametrize('dtype', [torch.float16, torch.float32], ids=['f16', 'f32split'])
+@pytest.mark.parametrize('name,xs,ws,pad,groups,stride', BACKWARD, ids=[c[0] for c in BACKWARD])
+def test_convnd_backward_one_call_equals_the_two_gradients(plug, name, xs, ws, pad, groups, stride, dtype):
+    """lvg_convnd_backward (dy re-tiled once) returns exactly what lvg_convnd_dgrad + lvg_convnd_wgrad return."""
+    x, w = rnd(xs, 31).to(dtype), rnd(ws, 32, 1.0 / math.sqrt(math.prod(ws[1:]))).to(dtype)
+    y = plug.fprop(x, w, pad, groups, stride=stride)
+    dy = rnd(tuple(y.shape), 33).to(dtype)
+    dx0 = plug.dgrad(dy, w, tuple(x.shape), pad, groups, stride=stride)
+    dw0 = plug.wgrad(x, dy, tuple(w.shape), pad, groups, stride=stride)
+    dx, dw = plug.backward(x, dy, w, pad, groups, stride=stride)
+    assert torch.equal(dx, dx0) and torch.equal(dw, dw0)
+    # and through autograd: a plain backward pass takes the fused call
+    from torch_utils.ops import conv_nd
+    xa, wa = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
+    nd = x.ndim - 2
+    st = stride if nd == 2 else 1
+    ya = (conv_nd.conv1d, conv_nd.conv2d, conv_nd.conv3d)[nd - 1](xa, wa, None, st, pad, 1, groups)
+    ya.backward(dy)
+    assert torch.equal(xa.grad, dx0) and torch.equal(wa.grad, dw0)
