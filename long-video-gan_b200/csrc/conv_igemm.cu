@@ -79,6 +79,8 @@ struct IgemmParams {
     int64_t total_tiles;         // tiles_x * tiles_y * tiles_t * mt * instances
     int ks;                      // k-steps per stage (> 1 only when kt == 1)
     int stages;
+    int a_resident;              // the ring length is a multiple of the stages per tile and every tile of the launch uses the same weights:
+                                 // slot s always holds the same weight images -- they are fetched for the first `stages` iterations only
     int a_stage, b_step, b_bytes, b_box, stage_bytes;    // bytes: A per stage, B stride per k-step / per pair of blocks, TMA payload of a pair, whole stage
     int64_t y_cs;                // output channel stride (= to*hos*wos)
     int ostride, hos, wos;       // output decimation (strided convolution): only rows / columns divisible by ostride are stored
@@ -330,7 +332,7 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) conv_igemm_kernel(const __gr
     const uint32_t tmem_base = tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (elect_one()) {
             int it = 0;
             for (int64_t L = blockIdx.x; L < p.total_tiles; L += gridDim.x) {
                 const TileCoord c = decode_tile(p, L);
@@ -343,10 +345,11 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) conv_igemm_kernel(const __gr
                         unsigned char* st = smem + (size_t)s * p.stage_bytes;
                         const int k0 = kcix * p.ks;
                         const int nks = min(p.ks, p.kc - k0);
-                        const uint32_t a_bytes = (uint32_t)(nks * taps2 * p.nimg * kATile);
+                        const bool load_a = !p.a_resident || it < p.stages;
+                        const uint32_t a_bytes = load_a ? (uint32_t)(nks * taps2 * p.nimg * kATile) : 0u;
                         mbar_expect_tx(&full_bar[s], a_bytes + (uint32_t)(nks * p.nimg * p.b_box));
                         // A: kt == 1 -> the nks steps' tiles are contiguous; kt > 1 -> ks == 1, the taps of this kt are contiguous
-                        bulk_copy_g2s(st, wpg + ((int64_t)k0 * p.kt + kt) * (int64_t)taps2 * (p.nimg * kATile), a_bytes, &full_bar[s]);
+                        if (load_a) bulk_copy_g2s(st, wpg + ((int64_t)k0 * p.kt + kt) * (int64_t)taps2 * (p.nimg * kATile), a_bytes, &full_bar[s]);
                         for (int j = 0; j < nks; j++) {
                             const int kb = (k0 + j) * 2;
                             for (int im = 0; im < p.nimg; im++)
@@ -358,7 +361,7 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) conv_igemm_kernel(const __gr
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        if (elect_one()) {
             // instruction descriptors: D = f32, A and B K-major, fp16 or bf16 operands, N >> 3, M >> 4
             const uint32_t ibase = (1u << 4) | (p.bf16 ? ((1u << 7) | (1u << 10)) : 0u) | ((uint32_t)(kBM >> 4) << 24);
             const int na = p.n0 > 0 ? p.n0 : p.ncols, nb = p.n0 > 0 ? p.ncols - p.n0 : 0;
@@ -378,20 +381,26 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) conv_igemm_kernel(const __gr
                         tc_fence_after();
                         const uint32_t st = smem_u32(smem + (size_t)s * p.stage_bytes);
                         const int nks = min(p.ks, p.kc - kcix * p.ks);
+                        // descriptors as (lo, hi) words, stepped with 32-bit adds on the low word (address >> 4): the next tap's weight
+                        // image(s) + nimg * 4096 bytes, the next tap column + 16 bytes, the next tap row + wtb * 16 bytes
+                        const uint32_t a_hi = desc_hi(128), b_hi = desc_hi(128);
+                        const uint32_t a_tap = (uint32_t)(p.nimg * kATile) >> 4, b_lo_img = (uint32_t)p.b_bytes >> 4, b_nb = (uint32_t)na;
                         for (int j = 0; j < nks; j++) {
-                            const uint32_t a0 = st + (uint32_t)(j * taps2 * p.nimg) * kATile;
-                            const uint32_t b0 = st + (uint32_t)p.a_stage + (uint32_t)j * (uint32_t)p.b_step;
-                            for (int ky = 0; ky < p.kh; ky++) {
-                                for (int kx = 0; kx < p.kw; kx++) {
-                                    const uint32_t at = a0 + (uint32_t)((ky * p.kw + kx) * p.nimg) * kATile;
-                                    const uint32_t bs = b0 + (uint32_t)(ky * p.wtb + kx) * 16;
-                                    // fp16: one product; split: hi*hi, hi*lo, lo*hi (term t: A image t / 2, B image t % 2)
-                                    for (int term = 0; term < (p.nimg == 2 ? 3 : 1); term++) {
-                                        const uint64_t adesc = make_desc(at + (term == 2 ? (uint32_t)kATile : 0u), 2048, 128);
-                                        const uint32_t bt = bs + (term == 1 ? (uint32_t)p.b_bytes : 0u);
-                                        umma_f16(tmem_d, adesc, make_desc(bt, blk_bytes, 128), idesc_a, first ? 0u : 1u);
-                                        if (nb > 0) umma_f16(tmem_d + (uint32_t)na, adesc, make_desc(bt + (uint32_t)na * 16, blk_bytes, 128), idesc_b, first ? 0u : 1u);
-                                        first = false;
+                            uint32_t a_lo = desc_lo(st + (uint32_t)(j * taps2 * p.nimg) * kATile, 2048);
+                            uint32_t b_row = desc_lo(st + (uint32_t)p.a_stage + (uint32_t)j * (uint32_t)p.b_step, blk_bytes);
+                            for (int ky = 0; ky < p.kh; ky++, b_row += (uint32_t)p.wtb) {
+                                uint32_t b_lo = b_row;
+                                for (int kx = 0; kx < p.kw; kx++, b_lo++, a_lo += a_tap) {
+                                    // fp16: one product; split: hi*hi, hi*lo, lo*hi (A image hi, hi, lo; B image hi, lo, hi)
+                                    const uint32_t acc = first ? 0u : 1u;
+                                    umma_f16_w(tmem_d, a_lo, a_hi, b_lo, b_hi, idesc_a, acc);
+                                    if (nb > 0) umma_f16_w(tmem_d + (uint32_t)na, a_lo, a_hi, b_lo + b_nb, b_hi, idesc_b, acc);
+                                    first = false;
+                                    if (p.nimg == 2) {
+                                        umma_f16_w(tmem_d, a_lo, a_hi, b_lo + b_lo_img, b_hi, idesc_a, 1u);
+                                        if (nb > 0) umma_f16_w(tmem_d + (uint32_t)na, a_lo, a_hi, b_lo + b_lo_img + b_nb, b_hi, idesc_b, 1u);
+                                        umma_f16_w(tmem_d, a_lo + (kATile >> 4), a_hi, b_lo, b_hi, idesc_a, 1u);
+                                        if (nb > 0) umma_f16_w(tmem_d + (uint32_t)na, a_lo + (kATile >> 4), a_hi, b_lo + b_nb, b_hi, idesc_b, 1u);
                                     }
                                 }
                             }
@@ -524,6 +533,12 @@ int encode_map(CUtensorMap* tm, void* base, int w, int h, int t, int64_t blocks,
 
 inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
 
+inline int env_flag(const char* name, int dflt)
+{
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+
 struct Geometry {
     int cpad, cblk, nblk, nimg, kc, mt;
     int64_t act_bytes, w_bytes;
@@ -640,6 +655,19 @@ int run_igemm(const void* x, const void* w, void* y, int dtype, int n, int group
     p.nbuf = p.ncols <= 256 ? 2 : 1;
     p.n0 = p.ncols <= 256 ? 0 : round_up(p.ncols / 2, 16);
     p.stages = stages_for(smem_budget);
+    // Short K loops (few input channels, 1x1 / 1x3x3 kernels): when the ring can be cut to a multiple of the stages one tile
+    // takes, slot s sees the same (kt, k-chunk) on every tile -- with one weight set for the whole launch (no groups, one
+    // m-tile) the weight images stay where the first pass put them and only the activation tiles stream (the weight images
+    // of a 32-channel 3x3 layer are 72 KB per k-step against 21 KB of activations: the re-fetch per 256-pixel tile was the
+    // L2 -> SM traffic of these layers).
+    {
+        const int period = kt * ((g.kc + p.ks - 1) / p.ks);
+        p.a_resident = 0;
+        if (groups == 1 && g.mt == 1 && period <= p.stages && env_flag("LVG_CONV_RESIDENT_W", 1)) {
+            p.stages = p.stages / period * period;
+            p.a_resident = 1;
+        }
+    }
     p.y_cs = (int64_t)p.to * p.hos * p.wos;
     p.total_tiles = (int64_t)p.tiles_x * p.tiles_y * p.tiles_t * g.mt * inst;
 
@@ -794,6 +822,7 @@ struct WgradV2Params {
     int nsplit;
     int a_bytes, b_bytes, stage_bytes, stages;      // per stage: one A (B) operand image; a stage holds split+1 of each
     int64_t split_stride;        // elements between fp32 partials
+    int mrows;                   // M of the MMA: 128, or 64 (cout <= 64): accumulator row 16 j + i then sits in TMEM lane 32 j + i
     int tail_bytes;              // shared memory behind the stage ring that the MMAs may read (kx-shifted last rows; the 128 - 8 * ablk rows without data)
 };
 
@@ -843,7 +872,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_v2_kernel(const __grid
     const uint32_t tmem_d = tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (elect_one()) {
             for (int s = s0; s < s1; s++) {
                 const int it = s - s0, slot = it % p.stages;
                 if (it >= p.stages) mbar_wait(&empty_bar[slot], (uint32_t)((it / p.stages - 1) & 1));
@@ -864,10 +893,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_v2_kernel(const __grid
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        if (elect_one()) {
             // instruction descriptor: D = f32, A and B MN-major (bits 15, 16), N >> 3, M >> 4
             const uint32_t idesc = (1u << 4) | (p.bf16 ? ((1u << 7) | (1u << 10)) : 0u) | (1u << 15) | (1u << 16) | ((uint32_t)(NT >> 3) << 17) |
-                                   ((uint32_t)(kBM >> 4) << 24);
+                                   ((uint32_t)(p.mrows >> 4) << 24);
             bool first = true;
             for (int s = s0; s < s1; s++) {
                 const int it = s - s0, slot = it % p.stages;
@@ -882,17 +911,21 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_v2_kernel(const __grid
                 tc_fence_after();
                 const uint32_t a0 = smem_u32(smem + (size_t)slot * p.stage_bytes);
                 const uint32_t b0 = a0 + (uint32_t)(nop * p.a_bytes);
+                // descriptors as (lo, hi) words: a K step is +16 on the low word (256 bytes >> 4), a tap column +1, a tap row
+                // + ky_step >> 4 -- the loop below is all this thread does, and its instruction count per MMA bounds the kernel
+                const uint32_t a_hi = desc_hi(blk_a), b_hi = desc_hi(blk_b);
+                const uint32_t ky16 = ky_step >> 4;
                 for (int term = 0; term < (p.split ? 3 : 1); term++) {
-                    const uint32_t at = a0 + (term == 1 ? (uint32_t)p.a_bytes : 0u);     // hi*hi, lo*hi, hi*lo
-                    const uint32_t bt = b0 + (term == 2 ? (uint32_t)p.b_bytes : 0u);
-                    for (int k = 0; k < ksteps; k++) {
-                        const uint64_t adesc = make_desc(at + (uint32_t)k * 256, 128, blk_a);
-                        for (int kyi = 0; kyi < p.khc; kyi++) {
-                            for (int kx = 0; kx < p.kw; kx++) {
-                                const uint64_t bdesc = make_desc(bt + (uint32_t)k * 256 + (uint32_t)kyi * ky_step + (uint32_t)kx * 16, 128, blk_b);
-                                umma_f16(tmem_d + (uint32_t)((kyi * p.kw + kx) * NT), adesc, bdesc, idesc, (first && k == 0) ? 0u : 1u);
-                            }
+                    uint32_t a_lo = desc_lo(a0 + (term == 1 ? (uint32_t)p.a_bytes : 0u), 128);     // hi*hi, lo*hi, hi*lo
+                    uint32_t b_lo = desc_lo(b0 + (term == 2 ? (uint32_t)p.b_bytes : 0u), 128);
+                    uint32_t acc = first ? 0u : 1u;
+                    for (int k = 0; k < ksteps; k++, a_lo += 16, b_lo += 16) {
+                        uint32_t b_row = b_lo, tcol = tmem_d;
+                        for (int kyi = 0; kyi < p.khc; kyi++, b_row += ky16) {
+                            uint32_t b_tap = b_row;
+                            for (int kx = 0; kx < p.kw; kx++, b_tap++, tcol += (uint32_t)NT) umma_f16_w(tcol, a_lo, a_hi, b_tap, b_hi, idesc, acc);
                         }
+                        acc = 1u;
                     }
                     first = false;
                 }
@@ -918,19 +951,23 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_v2_kernel(const __grid
             const int tap0 = (kt * p.kh + ky0 + kyi) * p.kw;
             if (warp >= 2) {
                 const int q = warp % 4;
-                const int r = q * 32 + lane;
+                const bool m64 = p.mrows == 64;
+                const int r = m64 ? q * 16 + (lane & 15) : q * 32 + lane;        // accumulator row held by this lane (M = 64: lanes 16-31 hold none)
+                const bool holds = !m64 || lane < 16;
                 for (int kx = 0; kx < p.kw; kx++) {
                     uint32_t acc[32];
                     tmem_ld32(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)((kyi * p.kw + kx) * NT + c0), acc);
+                    if (holds) {
 #pragma unroll
-                    for (int j = 0; j < 32; j++) tile[r * row_pitch + j * p.kw + kx] = any ? __uint_as_float(acc[j]) : 0.f;
+                        for (int j = 0; j < 32; j++) tile[r * row_pitch + j * p.kw + kx] = any ? __uint_as_float(acc[j]) : 0.f;
+                    }
                 }
             }
             __syncthreads();
             const int ci_n = min(32, min(NT - c0, p.cin - ci0 - c0));
             const int per_row = ci_n * p.kw;
             if (per_row > 0) {
-                for (int r = warp; r < kBM; r += kThreads / 32) {
+                for (int r = warp; r < p.mrows; r += kThreads / 32) {
                     const int co = co0 + r;
                     if (co >= p.cout) break;
                     const int64_t base = (((int64_t)g * p.cout + co) * p.cin + ci0 + c0) * taps + tap0;
@@ -968,18 +1005,12 @@ __global__ void __launch_bounds__(256) conv_wgrad_reduce_kernel(const float* __r
 
 struct WgradPlan {
     int split, cpad_a, cpad_b, nt, ntiles, mt, nsplit;
-    int ablk, khc;
+    int ablk, khc, mrows;
     int nseg, seg_w[4], seg_x0[4], ps, rh, stages;
     int a_stage, b_stage, stage_bytes, tail_bytes;
     size_t smem;
     int64_t a_bytes, b_bytes, part_bytes, dw_elems;
 };
-
-inline int env_flag(const char* name, int dflt)
-{
-    const char* e = getenv(name);
-    return e ? atoi(e) : dflt;
-}
 
 // channel padding of the dy8 operand of the weight gradient. cout < 128: only the channel blocks that exist (the same
 // tensor the input gradient reads, so one re-tiling pass serves both; the remaining rows of the 128-row MMA read whatever
@@ -992,12 +1023,18 @@ WgradPlan wgrad_plan(int dtype, int n, int groups, int cin, int cout, int t, int
     q.split = dtype == LVG_F32;
     q.cpad_a = wgrad_cpad_a(cout);
     q.ablk = q.cpad_a < kBM ? q.cpad_a / 8 : 16;
+    // M of the MMA. This kernel's MN-major MMAs are paced by their shared-memory operand reads (~64 clocks for 128 dy rows +
+    // N / 2 for the x columns, measured); with at most 64 output channels M = 64 halves the dy part. Accumulator rows
+    // 16 j .. 16 j + 15 then sit in TMEM lanes 32 j .. 32 j + 15 (probed on B200: tools/probe_m64.py).
+    q.mrows = (q.cpad_a <= 64 && env_flag("LVG_WGRAD_M64", 1)) ? 64 : kBM;
     q.cpad_b = round_up(cin, 16);
-    // Few input channels (<= 64): ONE CTA takes all kh tap rows -- the x tile carries kh - 1 halo rows and a tap row is a
+    // Few input channels (<= 32): ONE CTA takes all kh tap rows -- the x tile carries kh - 1 halo rows and a tap row is a
     // start-address shift of one tile row, like kx is a shift of one pixel -- so dy and x are fetched once per (kt, n-tile)
-    // instead of once per (kt, ky): these layers (32-64 channels at 64x64 ... 36x64) are bound by the L2 -> SM operand
-    // traffic, not by the tensor pipe. The kh * kw accumulators of NT columns each must fit the 512 TMEM columns.
-    q.khc = (kh > 1 && cin <= 64 && env_flag("LVG_WGRAD_FOLD", 1)) ? kh : 1;
+    // instead of once per (kt, ky). The kh * kw accumulators of NT columns each must fit the 512 TMEM columns, so NT <= 48:
+    // measured (B200, profiles/r02_lres_conv_table.txt), an MN-major MMA of this kernel costs ~(64 + N / 2) clocks whatever
+    // the issue rate -- 32 input channels: 2.56 vs 3.07 ms folded (same MMA count, a third of the operand traffic); 64 input
+    // channels would need two n-tiles of 32 = twice the MMAs: 6.5 vs 4.2 ms, hence the limit (LVG_WGRAD_FOLD_CIN).
+    q.khc = (kh > 1 && cin <= env_flag("LVG_WGRAD_FOLD_CIN", 32) && env_flag("LVG_WGRAD_FOLD", 1)) ? kh : 1;
     int nt_cap = (512 / (q.khc * kw)) / 16 * 16;
     if (nt_cap > 256) nt_cap = 256;
     if (q.split && nt_cap > 128) nt_cap = 128;
@@ -1029,13 +1066,13 @@ WgradPlan wgrad_plan(int dtype, int n, int groups, int cin, int cout, int t, int
     q.rh = 1;
     while (q.rh < ho && q.rh < 255 - q.khc && stage_of(q.rh + 1, q.nt) <= 80 * 1024) q.rh++;
     if (q.ps % 16 != 0) q.rh = q.rh >= 2 ? q.rh / 2 * 2 : 2;   // even row count (rows past the image are zero-filled)
-    // behind the ring: the kx-shifted reads of the last block (32 bytes) and, with fewer than 16 dy blocks, the rows of the
-    // 128-row MMA beyond them (read from the lo image's start: (nop - 1) * a_stage + 16 blocks). Two stages + tail must fit.
+    // behind the ring: the kx-shifted reads of the last block (32 bytes) and, with fewer dy blocks than the MMA has rows / 8,
+    // the rows beyond them (read from the lo image's start: (nop - 1) * a_stage + mrows / 8 blocks). Two stages + tail must fit.
     for (;;) {
         q.a_stage = q.ablk * q.rh * q.ps * 16;
         q.b_stage = (q.nt / 8) * (q.rh + q.khc - 1) * q.ps * 16;
         q.stage_bytes = round_up(nop * (q.a_stage + q.b_stage), 128);
-        const int over = (nop - 1) * q.a_stage + 16 * q.rh * q.ps * 16 - q.stage_bytes;
+        const int over = (nop - 1) * q.a_stage + (q.mrows / 8) * q.rh * q.ps * 16 - q.stage_bytes;
         q.tail_bytes = round_up(256 + (over > 0 ? over : 0), 128);
         const int step = q.ps % 16 != 0 ? 2 : 1;
         if (2 * q.stage_bytes + q.tail_bytes <= 220 * 1024 || q.rh <= step) break;
@@ -1107,6 +1144,7 @@ int run_wgrad(const void* x, const void* dy, void* dw, int dtype, int n, int gro
     p.nseg = q.nseg;
     for (int j = 0; j < 4; j++) { p.seg_w[j] = q.seg_w[j]; p.seg_x0[j] = q.seg_x0[j]; p.ps[j] = q.ps; }
     p.rh = q.rh; p.khc = q.khc; p.ablk = q.ablk;
+    p.mrows = q.mrows;
     p.a_bytes = q.a_stage; p.b_bytes = q.b_stage; p.stage_bytes = q.stage_bytes; p.stages = q.stages; p.tail_bytes = q.tail_bytes;
     const size_t smem = q.smem;
     LVG_REQUIRE(smem <= 227 * 1024, "convnd_wgrad: stage does not fit shared memory (%zu bytes)", smem);
@@ -1191,7 +1229,7 @@ extern "C" int lvg_convnd_wgrad_plan(int dtype, int n, int groups, int cin, int 
     const WgradPlan q = wgrad_plan(dtype, n, groups, cin, cout, t, h, wd, to, ho, wo, kt, kh, kw);
     const int v[32] = {q.split, q.cpad_a, q.cpad_b, q.nt, q.ntiles, q.mt, q.nsplit, q.ablk, q.khc, q.nseg, q.ps, q.rh, q.stages, q.a_stage, q.b_stage,
                        q.stage_bytes, q.tail_bytes, (int)q.smem, q.seg_w[0], q.seg_w[1], q.seg_w[2], q.seg_w[3], q.seg_x0[0], q.seg_x0[1], q.seg_x0[2],
-                       q.seg_x0[3], pw_supported(dtype, groups, cin, cout, kt, kh, kw, pad_t, pad_h, pad_w, 1, (int64_t)t * h * wd, 1) ? 1 : 0, 0, 0, 0, 0, 0};
+                       q.seg_x0[3], pw_supported(dtype, groups, cin, cout, kt, kh, kw, pad_t, pad_h, pad_w, 1, (int64_t)t * h * wd, 1) ? 1 : 0, q.mrows, 0, 0, 0, 0};
     for (int i = 0; i < 32; i++) out[i] = v[i];
     return LVG_OK;
 }

@@ -7,6 +7,21 @@ namespace tc {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// one lane of a converged warp (elect.sync): unlike `lane == 0` the compiler knows a single thread is active behind this
+// predicate and issues tcgen05.mma / TMA instructions straight, without wrapping each in an election loop
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n"
+        " .reg .pred p;\n"
+        " elect.sync _|p, 0xffffffff;\n"
+        " selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
 {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -77,6 +92,26 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
         " setp.ne.b32 p, %4, 0;\n"
         " tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
         "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// The same descriptor as two 32-bit words, so that the issuing thread steps through K / taps with ONE 32-bit add on the
+// low word (start address >> 4 in bits 0-13; shared-memory addresses stay below 256 KB, so the sum never carries into the
+// leading-offset field at bit 16) instead of rebuilding the 64-bit value. The MMA issue loop is a single thread: with small
+// N its instruction count per MMA, not the tensor pipe, sets the pace.
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo_bytes) { return ((saddr >> 4) & 0x3fffu) | (((lbo_bytes >> 4) & 0x3fffu) << 16); }
+__device__ __forceinline__ uint32_t desc_hi(uint32_t sbo_bytes) { return ((sbo_bytes >> 4) & 0x3fffu) | (1u << 14); }
+__device__ __forceinline__ void umma_f16_w(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                           uint32_t accumulate)
+{
+    asm volatile(
+        "{\n"
+        " .reg .pred p;\n"
+        " .reg .b64 da, db;\n"
+        " mov.b64 da, {%1, %2};\n"
+        " mov.b64 db, {%3, %4};\n"
+        " setp.ne.b32 p, %6, 0;\n"
+        " tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n"
+        "}\n" ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
         : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar)

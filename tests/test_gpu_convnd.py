@@ -220,12 +220,14 @@ def test_convnd_wgrad_few_channels_all_variants(plug, monkeypatch, name, xs, ws,
     dy = rnd((xs[0],) + ys, 22).to(dtype)
     gw = _wgrad_ref(x, dy, ws, pad)
     tol = 2e-3 if dtype == torch.float16 else 5e-5
-    for fold, compact in ((1, 1), (0, 1), (1, 0), (0, 0)):
+    monkeypatch.setenv('LVG_WGRAD_FOLD_CIN', '64')        # fold wherever the accumulators fit (default: up to 32 input channels)
+    for fold, compact, m64 in ((1, 1, 1), (0, 1, 1), (1, 1, 0), (0, 1, 0), (1, 0, 0), (0, 0, 0)):
         monkeypatch.setenv('LVG_WGRAD_FOLD', str(fold))
         monkeypatch.setenv('LVG_WGRAD_COMPACT', str(compact))
+        monkeypatch.setenv('LVG_WGRAD_M64', str(m64))          # 64-row MMAs where cout <= 64
         dw = plug.wgrad(x, dy, ws, pad, 1)
         err = float((dw.double() - gw).abs().max()) / float(gw.abs().max())
-        assert err <= tol, f'fold={fold} compact={compact}: {err:.3e}'
+        assert err <= tol, f'fold={fold} compact={compact} m64={m64}: {err:.3e}'
 
 
 BACKWARD = [
@@ -259,3 +261,30 @@ def test_convnd_backward_one_call_equals_the_two_gradients(plug, name, xs, ws, p
     ya = (conv_nd.conv1d, conv_nd.conv2d, conv_nd.conv3d)[nd - 1](xa, wa, None, st, pad, 1, groups)
     ya.backward(dy)
     assert torch.equal(xa.grad, dx0) and torch.equal(wa.grad, dw0)
+
+
+RESIDENT = [
+    ('3d 1x3x3 32->32 (two k-steps = two slots)', (2, 32, 3, 40, 64), (32, 32, 1, 3, 3), (0, 1, 1)),
+    ('3d 1x1x1 128->128 (k-chunks of four steps)', (1, 128, 4, 18, 32), (128, 128, 1, 1, 1), (0, 0, 0)),
+    ('3d 1x3x3 16->24 (one slot period)', (1, 16, 3, 20, 24), (24, 16, 1, 3, 3), (0, 1, 1)),
+    ('3d 3x3x3 16->16 (kt stages)', (1, 16, 5, 12, 16), (16, 16, 3, 3, 3), (1, 1, 1)),
+    ('2d 3x3 64->64', (4, 64, 33, 40), (64, 64, 3, 3), (1, 1)),
+]
+
+
+@pytest.mark.parametrize('dtype', [torch.float16, torch.float32], ids=['f16', 'f32split'])
+@pytest.mark.parametrize('name,xs,ws,pad', RESIDENT, ids=[c[0] for c in RESIDENT])
+def test_convnd_resident_weight_slots_change_nothing(plug, monkeypatch, name, xs, ws, pad, dtype):
+    """Short K loops keep the weight images in their ring slots across tiles (LVG_CONV_RESIDENT_W, default on): same bits as
+    re-fetching them per tile, and right against float64."""
+    x, w = rnd(xs, 41).to(dtype), rnd(ws, 42, 1.0 / math.sqrt(math.prod(ws[1:]))).to(dtype)
+    yr = conv_ref(x.double(), w.double(), pad, 1)
+    out = {}
+    for flag in ('1', '0'):
+        monkeypatch.setenv('LVG_CONV_RESIDENT_W', flag)
+        y = plug.fprop(x, w, pad, 1)
+        dx = plug.dgrad(y, w, tuple(x.shape), pad, 1)
+        out[flag] = (y, dx)
+    tol = 2e-3 if dtype == torch.float16 else 5e-5
+    assert float((out['1'][0].double() - yr).abs().max()) <= tol * float(yr.abs().max())
+    assert torch.equal(out['1'][0], out['0'][0]) and torch.equal(out['1'][1], out['0'][1])

@@ -32,6 +32,7 @@ def plan(dtype_code, n, groups, cin, cout, t, h, w, kt, kh, kw, pt, ph, pw):
     q['seg_w'] = [int(out[18 + j]) for j in range(4)]
     q['seg_x0'] = [int(out[22 + j]) for j in range(4)]
     q['pointwise'] = int(out[26])
+    q['mrows'] = int(out[27])
     return q
 
 
@@ -93,7 +94,8 @@ def emulate(x, dy, cin, cout, groups, k3, pad3, q, garbage):
             for nti in range(q['ntiles']):
                 for ktap in range(kt):
                     for ky0 in ([0] if khc > 1 else range(kh)):
-                        D = np.zeros((khc * kw, 128, NT))
+                        MR = q['mrows']                                                    # rows of the MMA (64 when cout <= 64)
+                        D = np.zeros((khc * kw, MR, NT))
                         for sp in range(q['nsplit']):
                             s0, s1 = total * sp // q['nsplit'], total * (sp + 1) // q['nsplit']
                             for it, s in enumerate(range(s0, s1)):
@@ -116,15 +118,15 @@ def emulate(x, dy, cin, cout, groups, k3, pad3, q, garbage):
                                 rows = min(rh, Ho - oy0)
                                 ksteps = -(-(rows * ps) // 16)
                                 # the lo images of the split (one image further) are read with the same offsets
-                                assert base + (nop - 1) * a_px + 15 * blk_a + 16 * ksteps <= smem_px, 'lo dy image: rows read past the allocation'
+                                assert base + (nop - 1) * a_px + (MR // 8 - 1) * blk_a + 16 * ksteps <= smem_px, 'lo dy image: rows read past the allocation'
                                 assert b_off + (nop - 1) * b_px + (NT // 8 - 1) * blk_b + 16 * ksteps + (khc - 1) * ps + kw - 1 <= smem_px, \
                                     'lo x image read past the allocation'
                                 for k in range(ksteps):
-                                    # A operand: row m, K index j -> smem[(m / 8) * blk_a + 16 k + j][m % 8]  (all 128 rows are read)
-                                    ia = base + (np.arange(128) // 8)[:, None] * blk_a + 16 * k + np.arange(16)[None, :]
+                                    # A operand: row m, K index j -> smem[(m / 8) * blk_a + 16 k + j][m % 8]  (all MR rows are read)
+                                    ia = base + (np.arange(MR) // 8)[:, None] * blk_a + 16 * k + np.arange(16)[None, :]
                                     max_read = max(max_read, int(ia.max()))
                                     assert ia.max() < smem_px, 'A rows read past the shared-memory allocation'
-                                    Am = smem[ia, (np.arange(128) % 8)[:, None]]             # [128][16]
+                                    Am = smem[ia, (np.arange(MR) % 8)[:, None]]              # [MR][16]
                                     for kyi in range(khc):
                                         for kx in range(kw):
                                             ib = b_off + (np.arange(NT) // 8)[:, None] * blk_b + 16 * k + np.arange(16)[None, :] + kyi * ps + kx
@@ -133,7 +135,7 @@ def emulate(x, dy, cin, cout, groups, k3, pad3, q, garbage):
                                             D[kyi * kw + kx] += Am @ Bm.T
                         for kyi in range(khc):
                             for kx in range(kw):
-                                for co in range(min(128, cout - mti * 128)):
+                                for co in range(min(MR, cout - mti * 128)):
                                     for c in range(min(NT, cin - nti * NT)):
                                         dw[g * cout + mti * 128 + co, nti * NT + c, ktap, ky0 + kyi, kx] = D[kyi * kw + kx, co, c]
     return dw, max_read
@@ -160,6 +162,7 @@ CASES = [
 @pytest.mark.parametrize('case', CASES, ids=[f'{c[2]}->{c[3]} k{c[5]} {c[4]}' for c in CASES])
 def test_wgrad_kernel_addressing_replayed_on_cpu(case, dtype_code, monkeypatch):
     n, groups, cin, cout, (T, H, W), k3, pad3 = case
+    monkeypatch.setenv('LVG_WGRAD_FOLD_CIN', '64')        # fold wherever the accumulators fit (default: up to 32 input channels)
     for fold, compact in ((1, 1), (0, 1), (1, 0), (0, 0)):
         monkeypatch.setenv('LVG_WGRAD_FOLD', str(fold))
         monkeypatch.setenv('LVG_WGRAD_COMPACT', str(compact))
@@ -168,6 +171,7 @@ def test_wgrad_kernel_addressing_replayed_on_cpu(case, dtype_code, monkeypatch):
             continue
         assert q['khc'] == (k3[1] if (fold and k3[1] > 1 and cin <= 64) else 1)
         assert q['ablk'] == (-(-cout // 16) * 2 if (compact and cout < 128) else 16)
+        assert q['mrows'] == (64 if (compact and cout <= 64) else 128)
         g = torch.Generator().manual_seed(5)
         x = torch.randn(n, groups * cin, T, H, W, generator=g, dtype=torch.float64)
         w = torch.zeros(groups * cout, cin, *k3, dtype=torch.float64, requires_grad=True)
@@ -198,5 +202,5 @@ def test_wgrad_plans_of_the_lowres_networks_fit_the_hardware(monkeypatch):
         seen += 1
         assert q['smem'] <= 227 * 1024 and q['stages'] >= 2, (c, q)
         assert q['khc'] * ws[4] * q['nt'] <= 512 and q['rh'] + q['khc'] - 1 <= 256 and q['ps'] <= 128, (c, q)
-        assert q['khc'] == (ws[3] if ws[3] > 1 and ws[1] <= 64 else 1), (c, q)
+        assert q['khc'] == (ws[3] if ws[3] > 1 and ws[1] <= 32 else 1), (c, q)
     assert seen >= 10
