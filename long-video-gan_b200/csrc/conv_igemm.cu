@@ -385,25 +385,30 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) conv_igemm_kernel(const __gr
                         // image(s) + nimg * 4096 bytes, the next tap column + 16 bytes, the next tap row + wtb * 16 bytes
                         const uint32_t a_hi = desc_hi(128), b_hi = desc_hi(128);
                         const uint32_t a_tap = (uint32_t)(p.nimg * kATile) >> 4, b_lo_img = (uint32_t)p.b_bytes >> 4, b_nb = (uint32_t)na;
+                        // wide tiles (two MMAs per tap, columns [0, na) and [na, ncols)): all taps of one half, then the other --
+                        // consecutive MMAs keep accumulating into the same tensor-memory columns (switching them costs ~60 clocks)
                         for (int j = 0; j < nks; j++) {
-                            uint32_t a_lo = desc_lo(st + (uint32_t)(j * taps2 * p.nimg) * kATile, 2048);
-                            uint32_t b_row = desc_lo(st + (uint32_t)p.a_stage + (uint32_t)j * (uint32_t)p.b_step, blk_bytes);
-                            for (int ky = 0; ky < p.kh; ky++, b_row += (uint32_t)p.wtb) {
-                                uint32_t b_lo = b_row;
-                                for (int kx = 0; kx < p.kw; kx++, b_lo++, a_lo += a_tap) {
-                                    // fp16: one product; split: hi*hi, hi*lo, lo*hi (A image hi, hi, lo; B image hi, lo, hi)
-                                    const uint32_t acc = first ? 0u : 1u;
-                                    umma_f16_w(tmem_d, a_lo, a_hi, b_lo, b_hi, idesc_a, acc);
-                                    if (nb > 0) umma_f16_w(tmem_d + (uint32_t)na, a_lo, a_hi, b_lo + b_nb, b_hi, idesc_b, acc);
-                                    first = false;
-                                    if (p.nimg == 2) {
-                                        umma_f16_w(tmem_d, a_lo, a_hi, b_lo + b_lo_img, b_hi, idesc_a, 1u);
-                                        if (nb > 0) umma_f16_w(tmem_d + (uint32_t)na, a_lo, a_hi, b_lo + b_lo_img + b_nb, b_hi, idesc_b, 1u);
-                                        umma_f16_w(tmem_d, a_lo + (kATile >> 4), a_hi, b_lo, b_hi, idesc_a, 1u);
-                                        if (nb > 0) umma_f16_w(tmem_d + (uint32_t)na, a_lo + (kATile >> 4), a_hi, b_lo + b_nb, b_hi, idesc_b, 1u);
+                            const uint32_t a_base = desc_lo(st + (uint32_t)(j * taps2 * p.nimg) * kATile, 2048);
+                            const uint32_t b_base = desc_lo(st + (uint32_t)p.a_stage + (uint32_t)j * (uint32_t)p.b_step, blk_bytes);
+                            for (int half = 0; half < (nb > 0 ? 2 : 1); half++) {
+                                const uint32_t tm = tmem_d + (half ? (uint32_t)na : 0u);
+                                const uint32_t id = half ? idesc_b : idesc_a;
+                                uint32_t a_lo = a_base, b_row = b_base + (half ? b_nb : 0u);
+                                uint32_t acc = first ? 0u : 1u;
+                                for (int ky = 0; ky < p.kh; ky++, b_row += (uint32_t)p.wtb) {
+                                    uint32_t b_lo = b_row;
+                                    for (int kx = 0; kx < p.kw; kx++, b_lo++, a_lo += a_tap) {
+                                        // fp16: one product; split: hi*hi, hi*lo, lo*hi (A image hi, hi, lo; B image hi, lo, hi)
+                                        umma_f16_w(tm, a_lo, a_hi, b_lo, b_hi, id, acc);
+                                        acc = 1u;
+                                        if (p.nimg == 2) {
+                                            umma_f16_w(tm, a_lo, a_hi, b_lo + b_lo_img, b_hi, id, 1u);
+                                            umma_f16_w(tm, a_lo + (kATile >> 4), a_hi, b_lo, b_hi, id, 1u);
+                                        }
                                     }
                                 }
                             }
+                            first = false;
                         }
                         umma_commit(&empty_bar[s]);
                     }
@@ -822,6 +827,7 @@ struct WgradV2Params {
     int nsplit;
     int a_bytes, b_bytes, stage_bytes, stages;      // per stage: one A (B) operand image; a stage holds split+1 of each
     int64_t split_stride;        // elements between fp32 partials
+    int tap_major;               // MMA order inside a stage: tap outermost, K steps innermost (else K step outermost, taps innermost)
     int mrows;                   // M of the MMA: 128, or 64 (cout <= 64): accumulator row 16 j + i then sits in TMEM lane 32 j + i
     int tail_bytes;              // shared memory behind the stage ring that the MMAs may read (kx-shifted last rows; the 128 - 8 * ablk rows without data)
 };
@@ -915,19 +921,35 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_v2_kernel(const __grid
                 // + ky_step >> 4 -- the loop below is all this thread does, and its instruction count per MMA bounds the kernel
                 const uint32_t a_hi = desc_hi(blk_a), b_hi = desc_hi(blk_b);
                 const uint32_t ky16 = ky_step >> 4;
-                for (int term = 0; term < (p.split ? 3 : 1); term++) {
-                    uint32_t a_lo = desc_lo(a0 + (term == 1 ? (uint32_t)p.a_bytes : 0u), 128);     // hi*hi, lo*hi, hi*lo
-                    uint32_t b_lo = desc_lo(b0 + (term == 2 ? (uint32_t)p.b_bytes : 0u), 128);
-                    uint32_t acc = first ? 0u : 1u;
-                    for (int k = 0; k < ksteps; k++, a_lo += 16, b_lo += 16) {
-                        uint32_t b_row = b_lo, tcol = tmem_d;
-                        for (int kyi = 0; kyi < p.khc; kyi++, b_row += ky16) {
-                            uint32_t b_tap = b_row;
-                            for (int kx = 0; kx < p.kw; kx++, b_tap++, tcol += (uint32_t)NT) umma_f16_w(tcol, a_lo, a_hi, b_tap, b_hi, idesc, acc);
+                if (p.tap_major) {
+                    // K steps innermost: consecutive MMAs accumulate into the SAME tensor-memory columns (one tap's accumulator)
+                    uint32_t tcol = tmem_d;
+                    for (int kyi = 0; kyi < p.khc; kyi++) {
+                        for (int kx = 0; kx < p.kw; kx++, tcol += (uint32_t)NT) {
+                            uint32_t acc = first ? 0u : 1u;
+                            for (int term = 0; term < (p.split ? 3 : 1); term++) {
+                                uint32_t a_lo = desc_lo(a0 + (term == 1 ? (uint32_t)p.a_bytes : 0u), 128);     // hi*hi, lo*hi, hi*lo
+                                uint32_t b_lo = desc_lo(b0 + (term == 2 ? (uint32_t)p.b_bytes : 0u), 128) + (uint32_t)kyi * ky16 + (uint32_t)kx;
+                                for (int k = 0; k < ksteps; k++, a_lo += 16, b_lo += 16) { umma_f16_w(tcol, a_lo, a_hi, b_lo, b_hi, idesc, acc); acc = 1u; }
+                            }
                         }
-                        acc = 1u;
                     }
                     first = false;
+                } else {
+                    for (int term = 0; term < (p.split ? 3 : 1); term++) {
+                        uint32_t a_lo = desc_lo(a0 + (term == 1 ? (uint32_t)p.a_bytes : 0u), 128);     // hi*hi, lo*hi, hi*lo
+                        uint32_t b_lo = desc_lo(b0 + (term == 2 ? (uint32_t)p.b_bytes : 0u), 128);
+                        uint32_t acc = first ? 0u : 1u;
+                        for (int k = 0; k < ksteps; k++, a_lo += 16, b_lo += 16) {
+                            uint32_t b_row = b_lo, tcol = tmem_d;
+                            for (int kyi = 0; kyi < p.khc; kyi++, b_row += ky16) {
+                                uint32_t b_tap = b_row;
+                                for (int kx = 0; kx < p.kw; kx++, b_tap++, tcol += (uint32_t)NT) umma_f16_w(tcol, a_lo, a_hi, b_tap, b_hi, idesc, acc);
+                            }
+                            acc = 1u;
+                        }
+                        first = false;
+                    }
                 }
                 umma_commit(&empty_bar[slot]);
             }
@@ -1145,6 +1167,14 @@ int run_wgrad(const void* x, const void* dy, void* dw, int dtype, int n, int gro
     for (int j = 0; j < 4; j++) { p.seg_w[j] = q.seg_w[j]; p.seg_x0[j] = q.seg_x0[j]; p.ps[j] = q.ps; }
     p.rh = q.rh; p.khc = q.khc; p.ablk = q.ablk;
     p.mrows = q.mrows;
+    // MMA order inside a stage. Switching the accumulator (another tap's TMEM columns) between two MMAs costs ~60 clocks on
+    // B200 whatever M and N are (measured: the 32 -> 32 layer of the low-res discriminator 2.63 -> 1.66 ms with the K steps
+    // innermost); with a single K step per stage there is nothing to keep together and the K-outermost order pipelines better
+    // (512 channels at 3x4 pixels: 0.36 vs 0.46 ms).
+    {
+        const int e = env_flag("LVG_WGRAD_TAP_MAJOR", -1);
+        p.tap_major = e >= 0 ? e : (q.rh * q.ps / 16 >= 2 ? 1 : 0);
+    }
     p.a_bytes = q.a_stage; p.b_bytes = q.b_stage; p.stage_bytes = q.stage_bytes; p.stages = q.stages; p.tail_bytes = q.tail_bytes;
     const size_t smem = q.smem;
     LVG_REQUIRE(smem <= 227 * 1024, "convnd_wgrad: stage does not fit shared memory (%zu bytes)", smem);
