@@ -217,9 +217,18 @@ bool pw_enabled()
 // 0.44 vs 0.58 ms); the weight-gradient kernel (shared-memory bound: 8 LDS.128 per 32 packed FMAs and row pitches that
 // collide in the banks) wins only for a handful of channel pairs (3->32: 0.59 vs 1.24 ms, 64->3: 0.68 vs 1.13 ms) and
 // loses from 32->64 on (2.7 vs 1.4 ms).
+// The weight gradient takes this path only on request (LVG_POINTWISE_WGRAD=1): since the engine's weight gradient keeps its K
+// steps together per accumulator it is the faster one even for 3 -> 32 and 64 -> 3 channels (0.40 vs 0.60 ms, 0.47 vs 0.71 ms on
+// B200, tools/lres_conv_table.py with LVG_POINTWISE=0); forward / input gradient stay here (0.15 vs 0.67 ms at 3 -> 32).
+bool pw_wgrad_enabled()
+{
+    const char* e = getenv("LVG_POINTWISE_WGRAD");      // read per call: tests switch it
+    return e && e[0] == '1';
+}
+
 bool pw_supported(int dtype, int groups, int cin, int cout, int kt, int kh, int kw, int pad_t, int pad_h, int pad_w, int stride, int64_t P, int wgrad)
 {
-    return pw_enabled() && dtype == LVG_F32 && groups == 1 && kt == 1 && kh == 1 && kw == 1 && pad_t == 0 && pad_h == 0 && pad_w == 0 && stride == 1 &&
+    return pw_enabled() && (!wgrad || pw_wgrad_enabled()) && dtype == LVG_F32 && groups == 1 && kt == 1 && kh == 1 && kw == 1 && pad_t == 0 && pad_h == 0 && pad_w == 0 && stride == 1 &&
            cin >= 1 && cout >= 1 && cin <= 128 && cout <= 128 && cin * cout <= (wgrad ? 512 : 4096) && P % 4 == 0 && P >= 4;
 }
 
