@@ -1051,7 +1051,7 @@ WgradPlan wgrad_plan(int dtype, int n, int groups, int cin, int cout, int t, int
     q.ablk = q.cpad_a < kBM ? q.cpad_a / 8 : 16;
     // M of the MMA. This kernel's MN-major MMAs are paced by their shared-memory operand reads (~64 clocks for 128 dy rows +
     // N / 2 for the x columns, measured); with at most 64 output channels M = 64 halves the dy part. Accumulator rows
-    // 16 j .. 16 j + 15 then sit in TMEM lanes 32 j .. 32 j + 15 (probed on B200: tools/probe_m64.py).
+    // 16 j .. 16 j + 15 then sit in TMEM lanes 32 j .. 32 j + 15 (probed on B200: profiles/r02_probe_m64_tmem_lanes.txt).
     q.mrows = (q.cpad_a <= 64 && env_flag("LVG_WGRAD_M64", 1)) ? 64 : kBM;
     q.cpad_b = round_up(cin, 16);
     // Few input channels (<= 32): ONE CTA takes all kh tap rows -- the x tile carries kh - 1 halo rows and a tap row is a
