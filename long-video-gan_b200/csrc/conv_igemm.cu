@@ -611,11 +611,13 @@ int run_igemm(const void* x, const void* w, void* y, int dtype, int n, int group
     if (p.ks > g.kc) p.ks = g.kc;
     p.a_stage = p.ks * taps2 * g.nimg * kATile;
     // the column budget shrinks until two stages fit shared memory (split precision doubles both operands of a stage)
-    // (default 256 columns since the MMA issue path costs 4 instructions per MMA: two alternating accumulators -- the epilogue
-    // of tile i under the main loop of tile i + 1 -- beat the better weight-tile amortisation of 512-column tiles on every
-    // layer class of a low-res step, 72.7 -> 69.8 ms forward, 55.6 -> 54.2 ms input gradients; the small-frame layers also
-    // get more tiles than SMs: 512 channels at 3x4 pixels 0.30 -> 0.22 ms. LVG_CONV_COLS=512 restores the wide tiles.)
-    for (int col_budget = cb_env ? atoi(cb_env) : 256;; col_budget -= 64) {
+    // (fp32 / split precision: 256 columns whatever the K loop, since the MMA issue path costs 4 instructions per MMA: two
+    // alternating accumulators -- the epilogue of tile i under the main loop of tile i + 1 -- beat the better weight-tile
+    // amortisation of 512-column tiles on every layer class of a low-res step, 72.7 -> 69.8 ms forward, 55.6 -> 54.2 ms input
+    // gradients; the small-frame layers also get more tiles than SMs: 512 channels at 3x4 pixels 0.30 -> 0.22 ms. fp16 layers
+    // (one product per tap against the same weight bytes per tap: the weight tile weighs 1.5x more) keep 512 columns for long
+    // K loops, the configuration their super-res numbers were measured with. LVG_CONV_COLS overrides both.)
+    for (int col_budget = cb_env ? atoi(cb_env) : ((split || g.kc * kt * taps2 <= 160) ? 256 : 512);; col_budget -= 64) {
         LVG_REQUIRE(col_budget >= 64, "convnd: no tile fits shared memory");
         const int max_wt = 128 - (kw - 1);                    // a TMA box row is at most 256 8-byte elements
         p.tiles_x = (p.wo + max_wt - 1) / max_wt;
