@@ -248,6 +248,16 @@ int lvg_convnd_wgrad(const void* x, const void* dy, void* dw, int dtype, int n, 
                      int t, int h, int wd, int kt, int kh, int kw, int pad_t, int pad_h, int pad_w, int stride,
                      void* workspace, int64_t workspace_bytes, void* stream);
 /*
+ * Introspection: the tiling lvg_convnd_fprop (mode 0) / lvg_convnd_dgrad (mode 1) launches with, as 48 ints -- wgroups, cout
+ * (rows of the GEMM), mt, kc, nblk, nimg, lo_blk, to, ho, wo, kt, kh, kw, pad_t, pad_h, pad_w, tt, th, wt, wtb, thb, frame_px,
+ * ncols, n0, epi_warps, nbuf, tiles_x, tiles_y, tiles_t, total_tiles, ks, stages, a_resident, a_stage, b_step, b_bytes, b_box,
+ * stage_bytes, ostride, hos, wos, 0..., [47] = 1 when the call takes the streaming 1x1x1 kernels instead -- host arithmetic only
+ * (no device needed): tests/test_igemm_emul.py replays the kernel's addressing with it on the CPU. The argument list describes
+ * the FORWARD convolution in both modes.
+ */
+int lvg_convnd_plan(int mode, int dtype, int n, int groups, int cin, int cout, int t, int h, int wd, int kt, int kh, int kw,
+                    int pad_t, int pad_h, int pad_w, int stride, int* out, int out_len);
+/*
  * Introspection: the tiling lvg_convnd_wgrad launches with, as 32 ints -- split, cpad_a, cpad_b, nt, ntiles, mt, nsplit,
  * ablk, khc, nseg, ps, rh, stages, a_stage, b_stage, stage_bytes, tail_bytes, smem, seg_w[4], seg_x0[4], pointwise, mrows, 0... --
  * host arithmetic only (no device needed): tests/test_wgrad_emul.py replays the kernel's addressing with it on the CPU.

@@ -567,6 +567,9 @@ Geometry geometry(int split, int64_t inst, int groups, int ck, int cm, int64_t t
 // shared driver of fprop and dgrad: `x` has `ck` channels per group, `y` gets `cm`; logical A[m][k][tap] = w[g*gs + m*sm + k*sk + tap']
 // `dil` > 1: x is given as an xin_h x xin_w image that is placed on every dil-th pixel of the h x wd grid (input gradient of
 // a strided convolution); `ostride` > 1: only every ostride-th output row / column is stored (strided forward convolution).
+// lvg_convnd_plan: run_igemm stops after its tile selection (pure host arithmetic, no CUDA call) and hands the parameters out
+thread_local IgemmParams* g_plan_only = nullptr;
+
 int run_igemm(const void* x, const void* w, void* y, int dtype, int n, int groups, int ck, int cm, int t, int h, int wd, int kt, int kh,
               int kw, int pad_t, int pad_h, int pad_w, int64_t w_gs, int64_t w_sm, int64_t w_sk, int flip, const float* bias, int act,
               float alpha, float gain, float clamp, int xin_h, int xin_w, int dil, int ostride, const unsigned char* x8_pre, void* workspace,
@@ -579,11 +582,12 @@ int run_igemm(const void* x, const void* w, void* y, int dtype, int n, int group
     const int64_t inst = (int64_t)n * groups;
     const int64_t thw = (int64_t)t * h * wd;
     const Geometry g = geometry(split, inst, groups, ck, cm, thw, taps);
-    LVG_REQUIRE(workspace && workspace_bytes >= (x8_pre ? 0 : g.act_bytes) + g.w_bytes + 256, "convnd: workspace too small");
-    LVG_REQUIRE(aligned16(workspace), "convnd: workspace must be 16-byte aligned");
+    const bool plan_only = g_plan_only != nullptr;
+    LVG_REQUIRE(plan_only || (workspace && workspace_bytes >= (x8_pre ? 0 : g.act_bytes) + g.w_bytes + 256), "convnd: workspace too small");
+    LVG_REQUIRE(plan_only || aligned16(workspace), "convnd: workspace must be 16-byte aligned");
     LVG_REQUIRE(inst * g.nblk < (1ll << 31), "convnd: too many channel blocks for a tensor map");
-    EncodeTiledFn enc = encode_fn();
-    LVG_REQUIRE(enc != nullptr, "convnd: cuTensorMapEncodeTiled is not available from this driver");
+    EncodeTiledFn enc = plan_only ? nullptr : encode_fn();
+    LVG_REQUIRE(plan_only || enc != nullptr, "convnd: cuTensorMapEncodeTiled is not available from this driver");
 
     unsigned char* wp = reinterpret_cast<unsigned char*>(workspace);
     unsigned char* x8 = x8_pre ? const_cast<unsigned char*>(x8_pre) : wp + ((g.w_bytes + 127) / 128) * 128;
@@ -681,6 +685,8 @@ int run_igemm(const void* x, const void* w, void* y, int dtype, int n, int group
     }
     p.y_cs = (int64_t)p.to * p.hos * p.wos;
     p.total_tiles = (int64_t)p.tiles_x * p.tiles_y * p.tiles_t * g.mt * inst;
+
+    if (plan_only) { *g_plan_only = p; return LVG_OK; }
 
     // re-tile the operands
     {
@@ -1250,6 +1256,47 @@ extern "C" int lvg_convnd_wgrad(const void* x, const void* dy, void* dw, int dty
     }
     return run_wgrad(x, dy, dw, dtype, n, groups, cin, cout, t, h, wd, kt, kh, kw, pad_t, pad_h, pad_w, stride, nullptr, workspace, workspace_bytes,
                      (cudaStream_t)stream);
+}
+
+// the tiling lvg_convnd_fprop (mode 0) / lvg_convnd_dgrad (mode 1) would launch with, as ints (host arithmetic only;
+// tests/test_igemm_emul.py replays the forward kernel's addressing with it on the CPU)
+extern "C" int lvg_convnd_plan(int mode, int dtype, int n, int groups, int cin, int cout, int t, int h, int wd, int kt, int kh, int kw, int pad_t,
+                               int pad_h, int pad_w, int stride, int* out, int out_len)
+{
+    LVG_REQUIRE(out && out_len >= 48, "convnd_plan: out must hold 48 ints");
+    LVG_REQUIRE(mode == 0 || mode == 1, "convnd_plan: mode 0 (forward) or 1 (input gradient)");
+    const int taps = kt * kh * kw;
+    if (!nd_supported(dtype, kt, kh, kw) || n < 1 || groups < 1 || pad_t < 0 || pad_h < 0 || pad_w < 0 || stride < 1 || stride > 4 ||
+        (mode == 1 && (pad_t > kt - 1 || pad_h > kh - 1 || pad_w > kw - 1))) {
+        set_error("convnd_plan: outside the tensor-core kernel's envelope");
+        return LVG_UNSUPPORTED;
+    }
+    for (int i = 0; i < out_len; i++) out[i] = 0;
+    if (pw_supported(dtype, groups, cin, cout, kt, kh, kw, pad_t, pad_h, pad_w, stride, (int64_t)t * h * wd, 0)) { out[47] = 1; return LVG_OK; }
+    IgemmParams p;
+    memset(&p, 0, sizeof(p));
+    void* dummy = reinterpret_cast<void*>(256);          // never dereferenced in plan-only mode
+    g_plan_only = &p;
+    int rc;
+    if (mode == 0) {
+        rc = run_igemm(dummy, dummy, dummy, dtype, n, groups, cin, cout, t, h, wd, kt, kh, kw, pad_t, pad_h, pad_w, (int64_t)cout * cin * taps,
+                       (int64_t)cin * taps, taps, 0, nullptr, 0, 0.f, 1.f, -1.f, h, wd, 1, stride, nullptr, nullptr, 0, nullptr);
+    } else {
+        const int to = t + 2 * pad_t - kt + 1, ho = h + 2 * pad_h - kh + 1, wo = wd + 2 * pad_w - kw + 1;
+        if (to < 1 || ho < 1 || wo < 1) { g_plan_only = nullptr; set_error("convnd_plan: empty output"); return LVG_UNSUPPORTED; }
+        const int hos = (ho - 1) / stride + 1, wos = (wo - 1) / stride + 1;
+        rc = run_igemm(dummy, dummy, dummy, dtype, n, groups, cout, cin, to, ho, wo, kt, kh, kw, kt - 1 - pad_t, kh - 1 - pad_h, kw - 1 - pad_w,
+                       (int64_t)cout * cin * taps, taps, (int64_t)cin * taps, 1, nullptr, 0, 0.f, 1.f, -1.f, hos, wos, stride, 1, nullptr, nullptr, 0,
+                       nullptr);
+    }
+    g_plan_only = nullptr;
+    if (rc) return rc;
+    const int v[48] = {p.wgroups, p.cout, p.mt, p.kc, p.nblk, p.nimg, p.lo_blk, p.to, p.ho, p.wo, p.kt, p.kh, p.kw, p.pad_t, p.pad_h, p.pad_w,
+                       p.tt, p.th, p.wt, p.wtb, p.thb, p.frame_px, p.ncols, p.n0, p.epi_warps, p.nbuf, p.tiles_x, p.tiles_y, p.tiles_t,
+                       (int)p.total_tiles, p.ks, p.stages, p.a_resident, p.a_stage, p.b_step, p.b_bytes, p.b_box, p.stage_bytes, p.ostride, p.hos, p.wos,
+                       0, 0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < 48; i++) out[i] = v[i];
+    return LVG_OK;
 }
 
 // the tiling lvg_convnd_wgrad would launch with (host arithmetic only; tests/test_wgrad_emul.py replays it on the CPU, tools print it)
